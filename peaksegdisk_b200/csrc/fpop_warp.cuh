@@ -1,0 +1,901 @@
+// fpop_warp.cuh -- the PeakSegFPOP dynamic program as warp-cooperative device code (sm_100a).
+//
+// One warp owns one problem (one bedGraph x one penalty).  The two cost functions of the
+// up-down-constrained optimal-partitioning DP are piecewise Poisson-loss functions of the
+// log-mean; each is a structure-of-arrays piece list in shared memory (global memory for the
+// overflow tier), one lane per piece.  Per bedGraph row the warp runs
+//     up_t   = rescale( min_env( min_less(down_{t-1}) + penalty/W_{t-1}, up_{t-1} ) )
+//     down_t = rescale( min_env( min_more(up_{t-1}),                     down_{t-1} ) )
+// and appends the breakpoints/back-pointers of both functions to the HBM cost-function store.
+//
+// Reference behaviour being reproduced (file:line into tdhock/PeakSegDisk):
+//   piece algebra, Newton roots     src/funPieceListLog.cpp:29-234
+//   set_to_min_less_of              src/funPieceListLog.cpp:236-437   -> min_less_op
+//   set_to_min_more_of              src/funPieceListLog.cpp:439-616   -> min_more_op
+//   set_to_min_env_of / push_min_pieces / push_piece
+//                                   src/funPieceListLog.cpp:832-1285  -> min_env_op (+ pair_rule)
+//   add / multiply / set_prev_seg_end  :618-641  -> fused into the operators' output writes
+//   Minimize / findMean             :689-712 / :643-653  -> best_piece / backtrack_problem
+//   DP loop, decode                 src/PeakSegFPOPLog.cpp:258-442  -> dp_problem / backtrack_problem
+//   per-row store                   src/PeakSegFPOPLog.cpp:12-141   -> StoreWriter (HBM chunk arena)
+// Every floating-point expression keeps the reference's operand order and rounding (build with
+// -fmad=false); exp/log are psd_math.h, bit-identical to the libm the reference links.
+//
+// How the sequential operators map onto a warp:
+//   * min_less / min_more: lanes evaluate everything that depends on one piece only (end costs,
+//     argmin, argmin cost); the left-to-right (right-to-left) state machine then advances by
+//     ballots: "first piece that starts a flat stretch", then "first piece that ends it", the
+//     Newton solves of the second question running speculatively in all candidate lanes.
+//   * min_env: the overlap intervals of the two breakpoint lists are enumerated with a per-lane
+//     binary search + warp scan (a merge path), one lane then owns one interval and applies the
+//     crossing rule (0/1/2 roots) independently; the resulting candidate pieces are compacted with
+//     a scan and adjacent equal pieces are merged by a run-head pass that reproduces push_piece.
+//
+// This header is compiled by nvcc for the product and, unmodified, by g++ against
+// tests/emu/warp_emu.h (PSD_EMU) where 32 fibers stand in for the lanes -- a test tool only.
+#pragma once
+#include "psd_math.h"
+
+#if defined(PSD_EMU)
+#include "warp_emu.h"
+#else
+#define PSD_DEV __device__ __forceinline__
+#define PSD_DEVNI __device__ __noinline__
+PSD_DEV int psd_lane() { return (int)(threadIdx.x & 31u); }
+PSD_DEV double psd_shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+PSD_DEV int psd_shfl_i(int v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+PSD_DEV unsigned long long psd_shfl_u64(unsigned long long v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+PSD_DEV double psd_shfl_up_d(double v, int d) { return __shfl_up_sync(0xffffffffu, v, d); }
+PSD_DEV double psd_shfl_down_d(double v, int d) { return __shfl_down_sync(0xffffffffu, v, d); }
+PSD_DEV int psd_shfl_up_i(int v, int d) { return __shfl_up_sync(0xffffffffu, v, d); }
+PSD_DEV double psd_shfl_xor_d(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+PSD_DEV int psd_shfl_xor_i(int v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+PSD_DEV unsigned psd_ballot(int p) { return __ballot_sync(0xffffffffu, p); }
+PSD_DEV void psd_syncwarp() { __syncwarp(); }
+PSD_DEV int psd_ffs(unsigned m) { return __ffs((int)m); }
+PSD_DEV int psd_clz(unsigned m) { return __clz((int)m); }
+PSD_DEV int psd_popc(unsigned m) { return __popc(m); }
+PSD_DEV unsigned long long psd_atomic_add_ull(unsigned long long* p, unsigned long long v) { return atomicAdd(p, v); }
+PSD_DEV int psd_atomic_add_int(int* p, int v) { return atomicAdd(p, v); }
+// the cost-function store is written once and read (sparsely) once: evict-first streaming stores
+PSD_DEV void psd_st_cs_d2(double* p, double x, double y) { __stcs((double2*)p, make_double2(x, y)); }
+PSD_DEV void psd_st_cs_i(int* p, int v) { __stcs(p, v); }
+PSD_DEV void psd_st_cs_u64(unsigned long long* p, unsigned long long v) { __stcs(p, v); }
+PSD_DEV void psd_st_cs_u4(unsigned* p, unsigned a, unsigned b, unsigned c, unsigned d) { __stcs((uint4*)p, make_uint4(a, b, c, d)); }
+#endif
+
+#define PSD_EPS 1e-12        /* NEWTON_EPSILON, src/funPieceListLog.cpp:9 */
+#define PSD_MAX_STEPS 100    /* NEWTON_STEPS,   src/funPieceListLog.cpp:10 */
+
+// status words a warp can raise for its problem (0 = ok)
+#define PSD_ST_OK 0
+#define PSD_ST_PIECE_OVERFLOW 101   /* a piece list outgrew the current tier's capacity */
+#define PSD_ST_STORE_EXHAUSTED 102  /* the HBM cost-function store ran out of chunks */
+#define PSD_ST_BACKTRACK_LOST 103   /* backtrack found no piece containing the mean */
+#define PSD_ST_INTERNAL 104         /* a "should never happen" branch of the reference was reached */
+
+// ---- piece list: structure of arrays behind one base pointer --------------------------------------
+// doubles [0,cap): a (coef of e^x)  [cap,2cap): b (coef of x)  [2cap,3cap): c (constant)
+//         [3cap,4cap): hi (right end of the piece, log-mean)   [4cap,5cap): back_x (prev_log_mean)
+// ints at byte offset 40*cap: back_i (data_i).  The left end of piece k is hi[k-1] (domain min for k=0).
+struct PList { double* base; int n; };
+#define PL_A(L, i) ((L).base[(i)])
+#define PL_B(L, i) ((L).base[cap + (i)])
+#define PL_C(L, i) ((L).base[2 * cap + (i)])
+#define PL_X(L, i) ((L).base[3 * cap + (i)])
+#define PL_P(L, i) ((L).base[4 * cap + (i)])
+#define PL_I(L, i) (((int*)((L).base + 5 * cap))[(i)])
+#define PSD_LIST_BYTES(cap) ((size_t)(cap) * 44)
+
+struct WarpCtx {
+  const uint64_t* etab;   // exp table (shared memory)
+  const uint64_t* ltab;   // log table (shared memory)
+  int cap;                // capacity (pieces) of every list buffer in the current tier
+  int* ivl;               // scratch: overlap intervals, (i_f | i_g << 16), capacity 2*cap
+  double* cand_x;         // scratch: candidate right ends, capacity ccap
+  int* cand_s;            // scratch: candidate source (bit 30 = from g) | piece index
+  int ccap;
+  int overflow;           // lane-local: set when a write fell outside a capacity
+  int internal;           // lane-local: an impossible branch was taken
+};
+
+// rescale applied while writing an operator's output:  ((v * mul) + add) * inv  per coefficient,
+// i.e. multiply(W_{t-1}); add(w, -z*w, 0); multiply(1/W_t)   (src/PeakSegFPOPLog.cpp:316-321)
+struct Rescale { double mul, add_a, add_b, inv; };
+
+PSD_DEV double pc_cost(double a, double b, double c, double x, const WarpCtx& cx) {
+  const double et = (x == -PSD_INF) ? 0.0 : a * psd_exp(x, cx.etab);
+  const double lt = (b == 0) ? 0.0 : b * x;
+  return et + lt + c;
+}
+// same, when e^x is already known
+PSD_DEV double pc_cost_e(double a, double b, double c, double x, double ex) {
+  const double et = (x == -PSD_INF) ? 0.0 : a * ex;
+  const double lt = (b == 0) ? 0.0 : b * x;
+  return et + lt + c;
+}
+// loss in mean space given log(m) (PoissonLoss, :52-61)
+PSD_DEV double pc_cost_m(double a, double b, double c, double m, double logm) {
+  const double base = a * m + c;
+  if (b == 0) return base;
+  const double prod = logm * b;
+  return base + prod;
+}
+PSD_DEV double pc_abs(double v) { return v < 0 ? -v : v; }
+
+// get_smaller_root (:129-190): Newton in log space from argmin-1.
+// x0 = argmin, c0 = cost(x0), cl = cost(lo) are passed in (the reference recomputes the same values).
+PSD_DEVNI double root_left(double a, double b, double c, double lo, double level,
+                           double x0, double c0, double cl, const uint64_t* etab) {
+  if ((level < cl && cl < c0) || (level > cl && cl > c0)) return lo - 1;
+  double x = x0 - 1;
+  double f, pos_f = PSD_INF, pos_x = PSD_INF, neg_f = -PSD_INF, neg_x = PSD_INF;
+  if (c0 < 0) { neg_f = c0; neg_x = x0; } else { pos_f = c0; pos_x = x0; }
+  int step = 0;
+  do {
+    const double et = (x == -PSD_INF) ? 0.0 : a * psd_exp(x, etab);
+    f = (et + b * x + c) - level;
+    if (0 < f && f < pos_f) { pos_f = f; pos_x = x; }
+    if (neg_f < f && f < 0) { neg_f = f; neg_x = x; }
+    if (PSD_MAX_STEPS <= ++step) {
+      const double mid = (pos_x + neg_x) / 2;
+      const double em = (mid == -PSD_INF) ? 0.0 : a * psd_exp(mid, etab);
+      const double fm = (em + b * mid + c) - level;
+      return (pc_abs(fm) < pc_abs(f)) ? mid : x;
+    }
+    const double d = et + b;
+    const double off = f / d;
+    x = x - off;
+  } while (PSD_EPS < pc_abs(f));
+  return x;
+}
+
+// get_larger_root (:69-127): Newton in mean space from argmin_mean+1; returns log(root).
+// m0 = argmin_mean, c0 = PoissonLoss(m0), cr = cost(hi) are passed in.
+PSD_DEVNI double root_right(double a, double b, double c, double hi, double level,
+                            double m0, double c0, double cr, const uint64_t* ltab) {
+  if ((c0 < cr && cr < level) || (c0 > cr && cr > level)) return hi + 1;
+  double m = m0 + 1;
+  double f, pos_f = PSD_INF, pos_m = PSD_INF, neg_f = -PSD_INF, neg_m = PSD_INF;
+  if (c0 < 0) { neg_f = c0; neg_m = m0; } else { pos_f = c0; pos_m = m0; }
+  int step = 0;
+  do {
+    f = ((a * m + c) + psd_log(m, ltab) * b) - level;
+    if (0 < f && f < pos_f) { pos_f = f; pos_m = m; }
+    if (neg_f < f && f < 0) { neg_f = f; neg_m = m; }
+    if (PSD_MAX_STEPS <= ++step) {
+      const double mid = (pos_m + neg_m) / 2;
+      const double fm = ((a * mid + c) + psd_log(mid, ltab) * b) - level;
+      return (pc_abs(fm) < pc_abs(f)) ? psd_log(mid, ltab) : psd_log(m, ltab);
+    }
+    const double d = a + b / m;
+    m = m - f / d;
+  } while (PSD_EPS < pc_abs(f));
+  return psd_log(m, ltab);
+}
+
+// has_two_roots (:29-50) from the precomputed optimum costs (log-space c1, mean-space c2)
+PSD_DEV bool two_roots(double a, double c1, double c2, double level) {
+  if (0 < a) return c1 + PSD_EPS < level && c2 + PSD_EPS < level;
+  return level + PSD_EPS < c1 && level + PSD_EPS < c2;
+}
+
+PSD_DEV bool same_coefs(double a1, double b1, double c1, double a2, double b2, double c2) {  // sameFuns :862-868
+  return a1 == a2 && b1 == b2 && pc_abs(c1 - c2) < PSD_EPS;
+}
+
+PSD_DEV void pl_emit(WarpCtx& cx, PList& out, int k, double a, double b, double c, double hi, double bx, int bi) {
+  const int cap = cx.cap;
+  if (k < cap) {
+    PL_A(out, k) = a; PL_B(out, k) = b; PL_C(out, k) = c; PL_X(out, k) = hi; PL_P(out, k) = bx; PL_I(out, k) = bi;
+  } else {
+    cx.overflow = 1;
+  }
+}
+
+// ---- set_to_min_less_of, then set_prev_seg_end(stamp) and add(0,0,cshift) --------------------------
+PSD_DEV void min_less_op(WarpCtx& cx, const PList in, PList& out, double dmin, int stamp, double cshift) {
+  const int lane = psd_lane();
+  const int cap = cx.cap;
+  const int n = in.n;
+  double level = PSD_INF;    // cost of the pending flat piece; +inf while following the input
+  double left_edge = dmin;   // where the next output piece starts
+  double arg_at = PSD_INF;   // where the flat piece's minimum is attained
+  int out_n = 0;
+  for (int base = 0; base < n; base += 32) {
+    const int i = base + lane;
+    const bool valid = i < n;
+    const int end = (n - base < 32) ? n : base + 32;
+    double a = 0, b = 0, c = 0, hi = 0, lo = 0;
+    double cl = 0, cr = 0, m = 0, mu = 0, cmu = 0, c2 = 0;
+    if (valid) {
+      a = PL_A(in, i); b = PL_B(in, i); c = PL_C(in, i); hi = PL_X(in, i);
+      lo = (i == 0) ? dmin : PL_X(in, i - 1);
+      cl = pc_cost(a, b, c, lo, cx);
+      cr = pc_cost(a, b, c, hi, cx);
+      if (b != 0) {
+        m = -b / a;
+        mu = psd_log(m, cx.ltab);
+        cmu = pc_cost(a, b, c, mu, cx);
+        c2 = pc_cost_m(a, b, c, m, mu);
+      }
+    }
+    // cost of the next piece at its left end
+    double nl = psd_shfl_down_d(cl, 1);
+    const bool has_next = i + 1 < n;
+    if (lane == 31 && has_next) nl = pc_cost(PL_A(in, i + 1), PL_B(in, i + 1), PL_C(in, i + 1), hi, cx);
+    // what this piece does when reached while following the input:
+    // 0 = copied whole, 1 = a flat stretch starts at its left end, 2 = its minimum is interior
+    int kind = 0;
+    if (valid) {
+      if (b == 0) {
+        const bool flat = (cr - cl) < PSD_EPS;
+        const bool next_above = !has_next || PSD_EPS < nl - cl;
+        kind = (next_above && !flat) ? 1 : 0;
+      } else {
+        const bool next_ok = !has_next || PSD_EPS < nl - cmu;
+        const bool ok = PSD_EPS < cr - cmu && next_ok;
+        kind = (mu <= lo && ok) ? 1 : ((mu < hi && ok) ? 2 : 0);
+      }
+    }
+    int pos = base;
+    while (pos < end) {
+      if (level == PSD_INF) {
+        const unsigned mask = psd_ballot(valid && i >= pos && kind != 0);
+        const int first = mask ? base + psd_ffs(mask) - 1 : end;
+        if (valid && i >= pos && i < first) pl_emit(cx, out, out_n + (i - pos), a + 0.0, b + 0.0, c + cshift, hi, PSD_INF, stamp);
+        const int src = (first < end) ? first - base : 0;
+        const int kf = psd_shfl_i(kind, src);
+        const double lo_f = psd_shfl_d(lo, src), cl_f = psd_shfl_d(cl, src);
+        const double mu_f = psd_shfl_d(mu, src), cmu_f = psd_shfl_d(cmu, src);
+        const double hi_last = psd_shfl_d(hi, end - 1 - base);
+        if (first > pos) left_edge = (first < end) ? lo_f : hi_last;
+        out_n += first - pos;
+        if (first >= end) { pos = end; break; }
+        if (kf == 1) { level = cl_f; arg_at = lo_f; }
+        else {
+          if (left_edge < mu_f) {
+            if (lane == src) pl_emit(cx, out, out_n, a + 0.0, b + 0.0, c + cshift, mu_f, PSD_INF, stamp);
+            out_n++;
+          }
+          left_edge = mu_f; arg_at = mu_f; level = cmu_f;
+        }
+        pos = first + 1;
+      } else {
+        int flag = 0;
+        double r = 0;
+        if (valid && i >= pos) {
+          if (b == 0) { if (a < 0) flag = 3; }   // the reference throws here ("should never happen")
+          else {
+            if (two_roots(a, cmu, c2, level)) {
+              r = root_left(a, b, c, lo, level, mu, cmu, cl, cx.etab);
+              if (lo < r && r < hi) flag = 1;
+            }
+            if (!flag && cr <= level + PSD_EPS) flag = 2;
+          }
+        }
+        const unsigned mask = psd_ballot(flag != 0);
+        if (!mask) { pos = end; break; }
+        const int src = psd_ffs(mask) - 1;
+        const int fl = psd_shfl_i(flag, src);
+        const double r_s = psd_shfl_d(r, src), hi_s = psd_shfl_d(hi, src);
+        if (fl == 3) { cx.internal = 1; pos = end; level = PSD_INF; break; }
+        const double xe = (fl == 1) ? r_s : hi_s;
+        if (lane == 0) pl_emit(cx, out, out_n, 0.0 + 0.0, 0.0 + 0.0, level + cshift, xe, arg_at, stamp);
+        out_n++;
+        level = PSD_INF; left_edge = xe;
+        pos = base + src + (fl == 1 ? 0 : 1);
+      }
+    }
+  }
+  if (level < PSD_INF) {
+    if (lane == 0) pl_emit(cx, out, out_n, 0.0 + 0.0, 0.0 + 0.0, level + cshift, PL_X(in, n - 1), arg_at, stamp);
+    out_n++;
+  }
+  out.n = out_n;
+  psd_syncwarp();
+}
+
+// ---- set_to_min_more_of, then set_prev_seg_end(stamp) ---------------------------------------------
+PSD_DEV void min_more_op(WarpCtx& cx, const PList in, PList& out, double dmin, int stamp) {
+  const int lane = psd_lane();
+  const int cap = cx.cap;
+  const int n = in.n;
+  double level = PSD_INF;
+  double right_edge = PL_X(in, n - 1);
+  double arg_at = PSD_INF;
+  int out_n = 0;   // pieces are emitted right to left, reversed at the end
+  for (int base = ((n - 1) >> 5) << 5; base >= 0; base -= 32) {
+    const int i = base + lane;
+    const bool valid = i < n;
+    double a = 0, b = 0, c = 0, hi = 0, lo = 0;
+    double cl = 0, cr = 0, m = 0, mu = 0, cmu = 0, c2 = 0;
+    if (valid) {
+      a = PL_A(in, i); b = PL_B(in, i); c = PL_C(in, i); hi = PL_X(in, i);
+      lo = (i == 0) ? dmin : PL_X(in, i - 1);
+      cl = pc_cost(a, b, c, lo, cx);
+      cr = pc_cost(a, b, c, hi, cx);
+      if (b != 0) {
+        m = -b / a;
+        mu = psd_log(m, cx.ltab);
+        cmu = pc_cost(a, b, c, mu, cx);
+        c2 = pc_cost_m(a, b, c, m, mu);
+      }
+    }
+    // cost of the previous piece at its right end
+    double pr = psd_shfl_up_d(cr, 1);
+    const bool has_prev = i > 0;
+    if (lane == 0 && has_prev && valid) pr = pc_cost(PL_A(in, i - 1), PL_B(in, i - 1), PL_C(in, i - 1), lo, cx);
+    int kind = 0;  // 0 = copied whole, 1 = flat stretch starts at its right end, 2 = interior minimum
+    if (valid && b != 0) {
+      const bool prev_ok = !has_prev || PSD_EPS < pr - cmu;
+      if (hi <= mu) kind = (PSD_EPS < cl - cr) ? 1 : 0;
+      else if (lo < mu && PSD_EPS < cl - cmu && prev_ok) kind = 2;
+    }
+    int pos = (n - 1 - base < 31) ? n - 1 : base + 31;   // highest unprocessed piece
+    while (pos >= base) {
+      if (level == PSD_INF) {
+        const unsigned mask = psd_ballot(valid && i <= pos && kind != 0);
+        const int first = mask ? base + 31 - psd_clz(mask) : base - 1;
+        if (valid && i <= pos && i > first) pl_emit(cx, out, out_n + (pos - i), a, b, c, (i == pos) ? right_edge : hi, PSD_INF, stamp);
+        const int src = (first >= base) ? first - base : 0;
+        const int kf = psd_shfl_i(kind, src);
+        const double hi_f = psd_shfl_d(hi, src), cr_f = psd_shfl_d(cr, src);
+        const double mu_f = psd_shfl_d(mu, src), cmu_f = psd_shfl_d(cmu, src);
+        const double lo_b = psd_shfl_d(lo, 0);
+        if (first < pos) right_edge = (first >= base) ? hi_f : lo_b;
+        out_n += pos - first;
+        if (first < base) { pos = base - 1; break; }
+        if (kf == 1) { level = cr_f; arg_at = hi_f; }
+        else {
+          if (mu_f < right_edge) {
+            if (lane == src) pl_emit(cx, out, out_n, a, b, c, right_edge, PSD_INF, stamp);
+            out_n++;
+          }
+          right_edge = mu_f; arg_at = mu_f; level = cmu_f;
+        }
+        pos = first - 1;
+      } else {
+        int flag = 0;
+        double r = PSD_INF;
+        if (valid && i <= pos) {
+          if (b == 0) r = psd_log((level - c) / a, cx.ltab);
+          else if (two_roots(a, cmu, c2, level)) r = root_right(a, b, c, hi, level, m, c2, cr, cx.ltab);
+          if (lo < r && r < hi) flag = 1;
+          else if (cl <= level + PSD_EPS) flag = 2;
+        }
+        const unsigned mask = psd_ballot(flag != 0);
+        if (!mask) { pos = base - 1; break; }
+        const int src = 31 - psd_clz(mask);
+        const int fl = psd_shfl_i(flag, src);
+        const double r_s = psd_shfl_d(r, src), lo_s = psd_shfl_d(lo, src);
+        if (lane == 0) pl_emit(cx, out, out_n, 0.0, 0.0, level, right_edge, arg_at, stamp);
+        out_n++;
+        level = PSD_INF;
+        if (fl == 1) { right_edge = r_s; pos = base + src; }
+        else { right_edge = lo_s; pos = base + src - 1; }
+      }
+    }
+  }
+  if (level < PSD_INF) {
+    if (lane == 0) pl_emit(cx, out, out_n, 0.0, 0.0, level, right_edge, arg_at, stamp);
+    out_n++;
+  }
+  psd_syncwarp();
+  // reverse into left-to-right order
+  const int live = out_n < cap ? out_n : cap;
+  if (out_n <= cap) {
+    for (int k = lane; k < (live >> 1); k += 32) {
+      const int j = live - 1 - k;
+      double t;
+      t = PL_A(out, k); PL_A(out, k) = PL_A(out, j); PL_A(out, j) = t;
+      t = PL_B(out, k); PL_B(out, k) = PL_B(out, j); PL_B(out, j) = t;
+      t = PL_C(out, k); PL_C(out, k) = PL_C(out, j); PL_C(out, j) = t;
+      t = PL_X(out, k); PL_X(out, k) = PL_X(out, j); PL_X(out, j) = t;
+      t = PL_P(out, k); PL_P(out, k) = PL_P(out, j); PL_P(out, j) = t;
+      const int ti = PL_I(out, k); PL_I(out, k) = PL_I(out, j); PL_I(out, j) = ti;
+    }
+  }
+  out.n = out_n;
+  psd_syncwarp();
+}
+
+// ---- push_min_pieces (:870-1259) for one overlap interval, one lane --------------------------------
+// Result: nc candidate pieces.  Candidate 0 comes from f if s0 == 0 else from g; candidates
+// alternate sources; split points x1 (and x2).   [s0] | x1 | [!s0] | x2 | [s0]
+struct PairOut { int nc; int s0; double x1, x2; };
+
+PSD_DEV PairOut pair_rule(const WarpCtx& cx, const PList f, const PList g, int i, int j, double dmin,
+                          double* lo_out, double* hi_out) {
+  const int cap = cx.cap;
+  PairOut o; o.nc = 1; o.s0 = 0; o.x1 = 0; o.x2 = 0;
+  const double pa = PL_A(f, i), pb = PL_B(f, i), pcst = PL_C(f, i);
+  const double qa = PL_A(g, j), qb = PL_B(g, j), qcst = PL_C(g, j);
+  const double plo = (i == 0) ? dmin : PL_X(f, i - 1), phi = PL_X(f, i);
+  const double qlo = (j == 0) ? dmin : PL_X(g, j - 1), qhi = PL_X(g, j);
+  bool eq_left, eq_right;
+  double lo, hi;
+  if (plo < qlo) { eq_left = same_coefs(PL_A(g, j - 1), PL_B(g, j - 1), PL_C(g, j - 1), pa, pb, pcst); lo = qlo; }
+  else {
+    lo = plo;
+    if (qlo < plo) eq_left = same_coefs(PL_A(f, i - 1), PL_B(f, i - 1), PL_C(f, i - 1), qa, qb, qcst);
+    else eq_left = (i == 0 || j == 0) ? false
+                   : same_coefs(PL_A(f, i - 1), PL_B(f, i - 1), PL_C(f, i - 1), PL_A(g, j - 1), PL_B(g, j - 1), PL_C(g, j - 1));
+  }
+  if (phi < qhi) { eq_right = same_coefs(PL_A(f, i + 1), PL_B(f, i + 1), PL_C(f, i + 1), qa, qb, qcst); hi = phi; }
+  else {
+    hi = qhi;
+    if (qhi < phi) eq_right = same_coefs(pa, pb, pcst, PL_A(g, j + 1), PL_B(g, j + 1), PL_C(g, j + 1));
+    else eq_right = (i + 1 == f.n || j + 1 == g.n) ? false
+                    : same_coefs(PL_A(f, i + 1), PL_B(f, i + 1), PL_C(f, i + 1), PL_A(g, j + 1), PL_B(g, j + 1), PL_C(g, j + 1));
+  }
+  *lo_out = lo; *hi_out = hi;
+  if (lo == hi) { o.nc = 0; return o; }
+  if (same_coefs(pa, pb, pcst, qa, qb, qcst)) { o.s0 = 0; return o; }
+  const double da = pa - qa, db = pb - qb, dc = pcst - qcst;
+  const double ehi = psd_exp(hi, cx.etab), elo = psd_exp(lo, cx.etab);
+  const double mid_m = (ehi + elo) / 2;
+  const double dmid = pc_cost(da, db, dc, psd_log(mid_m, cx.ltab), cx);
+  const int by_mid = (dmid < 0) ? 0 : 1;
+  if (eq_left && eq_right) { o.s0 = by_mid; return o; }
+  if (db == 0) {
+    if (da == 0) { o.s0 = (dc < 0) ? 0 : 1; return o; }
+    if (dc == 0) { o.s0 = (da < 0) ? 0 : 1; return o; }
+    const double x = psd_log(-dc / da, cx.ltab);
+    if (lo < x && x < hi) { o.nc = 2; o.x1 = x; o.s0 = (0 < da) ? 0 : 1; return o; }
+    o.s0 = by_mid; return o;
+  }
+  const double dl = pc_cost_e(da, db, dc, lo, elo), dr = pc_cost_e(da, db, dc, hi, ehi);
+  const double m = -db / da;
+  const double xo = psd_log(m, cx.ltab);
+  const double c1 = pc_cost(da, db, dc, xo, cx);
+  const double c2 = pc_cost_m(da, db, dc, m, xo);
+  const bool two = two_roots(da, c1, c2, 0.0);
+  double rs = PSD_INF, rl = PSD_INF;
+  if (two) {
+    rs = root_left(da, db, dc, lo, 0.0, xo, c1, dl, cx.etab);
+    rl = root_right(da, db, dc, hi, 0.0, m, c2, dr, cx.ltab);
+  }
+  if (eq_right) {
+    if (two) {
+      if (lo < rs && rs < xo && xo < hi) { o.nc = 2; o.x1 = rs; o.s0 = (dl < 0) ? 0 : 1; return o; }
+      const bool f_low_at_zero = 0 < db;
+      if (rs < lo) o.s0 = f_low_at_zero ? 1 : 0;
+      else o.s0 = f_low_at_zero ? 0 : 1;
+      return o;
+    }
+    o.s0 = by_mid; return o;
+  }
+  if (eq_left) {
+    if (two) {
+      if (lo < xo && xo < rl && rl < hi) { o.nc = 2; o.x1 = rl; o.s0 = (dr < 0) ? 1 : 0; return o; }
+    }
+    o.s0 = by_mid; return o;
+  }
+  double x1 = PSD_INF, x2 = PSD_INF;
+  if (two) {
+    const bool l_in = lo < rl && rl < hi;
+    const bool s_in = lo < rs && 0 < psd_exp(rs, cx.etab) && rs < hi;
+    if (l_in) { if (s_in && rs < rl) { x1 = rs; x2 = rl; } else x1 = rl; }
+    else if (s_in) x1 = rs;
+  }
+  if (x2 != PSD_INF) {
+    bool f_first;
+    if (x2 - x1 < x1 - lo) {
+      const double bm = (elo + psd_exp(x1, cx.etab)) / 2;
+      f_first = pc_cost(da, db, dc, psd_log(bm, cx.ltab), cx) < 0;
+    } else {
+      f_first = !(pc_cost(da, db, dc, (x1 + x2) / 2, cx) < 0);
+    }
+    o.nc = 3; o.x1 = x1; o.x2 = x2; o.s0 = f_first ? 0 : 1;
+  } else if (x1 != PSD_INF) {
+    const double bm = (elo + psd_exp(x1, cx.etab)) / 2;
+    const double before = pc_cost(da, db, dc, psd_log(bm, cx.ltab), cx);
+    const double after = pc_cost(da, db, dc, (hi + x1) / 2, cx);
+    if (before < 0) {
+      if (after < 0) o.s0 = 0;
+      else { o.nc = 2; o.x1 = x1; o.s0 = 0; }
+    } else {
+      if (after < 0) { o.nc = 2; o.x1 = x1; o.s0 = 1; }
+      else o.s0 = 1;
+    }
+  } else {
+    const double v = (pc_abs(dmid) < PSD_EPS) ? dr : dmid;
+    o.s0 = (v < 0) ? 0 : 1;
+  }
+  return o;
+}
+
+#define PSD_SRC_G 0x40000000
+
+// ---- set_to_min_env_of(f, g) followed by the row rescale -------------------------------------------
+// f is the freshly built min-less/min-more function, g the previous cost function.
+PSD_DEV void min_env_op(WarpCtx& cx, const PList f, const PList g, PList& out, double dmin, const Rescale rs) {
+  const int lane = psd_lane();
+  const int cap = cx.cap;
+  const int nf = f.n, ng = g.n;
+  // 1. enumerate overlap intervals, one g piece per lane: f pieces s..e overlap g[j]
+  int K = 0;
+  {
+    int carry_next = 0;   // first f piece that can overlap the next g piece
+    for (int base = 0; base < ng; base += 32) {
+      const int j = base + lane;
+      const bool valid = j < ng;
+      int e = 0, tie = 0;
+      if (valid) {
+        const double v = PL_X(g, j);
+        int lo_i = 0, hi_i = nf - 1;    // lower_bound: first f piece whose right end >= v
+        while (lo_i < hi_i) {
+          const int mid = (lo_i + hi_i) >> 1;
+          if (PL_X(f, mid) < v) lo_i = mid + 1; else hi_i = mid;
+        }
+        e = lo_i;
+        tie = (PL_X(f, e) == v) ? 1 : 0;
+      }
+      int s = psd_shfl_up_i(e + tie, 1);
+      if (lane == 0) s = carry_next;
+      int cnt = valid ? (e - s + 1) : 0;
+      if (cnt < 0) cnt = 0;
+      // exclusive scan of cnt
+      int incl = cnt;
+      for (int d = 1; d < 32; d <<= 1) { const int t = psd_shfl_up_i(incl, d); if (lane >= d) incl += t; }
+      const int off = K + incl - cnt;
+      for (int q = 0; q < cnt; q++) {
+        if (off + q < 2 * cap) cx.ivl[off + q] = (s + q) | (j << 16); else cx.overflow = 1;
+      }
+      K += psd_shfl_i(incl, 31);
+      carry_next = psd_shfl_i(e + tie, (ng - base < 32) ? ng - base - 1 : 31);
+    }
+  }
+  psd_syncwarp();
+  if (K > 2 * cap) { K = 2 * cap; }
+  // 2. crossing rule per interval -> candidate pieces
+  int T = 0;
+  for (int base = 0; base < K; base += 32) {
+    const int q = base + lane;
+    const bool valid = q < K;
+    PairOut o; o.nc = 0; o.s0 = 0; o.x1 = 0; o.x2 = 0;
+    double lo = 0, hi = 0;
+    int i = 0, j = 0;
+    if (valid) {
+      const int code = cx.ivl[q];
+      i = code & 0xffff; j = code >> 16;
+      o = pair_rule(cx, f, g, i, j, dmin, &lo, &hi);
+    }
+    int incl = o.nc;
+    for (int d = 1; d < 32; d <<= 1) { const int t = psd_shfl_up_i(incl, d); if (lane >= d) incl += t; }
+    const int off = T + incl - o.nc;
+    if (o.nc > 0) {
+      const int sf = i, sg = j | PSD_SRC_G;
+      const int c0 = o.s0 ? sg : sf, c1 = o.s0 ? sf : sg;
+      if (off + o.nc <= cx.ccap) {
+        cx.cand_s[off] = c0; cx.cand_x[off] = (o.nc > 1) ? o.x1 : hi;
+        if (o.nc > 1) { cx.cand_s[off + 1] = c1; cx.cand_x[off + 1] = (o.nc > 2) ? o.x2 : hi; }
+        if (o.nc > 2) { cx.cand_s[off + 2] = c0; cx.cand_x[off + 2] = hi; }
+      } else cx.overflow = 1;
+    }
+    T += psd_shfl_i(incl, 31);
+  }
+  psd_syncwarp();
+  if (T > cx.ccap) T = cx.ccap;
+  // 3. push_piece: merge each candidate into the current run when it equals the run's head
+  int out_n = 0;
+  bool carry_ok = false;
+  double ha = 0, hb = 0, hc = 0, hp = 0; int hi_i = 0;   // head of the run open at the chunk boundary
+  int carry_slot = 0;
+  for (int base = 0; base < T; base += 32) {
+    const int q = base + lane;
+    const bool valid = q < T;
+    double a = 0, b = 0, c = 0, p = 0, x = 0; int bi = 0;
+    if (valid) {
+      const int code = cx.cand_s[q];
+      x = cx.cand_x[q];
+      const int k = code & 0xffffff;
+      if (code & PSD_SRC_G) { a = PL_A(g, k); b = PL_B(g, k); c = PL_C(g, k); p = PL_P(g, k); bi = PL_I(g, k); }
+      else { a = PL_A(f, k); b = PL_B(f, k); c = PL_C(f, k); p = PL_P(f, k); bi = PL_I(f, k); }
+    }
+    // first guess: a candidate continues the run iff it equals its immediate predecessor
+    double pa_ = psd_shfl_up_d(a, 1), pb_ = psd_shfl_up_d(b, 1), pc_ = psd_shfl_up_d(c, 1), pp_ = psd_shfl_up_d(p, 1);
+    int pi_ = psd_shfl_up_i(bi, 1);
+    bool pv = lane > 0;
+    if (lane == 0) { pa_ = ha; pb_ = hb; pc_ = hc; pp_ = hp; pi_ = hi_i; pv = carry_ok; }
+    bool head = valid && !(pv && same_coefs(pa_, pb_, pc_, a, b, c) && p == pp_ && bi == pi_);
+    // verify against the true run heads (push_piece compares with the list's last piece, whose
+    // coefficients are those of the run's first member); repair the first disagreement and retry
+    for (;;) {
+      const unsigned hm = psd_ballot(head);
+      const unsigned below = hm & ((1u << lane) - 1u);
+      const int hl = below ? 31 - psd_clz(below) : -1;   // head of the run candidate q-1 belongs to
+      double ra = psd_shfl_d(a, hl < 0 ? 0 : hl), rb = psd_shfl_d(b, hl < 0 ? 0 : hl), rc = psd_shfl_d(c, hl < 0 ? 0 : hl);
+      double rp = psd_shfl_d(p, hl < 0 ? 0 : hl);
+      int ri = psd_shfl_i(bi, hl < 0 ? 0 : hl);
+      bool rv = true;
+      if (hl < 0) { ra = ha; rb = hb; rc = hc; rp = hp; ri = hi_i; rv = carry_ok; }
+      const bool want_head = valid && !(rv && same_coefs(ra, rb, rc, a, b, c) && p == rp && bi == ri);
+      const unsigned bad = psd_ballot(valid && want_head != head);
+      if (!bad) break;
+      if (lane == psd_ffs(bad) - 1) head = want_head;
+    }
+    const unsigned hm = psd_ballot(head);
+    const unsigned vm = psd_ballot(valid);
+    const int rank = psd_popc(hm & ((1u << lane) - 1u));
+    const unsigned upto = hm & ((2u << lane) - 1u);       // heads at or below this lane
+    const int my_head = upto ? 31 - psd_clz(upto) : -1;
+    const int slot = (my_head < 0) ? carry_slot : out_n + psd_popc(hm & ((1u << my_head) - 1u));
+    if (head) {
+      const double na = ((a * rs.mul) + rs.add_a) * rs.inv;
+      const double nb = ((b * rs.mul) + rs.add_b) * rs.inv;
+      const double nc = ((c * rs.mul) + 0.0) * rs.inv;
+      if (out_n + rank < cap) {
+        PList& o = out;
+        PL_A(o, out_n + rank) = na; PL_B(o, out_n + rank) = nb; PL_C(o, out_n + rank) = nc;
+        PL_P(o, out_n + rank) = p; PL_I(o, out_n + rank) = bi;
+      } else cx.overflow = 1;
+    }
+    // the last member of every run (within this chunk) sets the run's right end
+    const bool last_valid = valid && (lane == 31 || !((vm >> (lane + 1)) & 1u));
+    const bool next_is_head = (lane < 31) && ((hm >> (lane + 1)) & 1u);
+    if (valid && (last_valid || next_is_head)) { if (slot < cap) PL_X(out, slot) = x; }
+    // carry the open run into the next chunk
+    const int n_heads = psd_popc(hm);
+    if (n_heads) {
+      const int last_head = 31 - psd_clz(hm);
+      ha = psd_shfl_d(a, last_head); hb = psd_shfl_d(b, last_head); hc = psd_shfl_d(c, last_head);
+      hp = psd_shfl_d(p, last_head); hi_i = psd_shfl_i(bi, last_head);
+      carry_slot = out_n + n_heads - 1;
+      carry_ok = true;
+    }
+    out_n += n_heads;
+  }
+  out.n = out_n;
+  psd_syncwarp();
+}
+
+// copy with rescale (rows 0/1 of the DP, src/PeakSegFPOPLog.cpp:297-299, 324-328)
+PSD_DEV void copy_rescale_op(WarpCtx& cx, const PList in, PList& out, const Rescale rs) {
+  const int lane = psd_lane();
+  const int cap = cx.cap;
+  for (int k = lane; k < in.n; k += 32) {
+    PL_A(out, k) = ((PL_A(in, k) * rs.mul) + rs.add_a) * rs.inv;
+    PL_B(out, k) = ((PL_B(in, k) * rs.mul) + rs.add_b) * rs.inv;
+    PL_C(out, k) = ((PL_C(in, k) * rs.mul) + 0.0) * rs.inv;
+    PL_X(out, k) = PL_X(in, k); PL_P(out, k) = PL_P(in, k); PL_I(out, k) = PL_I(in, k);
+  }
+  out.n = in.n;
+  psd_syncwarp();
+}
+
+// ---- Minimize (:689-712): first piece with the strictly smallest clamped-argmin cost ---------------
+PSD_DEV void best_piece(WarpCtx& cx, const PList f, double dmin, double* best_c, double* best_x, int* back_i, double* back_x) {
+  const int lane = psd_lane();
+  const int cap = cx.cap;
+  double bc = PSD_INF, bx = 0, bpx = 0; int bbi = 0; int bidx = 0x7fffffff;
+  for (int base = 0; base < f.n; base += 32) {
+    const int i = base + lane;
+    double cc = PSD_INF, x = 0;
+    if (i < f.n) {
+      const double a = PL_A(f, i), b = PL_B(f, i), c = PL_C(f, i), hi = PL_X(f, i);
+      const double lo = (i == 0) ? dmin : PL_X(f, i - 1);
+      x = psd_log(-b / a, cx.ltab);
+      if (x < lo) x = lo; else if (hi < x) x = hi;
+      cc = pc_cost(a, b, c, x, cx);
+      if (!(cc < PSD_INF)) cc = PSD_INF;   // NaN/inf are never selected
+    }
+    if (cc < bc) { bc = cc; bx = x; bidx = i; bbi = PL_I(f, i); bpx = PL_P(f, i); }
+  }
+  for (int d = 16; d >= 1; d >>= 1) {
+    const double oc = psd_shfl_xor_d(bc, d), ox = psd_shfl_xor_d(bx, d), op = psd_shfl_xor_d(bpx, d);
+    const int oi = psd_shfl_xor_i(bidx, d), ob = psd_shfl_xor_i(bbi, d);
+    if (oc < bc || (oc == bc && oi < bidx)) { bc = oc; bx = ox; bpx = op; bidx = oi; bbi = ob; }
+  }
+  *best_c = bc; *best_x = bx; *back_i = bbi; *back_x = bpx;
+}
+
+// ---- HBM cost-function store ------------------------------------------------------------------------
+// A pool of fixed-size chunks; a warp appends its rows' records to its current chunk and takes a new
+// one (atomicAdd on the pool cursor) when the next record does not fit.  Record of row t, 16-byte
+// aligned:   u32 n_up | u32 n_down | u32 row | u32 0
+//            n_up   x { f64 hi, f64 back_x }      (128-bit stores, one piece per lane)
+//            n_down x { f64 hi, f64 back_x }
+//            (n_up + n_down) x i32 back_i, padded to 16 bytes
+// index[t] = byte offset of the record in the pool.  The reference's record
+// (src/PeakSegFPOPLog.cpp:12-34) carries the same fields at 8 + 20 bytes per piece per function.
+struct StorePool {
+  unsigned char* base;
+  unsigned long long* cursor;     // next free chunk
+  unsigned long long n_chunks;
+  unsigned long long chunk_bytes;
+};
+struct StoreWriter { unsigned long long cur, end; };
+
+PSD_DEV unsigned long long store_record_bytes(int n_up, int n_down) {
+  const unsigned long long np = (unsigned long long)(n_up + n_down);
+  return 16ull + 16ull * np + ((4ull * np + 15ull) & ~15ull);
+}
+
+// returns the record offset or ~0 when the pool is exhausted
+PSD_DEV unsigned long long store_alloc(const StorePool& sp, StoreWriter& w, unsigned long long bytes) {
+  if (w.cur + bytes > w.end) {
+    const unsigned long long need = (bytes + sp.chunk_bytes - 1) / sp.chunk_bytes;
+    unsigned long long first = 0;
+    if (psd_lane() == 0) first = psd_atomic_add_ull(sp.cursor, need);
+    first = psd_shfl_u64(first, 0);
+    if (first + need > sp.n_chunks) return ~0ull;
+    w.cur = first * sp.chunk_bytes;
+    w.end = w.cur + need * sp.chunk_bytes;
+  }
+  const unsigned long long off = w.cur;
+  w.cur += bytes;
+  return off;
+}
+
+PSD_DEV void store_write(WarpCtx& cx, const StorePool& sp, unsigned long long off, int row, const PList up, const PList down) {
+  const int lane = psd_lane();
+  const int cap = cx.cap;
+  unsigned char* rec = sp.base + off;
+  if (lane == 0) psd_st_cs_u4((unsigned*)rec, (unsigned)up.n, (unsigned)down.n, (unsigned)row, 0u);
+  double* pairs = (double*)(rec + 16);
+  for (int k = lane; k < up.n; k += 32) psd_st_cs_d2(pairs + 2 * k, PL_X(up, k), PL_P(up, k));
+  pairs += 2 * up.n;
+  for (int k = lane; k < down.n; k += 32) psd_st_cs_d2(pairs + 2 * k, PL_X(down, k), PL_P(down, k));
+  int* bis = (int*)(pairs + 2 * down.n);
+  for (int k = lane; k < up.n; k += 32) psd_st_cs_i(bis + k, PL_I(up, k));
+  bis += up.n;
+  for (int k = lane; k < down.n; k += 32) psd_st_cs_i(bis + k, PL_I(down, k));
+}
+
+// per-problem result of the DP (device -> host), and of the backtrack
+struct DpResult {
+  int status;
+  int back_i;                 // Minimize(): last row of the previous segment
+  double best_cost;           // mean penalized cost
+  double best_x;              // log-mean of the last segment
+  double back_x;
+  unsigned long long total_intervals;
+  int max_intervals;
+  int n_segments;
+  int n_equality;
+  int pad_;
+};
+
+// optional per-row trace for tests (null in production): called by lane 0 after every row
+#if defined(PSD_EMU)
+typedef void (*psd_trace_fn)(void* user, int row, int which, int n, int cap, const double* base);
+#endif
+
+struct DpProblem {
+  const int* weight;          // chromEnd - chromStart per row
+  const int* coverage;
+  int n_rows;
+  double penalty;
+  double dmin, dmax;          // log(min coverage), log(max coverage)
+  unsigned long long* index;  // n_rows record offsets
+};
+
+// The DP over all rows of one problem (src/PeakSegFPOPLog.cpp:258-397 + Minimize at :404).
+// buf[0..3] are four list buffers of capacity cx.cap.
+PSD_DEV void dp_problem(WarpCtx& cx, const DpProblem& pb, double* const buf[4], const StorePool& sp, DpResult* res
+#if defined(PSD_EMU)
+                        , psd_trace_fn trace, void* trace_user
+#endif
+) {
+  const int lane = psd_lane();
+  const int cap = cx.cap;
+  const int N = pb.n_rows;
+  // roles: up_prev, down_prev, scratch (min-less/more result), new
+  PList upP, downP, tmp, fresh;
+  upP.base = buf[0]; downP.base = buf[1]; tmp.base = buf[2]; fresh.base = buf[3];
+  upP.n = 0; downP.n = 0; tmp.n = 0; fresh.n = 0;
+  StoreWriter sw; sw.cur = 0; sw.end = 0;
+  double cw = 0.0, cw_prev = -1.0;
+  unsigned long long total_iv = 0; int max_iv = 0;
+  int status = PSD_ST_OK;
+  unsigned long long my_off = 0;   // lane (t & 31) keeps row t's record offset until the batch is flushed
+  int w_l = 0, z_l = 0;
+  for (int t = 0; t < N; t++) {
+    if ((t & 31) == 0) {   // coalesced load of the next 32 rows
+      const int r = t + lane;
+      w_l = (r < N) ? pb.weight[r] : 0;
+      z_l = (r < N) ? pb.coverage[r] : 0;
+    }
+    const int wi = psd_shfl_i(w_l, t & 31), z = psd_shfl_i(z_l, t & 31);
+    const double w = (double)wi;
+    cw += w;
+    Rescale rs; rs.mul = cw_prev; rs.add_a = w; rs.add_b = (double)(-z) * w; rs.inv = 1 / cw;
+    PList up_new, down_new;
+    if (t == 0) {
+      if (lane == 0) pl_emit(cx, downP, 0, 1.0, (double)(-z), 0.0, pb.dmax, -5.0, -1);
+      downP.n = 1; upP.n = 0;
+      psd_syncwarp();
+      up_new = upP; down_new = downP;
+    } else {
+      min_less_op(cx, downP, tmp, pb.dmin, t - 1, pb.penalty / cw_prev);
+      if (t == 1) { copy_rescale_op(cx, tmp, fresh, rs); }
+      else { min_env_op(cx, tmp, upP, fresh, pb.dmin, rs); }
+      // fresh = up_t.  down_t goes where up_{t-1} lived once min_more has consumed it.
+      if (t == 1) {
+        copy_rescale_op(cx, downP, upP, rs);
+      } else {
+        min_more_op(cx, upP, tmp, pb.dmin, t - 1);
+        // min_env reads tmp and downP, writes into upP's buffer: safe, upP is dead now
+        PList dst; dst.base = upP.base; dst.n = 0;
+        min_env_op(cx, tmp, downP, dst, pb.dmin, rs);
+        upP = dst;
+      }
+      // rotate roles: up_prev <- fresh, down_prev <- (old upP buffer), free <- old downP
+      PList old_down = downP;
+      downP = upP; upP = fresh; fresh = old_down; fresh.n = 0;
+      up_new = upP; down_new = downP;
+    }
+    if (psd_ballot(cx.overflow)) { status = PSD_ST_PIECE_OVERFLOW; break; }
+    if (psd_ballot(cx.internal)) { status = PSD_ST_INTERNAL; break; }
+    cw_prev = cw;
+    total_iv += (unsigned long long)(up_new.n + down_new.n);
+    if (max_iv < up_new.n) max_iv = up_new.n;
+    if (max_iv < down_new.n) max_iv = down_new.n;
+#if defined(PSD_EMU)
+    if (trace && lane == 0) { trace(trace_user, t, 0, up_new.n, cap, up_new.base); trace(trace_user, t, 1, down_new.n, cap, down_new.base); }
+#endif
+    const unsigned long long off = store_alloc(sp, sw, store_record_bytes(up_new.n, down_new.n));
+    if (off == ~0ull) { status = PSD_ST_STORE_EXHAUSTED; break; }
+    store_write(cx, sp, off, t, up_new, down_new);
+    if (lane == (t & 31)) my_off = off;
+    if ((t & 31) == 31 || t == N - 1) {
+      const int r = (t & ~31) + lane;
+      if (r <= t) psd_st_cs_u64(pb.index + r, my_off);
+    }
+  }
+  double bc = 0, bx = 0, bpx = 0; int bbi = -1;
+  if (status == PSD_ST_OK) best_piece(cx, downP, pb.dmin, &bc, &bx, &bbi, &bpx);
+  if (lane == 0) {
+    res->status = status; res->back_i = bbi; res->best_cost = bc; res->best_x = bx; res->back_x = bpx;
+    res->total_intervals = total_iv; res->max_intervals = max_iv; res->n_segments = 0; res->n_equality = 0;
+  }
+}
+
+// ---- decode (src/PeakSegFPOPLog.cpp:400-442 + findMean :643-653) ------------------------------------
+// Walks the stored functions from the last row back.  Output, last segment first:
+//   seg_x[s]   = log-mean of segment s            (s = 0 .. n_segments-1)
+//   seg_row[s] = last row of the segment before s (s = 0 .. n_segments-2)
+PSD_DEV void backtrack_problem(const unsigned char* pool, const unsigned long long* index, int n_rows,
+                               DpResult* res, int* seg_row, double* seg_x) {
+  const int lane = psd_lane();
+  if (res->status != PSD_ST_OK) return;
+  double best_x = res->best_x, back_x = res->back_x;
+  int back_i = res->back_i;
+  int use_down = 0;   // the last segment is "down"; the function read first is an "up" one
+  int n_seg = 1, n_eq = 0, status = PSD_ST_OK;
+  while (0 <= back_i) {
+    if (n_seg > n_rows) { status = PSD_ST_BACKTRACK_LOST; break; }
+    const unsigned char* rec = pool + index[back_i];
+    const unsigned* hdr = (const unsigned*)rec;
+    const int n_up = (int)hdr[0], n_down = (int)hdr[1];
+    const int n = use_down ? n_down : n_up;
+    const double* pairs = (const double*)(rec + 16) + (use_down ? 2 * n_up : 0);
+    const int* bis = (const int*)((const double*)(rec + 16) + 2 * (n_up + n_down)) + (use_down ? n_up : 0);
+    if (lane == 0) { seg_row[n_seg - 1] = back_i; seg_x[n_seg - 1] = best_x; }
+    n_seg++;
+    use_down ^= 1;
+    if (back_x != PSD_INF) best_x = back_x; else n_eq++;
+    // findMean: first piece k with lo_k <= x <= hi_k, lo_0 = -inf, lo_k = hi_{k-1}
+    int found = 0;
+    for (int base = 0; base < n && !found; base += 32) {
+      const int k = base + lane;
+      double hi = 0, lo = -PSD_INF;
+      if (k < n) { hi = pairs[2 * k]; if (k > 0) lo = pairs[2 * (k - 1)]; }
+      const unsigned mask = psd_ballot(k < n && lo <= best_x && best_x <= hi);
+      if (mask) {
+        const int kk = base + psd_ffs(mask) - 1;
+        back_i = bis[kk];
+        back_x = pairs[2 * kk + 1];
+        found = 1;
+      }
+    }
+    if (!found) { status = PSD_ST_BACKTRACK_LOST; break; }
+  }
+  if (lane == 0) {
+    seg_x[n_seg - 1] = best_x;
+    res->n_segments = n_seg; res->n_equality = n_eq;
+    if (status != PSD_ST_OK) res->status = status;
+  }
+}

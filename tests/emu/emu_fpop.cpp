@@ -1,0 +1,80 @@
+// TEST TOOL: runs the product's device source (peaksegdisk_b200/csrc/fpop_warp.cuh) for one problem
+// under the CPU warp emulator and exposes it with the oracle's in-memory signature, so tests can
+// diff it against the oracle row by row without a GPU.  Not part of the product.
+#define PSD_EMU 1
+#include <vector>
+#include <cmath>
+#include "warp_emu.h"
+#include "../../peaksegdisk_b200/csrc/fpop_warp.cuh"
+
+namespace {
+struct Job {
+  DpProblem pb; WarpCtx cx_proto; double* buf[4]; StorePool sp; DpResult* res;
+  psd_trace_fn trace; void* trace_user;
+  int* seg_row; double* seg_x;
+};
+void lane_main(void* arg) {
+  Job* J = (Job*)arg;
+  WarpCtx cx = J->cx_proto;   // lane-local copy (overflow/internal flags are per lane)
+  dp_problem(cx, J->pb, J->buf, J->sp, J->res, J->trace, J->trace_user);
+  psd_syncwarp();
+  backtrack_problem(J->sp.base, J->pb.index, J->pb.n_rows, J->res, J->seg_row, J->seg_x);
+}
+}  // namespace
+
+extern "C" {
+
+// Same outputs as oracle_fpop_rows (non-trivial problems only).  cap = list capacity to emulate.
+// Returns the DpResult status (0 ok, 101 piece overflow, ...).
+int emu_fpop_rows(int n_rows, const int* chrom_start, const int* chrom_end, const int* coverage,
+                  double penalty, int cap, int descending, double* out_summary,
+                  int* seg_start, int* seg_end, int* seg_peak, double* seg_mean,
+                  psd_trace_fn trace, void* trace_user) {
+  std::vector<int> w(n_rows);
+  double W = 0, dmin = INFINITY, dmax = -INFINITY;
+  for (int t = 0; t < n_rows; t++) {
+    w[t] = chrom_end[t] - chrom_start[t]; W += w[t];
+    double lx = psd_log((double)coverage[t], psd_log_tab_host);
+    if (lx < dmin) dmin = lx;
+    if (dmax < lx) dmax = lx;
+  }
+  Job J;
+  std::vector<unsigned long long> index(n_rows);
+  J.pb.weight = w.data(); J.pb.coverage = coverage; J.pb.n_rows = n_rows; J.pb.penalty = penalty;
+  J.pb.dmin = dmin; J.pb.dmax = dmax; J.pb.index = index.data();
+  std::vector<double> lists((size_t)4 * cap * 44 / 8 + 8);
+  for (int k = 0; k < 4; k++) J.buf[k] = lists.data() + (size_t)k * cap * 44 / 8;
+  std::vector<int> ivl(2 * cap);
+  const int ccap = 3 * cap;
+  std::vector<double> cand_x(ccap); std::vector<int> cand_s(ccap);
+  J.cx_proto.etab = psd_exp_tab_host; J.cx_proto.ltab = psd_log_tab_host; J.cx_proto.cap = cap;
+  J.cx_proto.ivl = ivl.data(); J.cx_proto.cand_x = cand_x.data(); J.cx_proto.cand_s = cand_s.data();
+  J.cx_proto.ccap = ccap; J.cx_proto.overflow = 0; J.cx_proto.internal = 0;
+  const unsigned long long chunk = 1 << 16;
+  std::vector<unsigned char> pool;
+  unsigned long long cursor = 0;
+  // generous pool: header + 20 bytes per piece, pieces <= cap per function
+  unsigned long long pool_bytes = (unsigned long long)n_rows * (32ull + 40ull * (unsigned)cap + 64ull) + chunk;
+  if (pool_bytes > (6ull << 30)) pool_bytes = 6ull << 30;
+  pool.resize((pool_bytes / chunk + 1) * chunk);
+  J.sp.base = pool.data(); J.sp.cursor = &cursor; J.sp.n_chunks = pool.size() / chunk; J.sp.chunk_bytes = chunk;
+  DpResult res; res.status = -1;
+  J.res = &res; J.trace = trace; J.trace_user = trace_user;
+  std::vector<int> seg_row(n_rows + 1); std::vector<double> seg_x(n_rows + 1);
+  J.seg_row = seg_row.data(); J.seg_x = seg_x.data();
+  psd_emu::run_warp(lane_main, &J, descending);
+  if (res.status != 0) return res.status;
+  const int ns = res.n_segments, np = (ns - 1) / 2;
+  out_summary[0] = penalty; out_summary[1] = ns; out_summary[2] = np; out_summary[3] = W; out_summary[4] = n_rows;
+  out_summary[5] = res.best_cost; out_summary[6] = res.best_cost * W - penalty * np; out_summary[7] = res.n_equality;
+  out_summary[8] = (double)res.total_intervals / (n_rows * 2); out_summary[9] = res.max_intervals;
+  int prev_end = chrom_end[n_rows - 1];
+  for (int s = 0; s < ns; s++) {
+    const int st = (s < ns - 1) ? chrom_end[seg_row[s]] : chrom_start[0];
+    seg_start[s] = st; seg_end[s] = prev_end; seg_peak[s] = s & 1; seg_mean[s] = psd_exp(seg_x[s], psd_exp_tab_host);
+    prev_end = st;
+  }
+  return 0;
+}
+
+}  // extern "C"
