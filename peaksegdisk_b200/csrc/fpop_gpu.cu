@@ -1,0 +1,524 @@
+// fpop_gpu.cu -- sm_100a kernels and the batched plan behind the C ABI (include/peaksegdisk_b200.h).
+//
+// Launch structure (one CUDA stream, no host sync between kernels):
+//   fpop_dp_kernel         persistent warps; each warp pops problems (longest first) from an atomic
+//                          queue and runs dp_problem() (fpop_warp.cuh): the whole DP of one
+//                          (bedGraph x penalty), piece lists in shared memory, cost-function
+//                          records streamed to the HBM chunk pool.
+//   fpop_backtrack_kernel  one warp per problem: backtrack_problem() walks the stored records,
+//                          then compacts the segments into one array for a single D2H copy.
+// Problems whose functions outgrow the shared-memory tier (status 101) are re-run by the same
+// kernel with per-warp piece lists in global memory; problems that do not fit the store pool
+// (status 102) are re-run in a later wave after the pool is recycled.
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+#include "fpop_warp.cuh"
+#include "plan_internal.h"
+
+#define PSD_WARPS_PER_BLOCK 4
+#define PSD_TAB_BYTES 4096
+
+__device__ const uint64_t d_exp_tab[256] = PSD_EXP_TAB_INIT;
+__device__ const uint64_t d_log_tab[256] = PSD_LOG_TAB_INIT;
+
+struct DpKernelParams {
+  const DpProblem* problems;
+  const int* order;           // problem ids, longest first
+  int n_order;
+  int* queue;                 // atomic cursor into order
+  DpResult* results;
+  StorePool pool;
+  int cap, ccap;
+  unsigned char* gws;         // global-tier workspace (null: piece lists live in shared memory)
+  unsigned long long ws_bytes_per_warp;
+};
+
+__host__ __device__ inline unsigned long long psd_ws_bytes(int cap, int ccap) {
+  // 4 piece lists + interval scratch + candidate scratch, 16-byte aligned
+  unsigned long long b = 4ull * 44ull * (unsigned)cap + 4ull * 2ull * (unsigned)cap + 12ull * (unsigned)ccap;
+  return (b + 15ull) & ~15ull;
+}
+
+__global__ void __launch_bounds__(PSD_WARPS_PER_BLOCK * 32)
+fpop_dp_kernel(const DpKernelParams P) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  uint64_t* etab = (uint64_t*)smem;
+  uint64_t* ltab = etab + 256;
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) { etab[i] = d_exp_tab[i]; ltab[i] = d_log_tab[i]; }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  unsigned char* ws = P.gws ? P.gws + ((unsigned long long)blockIdx.x * PSD_WARPS_PER_BLOCK + warp) * P.ws_bytes_per_warp
+                            : smem + PSD_TAB_BYTES + (unsigned long long)warp * P.ws_bytes_per_warp;
+  WarpCtx cx;
+  cx.etab = etab; cx.ltab = ltab; cx.cap = P.cap; cx.ccap = P.ccap;
+  double* buf[4];
+  for (int k = 0; k < 4; k++) buf[k] = (double*)(ws + (unsigned long long)k * 44ull * (unsigned)P.cap);
+  cx.cand_x = (double*)(ws + 4ull * 44ull * (unsigned)P.cap);
+  cx.ivl = (int*)(cx.cand_x + P.ccap);
+  cx.cand_s = cx.ivl + 2 * P.cap;
+  for (;;) {
+    int q = 0;
+    if (lane == 0) q = atomicAdd(P.queue, 1);
+    q = __shfl_sync(0xffffffffu, q, 0);
+    if (q >= P.n_order) break;
+    const int id = P.order[q];
+    cx.overflow = 0; cx.internal = 0;
+    dp_problem(cx, P.problems[id], buf, P.pool, &P.results[id]);
+    __syncwarp();
+  }
+}
+
+struct BtKernelParams {
+  const DpProblem* problems;
+  const int* order;
+  int n_order;
+  DpResult* results;
+  const unsigned char* pool;
+  const unsigned long long* seg_scratch_off;   // per problem: offset of its scratch segment arrays
+  int* scratch_row; double* scratch_x;         // n_rows + 1 entries per problem
+  int* seg_row; double* seg_x;                 // compacted output
+  unsigned long long* seg_cursor;
+};
+
+__global__ void __launch_bounds__(PSD_WARPS_PER_BLOCK * 32)
+fpop_backtrack_kernel(const BtKernelParams P) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= P.n_order) return;
+  const int id = P.order[warp];
+  DpResult* res = &P.results[id];
+  if (res->status != PSD_ST_OK) return;
+  const DpProblem pb = P.problems[id];
+  int* srow = P.scratch_row + P.seg_scratch_off[id];
+  double* sx = P.scratch_x + P.seg_scratch_off[id];
+  backtrack_problem(P.pool, pb.index, pb.n_rows, res, srow, sx);
+  __syncwarp();
+  __threadfence_block();
+  const int ns = __shfl_sync(0xffffffffu, (lane == 0) ? res->n_segments : 0, 0);
+  const int st = __shfl_sync(0xffffffffu, (lane == 0) ? res->status : 0, 0);
+  if (st != PSD_ST_OK) return;
+  unsigned long long off = 0;
+  if (lane == 0) { off = atomicAdd(P.seg_cursor, (unsigned long long)ns); res->seg_offset = off; }
+  off = __shfl_sync(0xffffffffu, off, 0);
+  for (int s = lane; s < ns; s += 32) {
+    P.seg_x[off + s] = sx[s];
+    P.seg_row[off + s] = (s < ns - 1) ? srow[s] : -1;
+  }
+}
+
+// ---- plan ---------------------------------------------------------------------------------------
+namespace {
+thread_local std::string g_last_error;
+std::mutex g_opt_mutex;
+struct Options { int piece_cap = 64; int overflow_cap = 8192; double store_gb = 0; int chunk_kb = 64; int max_warps_per_sm = 0; } g_opt;
+
+bool cuda_ok(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return true;
+  g_last_error = std::string(what) + ": " + cudaGetErrorString(e);
+  return false;
+}
+#define CK(call) do { if (!cuda_ok((call), #call)) return PSD_ERR_CUDA; } while (0)
+
+template <class T> void dfree(T*& p) { if (p) cudaFree(p); p = nullptr; }
+}  // namespace
+
+void psd_set_last_error(const std::string& s) { g_last_error = s; }
+const std::string& psd_get_last_error() { return g_last_error; }
+
+int psd_set_option_impl(const char* name, double value) {
+  std::lock_guard<std::mutex> lk(g_opt_mutex);
+  std::string n(name);
+  if (n == "piece_cap") g_opt.piece_cap = (int)value;
+  else if (n == "overflow_cap") g_opt.overflow_cap = (int)value;
+  else if (n == "store_gb") g_opt.store_gb = value;
+  else if (n == "chunk_kb") g_opt.chunk_kb = (int)value;
+  else if (n == "max_warps_per_sm") g_opt.max_warps_per_sm = (int)value;
+  else return PSD_ERR_ARG;
+  return 0;
+}
+
+struct psd_plan {
+  int device = 0;
+  Options opt;
+  cudaDeviceProp prop;
+  // host side
+  std::vector<HostProblem> probs;
+  std::vector<int32_t> h_weight, h_cov;        // packed rows of the non-trivial problems
+  // device side
+  int *d_weight = nullptr, *d_cov = nullptr;
+  unsigned long long* d_index = nullptr;
+  DpProblem* d_problems = nullptr;
+  DpResult* d_results = nullptr;
+  int* d_order = nullptr;
+  int* d_queue = nullptr;
+  unsigned long long* d_cursors = nullptr;     // [0] store chunk cursor, [1] segment cursor
+  unsigned long long* d_seg_scratch_off = nullptr;
+  int *d_scratch_row = nullptr, *d_seg_row = nullptr;
+  double *d_scratch_x = nullptr, *d_seg_x = nullptr;
+  unsigned char* d_pool = nullptr; unsigned long long pool_bytes = 0;
+  unsigned char* d_gws = nullptr; unsigned long long gws_bytes = 0;
+  // pinned staging
+  int32_t *p_weight = nullptr, *p_cov = nullptr;
+  DpResult* p_results = nullptr;
+  int* p_seg_row = nullptr; double* p_seg_x = nullptr;
+  unsigned long long* p_cursors = nullptr;
+  size_t p_rows_cap = 0, p_res_cap = 0, p_seg_cap = 0;
+  // bookkeeping
+  std::vector<int> gpu_ids;                    // problem ids that go to the GPU
+  int64_t total_rows = 0;
+  bool uploaded = false, solved = false;
+  std::vector<DpResult> results;               // per gpu problem (indexed like gpu_ids)
+  std::vector<int> seg_row; std::vector<double> seg_x;
+  unsigned long long n_seg_total = 0;
+  psd_stats stats;
+  cudaEvent_t ev[8];
+  bool ev_ok = false;
+  int blocks_per_sm = 0, cap = 0, ccap = 0;
+  size_t smem_bytes = 0;
+
+  ~psd_plan() { release(); }
+  void release_device() {
+    dfree(d_weight); dfree(d_cov); dfree(d_index); dfree(d_problems); dfree(d_results); dfree(d_order);
+    dfree(d_queue); dfree(d_cursors); dfree(d_seg_scratch_off); dfree(d_scratch_row); dfree(d_seg_row);
+    dfree(d_scratch_x); dfree(d_seg_x); dfree(d_pool); dfree(d_gws);
+    uploaded = false;
+  }
+  void release() {
+    release_device();
+    if (p_weight) cudaFreeHost(p_weight); if (p_cov) cudaFreeHost(p_cov);
+    if (p_results) cudaFreeHost(p_results); if (p_seg_row) cudaFreeHost(p_seg_row);
+    if (p_seg_x) cudaFreeHost(p_seg_x); if (p_cursors) cudaFreeHost(p_cursors);
+    p_weight = p_cov = nullptr; p_results = nullptr; p_seg_row = nullptr; p_seg_x = nullptr; p_cursors = nullptr;
+    if (ev_ok) { for (auto& e : ev) cudaEventDestroy(e); ev_ok = false; }
+  }
+};
+
+psd_plan* psd_plan_create_impl(int device) {
+  // No CUDA call here: a plan holding only one-segment (trivial) problems never needs the device.
+  psd_plan* p = new psd_plan();
+  p->device = device;
+  { std::lock_guard<std::mutex> lk(g_opt_mutex); p->opt = g_opt; }
+  memset(&p->stats, 0, sizeof p->stats);
+  return p;
+}
+
+// First use of the device by this plan.  Fails loudly when there is no GPU: there is no CPU path.
+static int ensure_device(psd_plan* p) {
+  if (p->ev_ok) return cuda_ok(cudaSetDevice(p->device), "cudaSetDevice") ? 0 : PSD_ERR_CUDA;
+  int ndev = 0;
+  if (!cuda_ok(cudaGetDeviceCount(&ndev), "cudaGetDeviceCount")) return PSD_ERR_CUDA;
+  if (ndev == 0) { g_last_error = "no CUDA device"; return PSD_ERR_CUDA; }
+  if (p->device < 0) CK(cudaGetDevice(&p->device));
+  CK(cudaSetDevice(p->device));
+  CK(cudaGetDeviceProperties(&p->prop, p->device));
+  if (p->prop.major < 10) { g_last_error = "peaksegdisk_b200 is built for sm_100a only"; return PSD_ERR_CUDA; }
+  for (auto& e : p->ev) CK(cudaEventCreate(&e));
+  p->ev_ok = true;
+  return 0;
+}
+
+void psd_plan_destroy_impl(psd_plan* p) { if (p) { if (p->ev_ok) cudaSetDevice(p->device); delete p; } }
+
+std::vector<HostProblem>& psd_plan_problems(psd_plan* p) { return p->probs; }
+const std::vector<HostProblem>& psd_plan_problems_c(const psd_plan* p) { return p->probs; }
+void psd_plan_invalidate(psd_plan* p) { p->uploaded = false; p->solved = false; }
+void psd_plan_mark_penalty_changed(psd_plan* p) { p->solved = false; }
+const psd_stats& psd_plan_stats_ref(const psd_plan* p) { return p->stats; }
+
+// H2D: pack the rows of the non-trivial problems, allocate index / result / segment buffers.
+int psd_plan_upload_impl(psd_plan* p, void* stream_v) {
+  cudaStream_t st = (cudaStream_t)stream_v;
+  if (p->ev_ok) { CK(cudaSetDevice(p->device)); p->release_device(); }
+  p->gpu_ids.clear();
+  int64_t total = 0;
+  for (size_t i = 0; i < p->probs.size(); i++) {
+    HostProblem& hp = p->probs[i];
+    if (hp.status == 0 && !hp.trivial) { hp.row_off = total; total += hp.n_rows; p->gpu_ids.push_back((int)i); }
+  }
+  p->total_rows = total;
+  p->stats.h2d_bytes = 0; p->stats.h2d_ms = 0;
+  const size_t ng = p->gpu_ids.size();
+  if (ng == 0) { p->uploaded = true; p->solved = false; return 0; }
+  { const int rc = ensure_device(p); if (rc) return rc; }
+  if ((size_t)total > p->p_rows_cap) {
+    if (p->p_weight) cudaFreeHost(p->p_weight); if (p->p_cov) cudaFreeHost(p->p_cov);
+    CK(cudaMallocHost(&p->p_weight, sizeof(int32_t) * total));
+    CK(cudaMallocHost(&p->p_cov, sizeof(int32_t) * total));
+    p->p_rows_cap = total;
+  }
+  for (int id : p->gpu_ids) {
+    const HostProblem& hp = p->probs[id];
+    memcpy(p->p_weight + hp.row_off, hp.weight.data(), sizeof(int32_t) * hp.n_rows);
+    memcpy(p->p_cov + hp.row_off, hp.coverage.data(), sizeof(int32_t) * hp.n_rows);
+  }
+  CK(cudaMalloc(&p->d_weight, sizeof(int) * total));
+  CK(cudaMalloc(&p->d_cov, sizeof(int) * total));
+  CK(cudaMalloc(&p->d_index, sizeof(unsigned long long) * total));
+  CK(cudaMalloc(&p->d_problems, sizeof(DpProblem) * ng));
+  CK(cudaMalloc(&p->d_results, sizeof(DpResult) * ng));
+  CK(cudaMalloc(&p->d_order, sizeof(int) * ng));
+  CK(cudaMalloc(&p->d_queue, sizeof(int) * 4));
+  CK(cudaMalloc(&p->d_cursors, sizeof(unsigned long long) * 4));
+  CK(cudaMalloc(&p->d_seg_scratch_off, sizeof(unsigned long long) * ng));
+  CK(cudaMalloc(&p->d_scratch_row, sizeof(int) * (total + ng)));
+  CK(cudaMalloc(&p->d_scratch_x, sizeof(double) * (total + ng)));
+  CK(cudaMalloc(&p->d_seg_row, sizeof(int) * (total + ng)));
+  CK(cudaMalloc(&p->d_seg_x, sizeof(double) * (total + ng)));
+  if (ng > p->p_res_cap) {
+    if (p->p_results) cudaFreeHost(p->p_results);
+    CK(cudaMallocHost(&p->p_results, sizeof(DpResult) * ng));
+    p->p_res_cap = ng;
+  }
+  if ((size_t)(total + ng) > p->p_seg_cap) {
+    if (p->p_seg_row) cudaFreeHost(p->p_seg_row); if (p->p_seg_x) cudaFreeHost(p->p_seg_x);
+    CK(cudaMallocHost(&p->p_seg_row, sizeof(int) * (total + ng)));
+    CK(cudaMallocHost(&p->p_seg_x, sizeof(double) * (total + ng)));
+    p->p_seg_cap = total + ng;
+  }
+  if (!p->p_cursors) CK(cudaMallocHost(&p->p_cursors, sizeof(unsigned long long) * 4));
+  // store pool: sized from free memory unless the option pins it
+  size_t free_b = 0, total_b = 0;
+  CK(cudaMemGetInfo(&free_b, &total_b));
+  unsigned long long want;
+  if (p->opt.store_gb > 0) want = (unsigned long long)(p->opt.store_gb * (double)(1ull << 30));
+  else {
+    // estimate: 16 B header + 20 B x ~2x16 pieces per row, x1.5 headroom; clamp to 80% of free memory
+    want = (unsigned long long)total * 1000ull + (64ull << 20);
+    const unsigned long long lim = (unsigned long long)((double)free_b * 0.80);
+    if (want > lim) want = lim;
+  }
+  const unsigned long long chunk = (unsigned long long)p->opt.chunk_kb << 10;
+  want = (want / chunk) * chunk;
+  if (want < chunk * 16) want = chunk * 16;
+  CK(cudaMalloc(&p->d_pool, want));
+  p->pool_bytes = want;
+  // device problem descriptors
+  std::vector<DpProblem> hp(ng);
+  std::vector<unsigned long long> soff(ng);
+  for (size_t g = 0; g < ng; g++) {
+    const HostProblem& h = p->probs[p->gpu_ids[g]];
+    hp[g].weight = p->d_weight + h.row_off; hp[g].coverage = p->d_cov + h.row_off;
+    hp[g].n_rows = (int)h.n_rows; hp[g].penalty = h.penalty; hp[g].dmin = h.dmin; hp[g].dmax = h.dmax;
+    hp[g].index = p->d_index + h.row_off;
+    soff[g] = (unsigned long long)h.row_off + g;
+  }
+  CK(cudaEventRecord(p->ev[0], st));
+  CK(cudaMemcpyAsync(p->d_weight, p->p_weight, sizeof(int) * total, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(p->d_cov, p->p_cov, sizeof(int) * total, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(p->d_problems, hp.data(), sizeof(DpProblem) * ng, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(p->d_seg_scratch_off, soff.data(), sizeof(unsigned long long) * ng, cudaMemcpyHostToDevice, st));
+  CK(cudaEventRecord(p->ev[1], st));
+  CK(cudaStreamSynchronize(st));   // hp/soff are pageable temporaries
+  float ms = 0; cudaEventElapsedTime(&ms, p->ev[0], p->ev[1]);
+  p->stats.h2d_ms = ms;
+  p->stats.h2d_bytes = (int64_t)(2 * sizeof(int) * total + (sizeof(DpProblem) + 8) * ng);
+  p->uploaded = true; p->solved = false;
+  return 0;
+}
+
+static int configure_kernel(psd_plan* p) {
+  if (p->blocks_per_sm) return 0;
+  int cap = p->opt.piece_cap;
+  if (cap < 8) cap = 8;
+  cap = (cap + 1) & ~1;
+  for (;;) {
+    const int ccap = 2 * cap;
+    const size_t smem = PSD_TAB_BYTES + PSD_WARPS_PER_BLOCK * psd_ws_bytes(cap, ccap);
+    if (smem <= (size_t)p->prop.sharedMemPerBlockOptin) {
+      CK(cudaFuncSetAttribute(fpop_dp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      int nb = 0;
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fpop_dp_kernel, PSD_WARPS_PER_BLOCK * 32, smem));
+      if (nb >= 1) {
+        if (p->opt.max_warps_per_sm > 0) nb = std::max(1, std::min(nb, p->opt.max_warps_per_sm / PSD_WARPS_PER_BLOCK));
+        p->blocks_per_sm = nb; p->cap = cap; p->ccap = ccap; p->smem_bytes = smem;
+        return 0;
+      }
+    }
+    cap /= 2;
+    if (cap < 8) { g_last_error = "cannot fit the DP kernel's shared memory"; return PSD_ERR_CUDA; }
+  }
+}
+
+// DP + backtrack for every uploaded problem.  Device-only: no host<->device row traffic.
+int psd_plan_solve_impl(psd_plan* p, void* stream_v) {
+  cudaStream_t st = (cudaStream_t)stream_v;
+  if (!p->uploaded) { g_last_error = "psd_plan_solve before psd_plan_upload"; return PSD_ERR_ARG; }
+  const size_t ng = p->gpu_ids.size();
+  if (ng) CK(cudaSetDevice(p->device));
+  psd_stats& S = p->stats;
+  S.dp_ms = S.backtrack_ms = 0; S.n_launches = 0; S.n_waves = 0; S.n_overflow_tier = 0;
+  S.rows_solved = 0; S.store_bytes_algorithmic = 0; S.store_bytes_written = 0; S.backtrack_bytes_read = 0;
+  p->results.assign(ng, DpResult());
+  p->n_seg_total = 0;
+  if (ng == 0) { p->solved = true; return 0; }
+  int rc = configure_kernel(p);
+  if (rc) return rc;
+  S.piece_cap = p->cap; S.warps_per_sm = p->blocks_per_sm * PSD_WARPS_PER_BLOCK; S.n_sm = p->prop.multiProcessorCount;
+  // penalties may have changed since upload (sequential search): refresh the descriptors' penalty
+  {
+    std::vector<DpProblem> hp(ng);
+    for (size_t g = 0; g < ng; g++) {
+      const HostProblem& h = p->probs[p->gpu_ids[g]];
+      hp[g].weight = p->d_weight + h.row_off; hp[g].coverage = p->d_cov + h.row_off;
+      hp[g].n_rows = (int)h.n_rows; hp[g].penalty = h.penalty; hp[g].dmin = h.dmin; hp[g].dmax = h.dmax;
+      hp[g].index = p->d_index + h.row_off;
+    }
+    CK(cudaMemcpyAsync(p->d_problems, hp.data(), sizeof(DpProblem) * ng, cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));
+  }
+  const unsigned long long chunk = (unsigned long long)p->opt.chunk_kb << 10;
+  std::vector<int> todo(ng);            // problems of the wave about to run (current tier)
+  for (size_t g = 0; g < ng; g++) todo[g] = (int)g;
+  std::sort(todo.begin(), todo.end(), [&](int a, int b) {
+    const int64_t na = p->probs[p->gpu_ids[a]].n_rows, nb = p->probs[p->gpu_ids[b]].n_rows;
+    return na != nb ? na > nb : a < b;
+  });
+  std::vector<int> deferred;            // same tier, waiting for the store pool to be recycled
+  std::vector<int> overflow_acc;        // need the next piece-list tier
+  CK(cudaMemsetAsync(p->d_cursors, 0, sizeof(unsigned long long) * 4, st));
+  bool global_tier = false;
+  int gcap = p->opt.overflow_cap;
+  if (gcap > 32768) gcap = 32768;
+  for (int guard = 0;; guard++) {
+    if (guard > 4096) { g_last_error = "solve did not converge"; return PSD_ERR_INTERNAL; }
+    if (todo.empty()) {
+      if (!deferred.empty()) todo.swap(deferred);
+      else if (!overflow_acc.empty()) {
+        if (global_tier) {
+          if (gcap >= 32768) {   // largest tier exhausted: report status 101 for these problems
+            for (int g : overflow_acc) { p->results[g] = DpResult(); p->results[g].status = PSD_ST_PIECE_OVERFLOW; }
+            overflow_acc.clear();
+            continue;
+          }
+          gcap *= 2;
+        } else {
+          S.n_overflow_tier += (int)overflow_acc.size();
+        }
+        global_tier = true;
+        todo.swap(overflow_acc);
+      } else break;
+    }
+    const int n = (int)todo.size();
+    DpKernelParams K;
+    K.problems = p->d_problems; K.order = p->d_order; K.n_order = n; K.queue = p->d_queue; K.results = p->d_results;
+    K.pool.base = p->d_pool; K.pool.cursor = p->d_cursors; K.pool.n_chunks = p->pool_bytes / chunk; K.pool.chunk_bytes = chunk;
+    int grid; size_t smem;
+    if (!global_tier) {
+      K.cap = p->cap; K.ccap = p->ccap; K.gws = nullptr; K.ws_bytes_per_warp = psd_ws_bytes(K.cap, K.ccap);
+      smem = p->smem_bytes;
+      grid = p->prop.multiProcessorCount * p->blocks_per_sm;
+    } else {
+      K.cap = gcap; K.ccap = 3 * gcap; K.ws_bytes_per_warp = psd_ws_bytes(K.cap, K.ccap);
+      smem = PSD_TAB_BYTES;
+      int nb = 0;
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fpop_dp_kernel, PSD_WARPS_PER_BLOCK * 32, smem));
+      grid = p->prop.multiProcessorCount * std::max(1, nb);
+    }
+    grid = std::max(1, std::min(grid, (n + PSD_WARPS_PER_BLOCK - 1) / PSD_WARPS_PER_BLOCK));
+    if (global_tier) {
+      const unsigned long long need = (unsigned long long)grid * PSD_WARPS_PER_BLOCK * K.ws_bytes_per_warp;
+      if (need > p->gws_bytes) { dfree(p->d_gws); CK(cudaMalloc(&p->d_gws, need)); p->gws_bytes = need; }
+      K.gws = p->d_gws;
+    }
+    CK(cudaMemcpyAsync(p->d_order, todo.data(), sizeof(int) * n, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(p->d_queue, 0, sizeof(int) * 4, st));
+    CK(cudaMemsetAsync(p->d_cursors, 0, sizeof(unsigned long long), st));   // recycle the store pool
+    CK(cudaEventRecord(p->ev[2], st));
+    fpop_dp_kernel<<<grid, PSD_WARPS_PER_BLOCK * 32, smem, st>>>(K);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(p->ev[3], st));
+    BtKernelParams B;
+    B.problems = p->d_problems; B.order = p->d_order; B.n_order = n; B.results = p->d_results; B.pool = p->d_pool;
+    B.seg_scratch_off = p->d_seg_scratch_off; B.scratch_row = p->d_scratch_row; B.scratch_x = p->d_scratch_x;
+    B.seg_row = p->d_seg_row; B.seg_x = p->d_seg_x; B.seg_cursor = p->d_cursors + 1;
+    fpop_backtrack_kernel<<<(n + PSD_WARPS_PER_BLOCK - 1) / PSD_WARPS_PER_BLOCK, PSD_WARPS_PER_BLOCK * 32, 0, st>>>(B);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(p->ev[4], st));
+    S.n_launches += 2; S.n_waves++;
+    // the wave's status words decide what (if anything) has to be re-run
+    CK(cudaMemcpyAsync(p->p_results, p->d_results, sizeof(DpResult) * ng, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(p->p_cursors, p->d_cursors, sizeof(unsigned long long) * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, p->ev[2], p->ev[3]); S.dp_ms += ms;
+    cudaEventElapsedTime(&ms, p->ev[3], p->ev[4]); S.backtrack_ms += ms;
+    S.store_bytes_written += (int64_t)(std::min<unsigned long long>(p->p_cursors[0], K.pool.n_chunks) * chunk);
+    std::vector<int> exhausted;
+    for (int g : todo) {
+      const DpResult& r = p->p_results[g];
+      if (r.status == PSD_ST_PIECE_OVERFLOW) overflow_acc.push_back(g);
+      else if (r.status == PSD_ST_STORE_EXHAUSTED) exhausted.push_back(g);
+      else p->results[g] = r;
+    }
+    if (!exhausted.empty() && (int)exhausted.size() == n) {   // the pool held none of them
+      if (n == 1) { p->results[exhausted[0]] = p->p_results[exhausted[0]]; exhausted.clear(); }
+      else {
+        const int h = (n + 1) / 2;
+        deferred.insert(deferred.end(), exhausted.begin() + h, exhausted.end());
+        exhausted.resize(h);
+      }
+    }
+    todo.swap(exhausted);
+  }
+  // algorithmic bytes: per problem N*24 + 20*total_intervals
+  for (size_t g = 0; g < ng; g++) {
+    const DpResult& r = p->results[g];
+    const HostProblem& h = p->probs[p->gpu_ids[g]];
+    if (r.status == 0) {
+      S.rows_solved += h.n_rows;
+      S.store_bytes_algorithmic += h.n_rows * 24 + 20 * (int64_t)r.total_intervals;
+      S.backtrack_bytes_read += (int64_t)r.n_segments * 16;   // + 20 B per piece read, unknown here
+    }
+  }
+  p->n_seg_total = p->p_cursors[1];
+  p->solved = true;
+  return 0;
+}
+
+int psd_plan_download_impl(psd_plan* p, void* stream_v) {
+  cudaStream_t st = (cudaStream_t)stream_v;
+  if (!p->solved) { g_last_error = "psd_plan_download before psd_plan_solve"; return PSD_ERR_ARG; }
+  const size_t ng = p->gpu_ids.size();
+  if (ng) CK(cudaSetDevice(p->device));
+  p->stats.d2h_bytes = 0; p->stats.d2h_ms = 0;
+  if (ng) {
+    const unsigned long long ns = p->n_seg_total;
+    CK(cudaEventRecord(p->ev[5], st));
+    if (ns) {
+      CK(cudaMemcpyAsync(p->p_seg_row, p->d_seg_row, sizeof(int) * ns, cudaMemcpyDeviceToHost, st));
+      CK(cudaMemcpyAsync(p->p_seg_x, p->d_seg_x, sizeof(double) * ns, cudaMemcpyDeviceToHost, st));
+    }
+    CK(cudaEventRecord(p->ev[6], st));
+    CK(cudaStreamSynchronize(st));
+    float ms = 0; cudaEventElapsedTime(&ms, p->ev[5], p->ev[6]);
+    p->stats.d2h_ms = ms;
+    p->stats.d2h_bytes = (int64_t)(12 * ns + sizeof(DpResult) * ng);
+  }
+  // fill the host problems' results
+  for (size_t g = 0; g < ng; g++) {
+    HostProblem& h = p->probs[p->gpu_ids[g]];
+    const DpResult& r = p->results[g];
+    h.seg_row.clear(); h.seg_x.clear();
+    if (r.status != 0) { h.result_status = r.status; continue; }
+    h.result_status = 0;
+    h.n_segments = r.n_segments; h.n_equality = r.n_equality;
+    h.best_cost = r.best_cost; h.total_intervals = (double)r.total_intervals; h.max_intervals = r.max_intervals;
+    h.seg_row.assign(p->p_seg_row + r.seg_offset, p->p_seg_row + r.seg_offset + r.n_segments);
+    h.seg_x.assign(p->p_seg_x + r.seg_offset, p->p_seg_x + r.seg_offset + r.n_segments);
+  }
+  return 0;
+}
+
+int psd_device_count_impl() {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}

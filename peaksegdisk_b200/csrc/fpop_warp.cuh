@@ -756,6 +756,7 @@ struct DpResult {
   int n_segments;
   int n_equality;
   int pad_;
+  unsigned long long seg_offset;   // where the backtrack kernel put this problem's segments
 };
 
 // optional per-row trace for tests (null in production): called by lane 0 after every row

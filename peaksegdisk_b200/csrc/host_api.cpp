@@ -1,0 +1,444 @@
+// host_api.cpp -- the C ABI (include/peaksegdisk_b200.h): penalty / bedGraph text front end with the
+// reference's validation order and status codes, the result writers reproducing the reference's
+// iostream formatting, and the thin glue onto the device plan (fpop_gpu.cu).
+//
+// Reference behaviour mirrored here (file:line into tdhock/PeakSegDisk):
+//   penalty parsing and its error order      src/PeakSegFPOPLog.cpp:145-159
+//   bedGraph pass 1 (validation + totals)    src/PeakSegFPOPLog.cpp:160-209
+//   output file creation before any solve    src/PeakSegFPOPLog.cpp:212-223
+//   trivial one-segment model                src/PeakSegFPOPLog.cpp:224-243
+//   segments / loss lines                    src/PeakSegFPOPLog.cpp:419-454
+//   output failure checks                    src/PeakSegFPOPLog.cpp:456-461
+//   status -> message                        src/interface.cpp:16-55
+#include <cerrno>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+#include "psd_math.h"
+#include "plan_internal.h"
+
+namespace {
+
+inline double hlog(double x) { return psd_log(x, psd_log_tab_host); }
+inline double hexp(double x) { return psd_exp(x, psd_exp_tab_host); }
+
+int parse_penalty(const char* s, double* pen, bool* is_inf) {
+  *is_inf = strcmp(s, "Inf") == 0;
+  try { *pen = std::stod(s); }
+  catch (const std::invalid_argument&) { return PSD_ERR_PENALTY_NOT_NUMERIC; }
+  catch (const std::out_of_range&) { return PSD_ERR_PENALTY_NOT_FINITE; }  // the reference aborts (uncaught); documented deviation
+  if (*is_inf) return 0;
+  if (!std::isfinite(*pen)) return PSD_ERR_PENALTY_NOT_FINITE;
+  if (*pen < 0) return PSD_ERR_PENALTY_NEGATIVE;
+  return 0;
+}
+
+inline bool is_ws(unsigned char c) { return c == ' ' || (c >= '\t' && c <= '\r'); }
+
+// One integer field with sscanf("%d") semantics: optional whitespace, optional sign, decimal digits,
+// value clamped to long then truncated to int.  Returns false on a matching failure.
+inline bool scan_int(const char*& p, const char* end, int* out) {
+  while (p < end && is_ws((unsigned char)*p)) p++;
+  if (p >= end) return false;
+  bool neg = false;
+  const char* q = p;
+  if (*q == '+' || *q == '-') { neg = (*q == '-'); q++; }
+  if (q >= end || *q < '0' || *q > '9') return false;
+  unsigned long long v = 0;
+  bool over = false;
+  while (q < end && *q >= '0' && *q <= '9') {
+    if (v > (0x7fffffffffffffffULL - 9) / 10) over = true; else v = v * 10 + (unsigned)(*q - '0');
+    q++;
+  }
+  long long sv;
+  if (over) sv = neg ? (long long)0x8000000000000000ULL : 0x7fffffffffffffffLL;
+  else sv = neg ? -(long long)v : (long long)v;
+  *out = (int)sv;
+  p = q;
+  return true;
+}
+
+struct Parsed {
+  int status = 0;
+  int bad_items = 0, bad_line = 0;
+  std::string chrom;
+  std::vector<int32_t> start, end, cov;
+};
+
+// Pass 1 of the reference with its first-error semantics; the text is scanned once.
+void parse_bedgraph(const char* path, Parsed& P) {
+  FILE* f = fopen(path, "rb");
+  if (!f) { P.status = PSD_ERR_UNABLE_TO_OPEN_BEDGRAPH; return; }
+  std::vector<char> buf;
+  {
+    char tmp[1 << 16];
+    size_t n;
+    while ((n = fread(tmp, 1, sizeof tmp, f)) > 0) buf.insert(buf.end(), tmp, tmp + n);
+  }
+  const bool rd_err = ferror(f) != 0;
+  fclose(f);
+  if (rd_err && buf.empty()) { P.status = PSD_ERR_UNABLE_TO_OPEN_BEDGRAPH; return; }
+  const char* p = buf.data();
+  const char* const fend = p + buf.size();
+  int line_i = 0, prev_end = -1;
+  const char* chrom_b = nullptr; const char* chrom_e = nullptr;
+  while (p < fend) {
+    const char* nl = (const char*)memchr(p, '\n', (size_t)(fend - p));
+    const char* lend = nl ? nl : fend;
+    const char* nul = (const char*)memchr(p, '\0', (size_t)(lend - p));
+    const char* e = nul ? nul : lend;
+    line_i++;
+    const char* q = p;
+    int items = 0;
+    int cs = 0, ce = 0, cv = 0;
+    while (q < e && is_ws((unsigned char)*q)) q++;
+    if (q >= e) items = -1;   // sscanf returns EOF on an empty line
+    else {
+      chrom_b = q;
+      while (q < e && !is_ws((unsigned char)*q)) q++;
+      chrom_e = q;
+      items = 1;
+      if (scan_int(q, e, &cs)) { items = 2; if (scan_int(q, e, &ce)) { items = 3; if (scan_int(q, e, &cv)) items = 4; } }
+    }
+    if (items < 4) { P.status = PSD_ERR_NOT_ENOUGH_COLUMNS; P.bad_items = items; P.bad_line = line_i; return; }
+    while (q < e && is_ws((unsigned char)*q)) q++;
+    if (q < e) { P.status = PSD_ERR_NON_INTEGER_DATA; return; }   // "%d%s": trailing text after the 4th column
+    if (line_i > 1 && cs != prev_end) { P.status = PSD_ERR_INCONSISTENT_CHROMSTART_CHROMEND; return; }
+    prev_end = ce;
+    P.start.push_back(cs); P.end.push_back(ce); P.cov.push_back(cv);
+    p = nl ? nl + 1 : fend;
+  }
+  if (line_i == 0) { P.status = PSD_ERR_NO_DATA; return; }
+  size_t len = (size_t)(chrom_e - chrom_b);
+  P.chrom.assign(chrom_b, len);
+}
+
+// Fills the derived fields of a problem from its rows (pass-1 totals, log range, triviality).
+void finish_problem(HostProblem& h) {
+  const int64_t n = h.n_rows;
+  h.weight.resize(n);
+  double W = 0, SWZ = 0, xmin = INFINITY, xmax = -INFINITY;
+  int32_t last_cov = 0; double last_log = 0; bool have = false;
+  for (int64_t t = 0; t < n; t++) {
+    const int32_t wi = h.chrom_end[t] - h.chrom_start[t];
+    h.weight[t] = wi;
+    const double w = (double)wi;
+    W += w;
+    SWZ += w * h.coverage[t];
+    const int32_t z = h.coverage[t];
+    if (!have || z != last_cov) { last_log = hlog((double)z); last_cov = z; have = true; }
+    if (last_log < xmin) xmin = last_log;
+    if (xmax < last_log) xmax = last_log;
+  }
+  h.bases = W; h.sum_wz = SWZ; h.dmin = xmin; h.dmax = xmax;
+  h.trivial = h.penalty_is_inf || xmin == xmax;
+}
+
+void format_g(std::string& out, const char* fmt, double v) {
+  char b[64];
+  snprintf(b, sizeof b, fmt, v);
+  out += b;
+}
+
+// text of <prefix>_segments.bed and <prefix>_loss.tsv for a solved problem
+void render(const HostProblem& h, const std::string& chrom, const char* penalty_str,
+            std::string& seg_txt, std::string& loss_txt) {
+  char ib[64];
+  const int64_t n = h.n_rows;
+  if (h.trivial) {
+    const double SWZ = h.sum_wz, W = h.bases;
+    const double bc = (SWZ != 0) ? SWZ * (1 - hlog(SWZ) + hlog(W)) : 0;
+    seg_txt = chrom; seg_txt += "\t";
+    snprintf(ib, sizeof ib, "%d\t%d\tbackground\t", h.chrom_start[0], h.chrom_end[n - 1]); seg_txt += ib;
+    format_g(seg_txt, "%g", SWZ / W); seg_txt += "\n";
+    loss_txt = penalty_str;
+    snprintf(ib, sizeof ib, "\t1\t0\t%d\t%d\t", (int)W, (int)n); loss_txt += ib;
+    format_g(loss_txt, "%.20g", bc / W); loss_txt += "\t";
+    format_g(loss_txt, "%.20g", bc); loss_txt += "\t0\t0\t0\n";
+    return;
+  }
+  const int ns = h.n_segments;
+  int prev_end = h.chrom_end[n - 1];
+  seg_txt.clear();
+  for (int s = 0; s < ns; s++) {
+    const int st = (s < ns - 1) ? h.chrom_end[h.seg_row[s]] : h.chrom_start[0];
+    seg_txt += chrom;
+    snprintf(ib, sizeof ib, "\t%d\t%d\t%s\t", st, prev_end, (s & 1) ? "peak" : "background"); seg_txt += ib;
+    format_g(seg_txt, "%g", hexp(h.seg_x[s])); seg_txt += "\n";
+    prev_end = st;
+  }
+  const int n_peaks = (ns - 1) / 2;
+  loss_txt.clear();
+  format_g(loss_txt, "%.20g", h.penalty);
+  snprintf(ib, sizeof ib, "\t%d\t%d\t%d\t%d\t", ns, n_peaks, (int)h.bases, (int)n); loss_txt += ib;
+  format_g(loss_txt, "%.20g", h.best_cost); loss_txt += "\t";
+  format_g(loss_txt, "%.20g", h.best_cost * h.bases - h.penalty * n_peaks);
+  snprintf(ib, sizeof ib, "\t%d\t", h.n_equality); loss_txt += ib;
+  format_g(loss_txt, "%.20g", h.total_intervals / (double)((int)n * 2)); loss_txt += "\t";
+  format_g(loss_txt, "%.20g", h.max_intervals); loss_txt += "\n";
+}
+
+bool write_all(FILE* f, const std::string& s) {
+  if (!f) return false;
+  bool ok = s.empty() || fwrite(s.data(), 1, s.size(), f) == s.size();
+  if (fflush(f) != 0) ok = false;
+  return ok;
+}
+
+struct FileJob {
+  std::string bedgraph, penalty_str, db;
+  int status = 0;
+  double penalty = 0; bool is_inf = false;
+  std::shared_ptr<Parsed> parsed;
+  FILE* loss_f = nullptr; FILE* seg_f = nullptr;
+  int plan_id = -1;
+};
+
+void close_job(FileJob& j) {
+  if (j.loss_f) fclose(j.loss_f);
+  if (j.seg_f) fclose(j.seg_f);
+  j.loss_f = j.seg_f = nullptr;
+}
+
+int run_file_batch(int n, const char* const* bedgraphs, const char* const* penalties, const char* const* dbs, int* status_out) {
+  std::vector<FileJob> jobs(n);
+  std::map<std::string, std::shared_ptr<Parsed>> cache;   // several penalties on one bedGraph parse it once
+  psd_plan* plan = nullptr;
+  int fatal = 0;
+  for (int i = 0; i < n; i++) {
+    FileJob& j = jobs[i];
+    j.bedgraph = bedgraphs[i]; j.penalty_str = penalties[i]; j.db = dbs[i];
+    j.status = parse_penalty(penalties[i], &j.penalty, &j.is_inf);
+    if (j.status) continue;
+    auto it = cache.find(j.bedgraph);
+    if (it == cache.end()) {
+      auto P = std::make_shared<Parsed>();
+      parse_bedgraph(bedgraphs[i], *P);
+      it = cache.emplace(j.bedgraph, P).first;
+    }
+    j.parsed = it->second;
+    j.status = j.parsed->status;
+    if (j.status == PSD_ERR_NOT_ENOUGH_COLUMNS)
+      printf("problem: %d items on line %d\n", j.parsed->bad_items, j.parsed->bad_line);
+    if (j.status) continue;
+    // outputs are created (empty) before anything else can fail, as the reference does
+    const std::string prefix = j.bedgraph + "_penalty=" + j.penalty_str;
+    j.loss_f = fopen((prefix + "_loss.tsv").c_str(), "wb");
+    j.seg_f = fopen((prefix + "_segments.bed").c_str(), "wb");
+  }
+  // build the plan
+  for (int i = 0; i < n; i++) {
+    FileJob& j = jobs[i];
+    if (j.status) continue;
+    if (!plan) {
+      plan = psd_plan_create_impl(-1);
+      if (!plan) { fatal = PSD_ERR_CUDA; break; }
+    }
+    const Parsed& P = *j.parsed;
+    j.plan_id = psd_plan_add(plan, (int64_t)P.cov.size(), P.start.data(), P.end.data(), P.cov.data(), j.penalty, j.is_inf ? 1 : 0);
+    if (j.plan_id < 0) { j.status = -j.plan_id; continue; }
+    const HostProblem& h = psd_plan_problems(plan)[j.plan_id];
+    if (!h.trivial) {
+      // the reference creates its scratch db here; keep that contract (error 7 when unwritable)
+      FILE* d = fopen(j.db.c_str(), "wb");
+      bool ok = d != nullptr;
+      if (ok) {
+        char hdr[64];
+        memset(hdr, 0, sizeof hdr);
+        snprintf(hdr, sizeof hdr, "PSD-B200 cost functions live in HBM; rows=%lld", (long long)h.n_rows);
+        ok = fwrite(hdr, 1, sizeof hdr, d) == sizeof hdr;
+        if (fclose(d) != 0) ok = false;
+      }
+      if (!ok) { j.status = PSD_ERR_WRITING_COST_FUNCTIONS; psd_plan_problems(plan)[j.plan_id].status = j.status; }
+    }
+  }
+  if (!fatal && plan) {
+    int rc = psd_plan_run(plan, nullptr);
+    if (rc) fatal = rc;
+  }
+  for (int i = 0; i < n; i++) {
+    FileJob& j = jobs[i];
+    if (!j.status && fatal) j.status = fatal;
+    if (!j.status) {
+      const HostProblem& h = psd_plan_problems(plan)[j.plan_id];
+      if (!h.trivial && h.result_status != 0) j.status = (h.result_status < 0) ? PSD_ERR_INTERNAL : h.result_status;
+      else {
+        std::string seg_txt, loss_txt;
+        render(h, j.parsed->chrom, j.penalty_str.c_str(), seg_txt, loss_txt);
+        const bool seg_ok = write_all(j.seg_f, seg_txt);
+        const bool loss_ok = write_all(j.loss_f, loss_txt);
+        if (!loss_ok) j.status = PSD_ERR_WRITING_LOSS_OUTPUT;
+        else if (!seg_ok) j.status = PSD_ERR_WRITING_SEGMENTS_OUTPUT;
+      }
+    }
+    close_job(j);
+    status_out[i] = j.status;
+  }
+  if (plan) psd_plan_destroy_impl(plan);
+  return fatal;
+}
+
+}  // namespace
+
+extern "C" {
+
+int psd_fpop_disk_batch(int n, const char* const* bedGraph_file_names, const char* const* penalty_strs,
+                        const char* const* db_file_names, int* status_out) {
+  if (n < 0 || (n > 0 && (!bedGraph_file_names || !penalty_strs || !db_file_names || !status_out))) return PSD_ERR_ARG;
+  if (n == 0) return 0;
+  return run_file_batch(n, bedGraph_file_names, penalty_strs, db_file_names, status_out);
+}
+
+int psd_fpop_disk(const char* bedGraph_file_name, const char* penalty_str, const char* db_file_name) {
+  if (!bedGraph_file_name || !penalty_str || !db_file_name) return PSD_ERR_ARG;
+  int st = -1;
+  const int rc = run_file_batch(1, &bedGraph_file_name, &penalty_str, &db_file_name, &st);
+  return st >= 0 ? st : rc;
+}
+
+const char* psd_status_message(int status) {
+  switch (status) {
+    case 0: return "ok";
+    case 1: return "penalty=%s but must be finite";
+    case 2: return "penalty=%s must be non-negative";
+    case 3: return "unable to open input file for reading %s";
+    case 4: return "each line of input data file %s should have exactly four columns";
+    case 5: return "fourth column of input data file %s should be integer";
+    case 6: return "there should be no gaps (columns 2-3) in input data file %s";
+    case 7: return "unable to write to cost function database file %s";
+    case 8: return "unable to write to loss output file %s_penalty=%s_loss.tsv";
+    case 9: return "input file %s contains no data";
+    case 10: return "penalty string '%s' is not numeric; it should be convertible to double";
+    case 11: return "unable to write to segments output file %s_penalty=%s_segments.bed";
+    case PSD_ERR_PIECE_OVERFLOW: return "a cost function outgrew the largest piece-list tier";
+    case PSD_ERR_STORE_EXHAUSTED: return "the HBM cost-function store cannot hold this problem";
+    case PSD_ERR_BACKTRACK: return "backtrack lost the optimal mean";
+    case PSD_ERR_INTERNAL: return "internal solver error";
+    case PSD_ERR_CUDA: return "CUDA error (no device, driver failure or kernel fault)";
+    case PSD_ERR_ARG: return "invalid argument";
+    default: return "error code %d";
+  }
+}
+
+const char* psd_last_error(void) { return psd_get_last_error().c_str(); }
+
+psd_plan* psd_plan_create(int device) { return psd_plan_create_impl(device); }
+void psd_plan_destroy(psd_plan* plan) { psd_plan_destroy_impl(plan); }
+
+int psd_plan_add(psd_plan* plan, int64_t n_rows, const int32_t* chromStart, const int32_t* chromEnd,
+                 const int32_t* coverage, double penalty, int penalty_is_inf) {
+  if (!plan || n_rows <= 0 || n_rows > 0x3fffffff || !chromStart || !chromEnd || !coverage) return -PSD_ERR_ARG;
+  if (!penalty_is_inf) {
+    if (!std::isfinite(penalty)) return -PSD_ERR_PENALTY_NOT_FINITE;
+    if (penalty < 0) return -PSD_ERR_PENALTY_NEGATIVE;
+  }
+  std::vector<HostProblem>& v = psd_plan_problems(plan);
+  v.emplace_back();
+  HostProblem& h = v.back();
+  h.n_rows = n_rows; h.penalty = penalty; h.penalty_is_inf = penalty_is_inf != 0;
+  h.chrom_start.assign(chromStart, chromStart + n_rows);
+  h.chrom_end.assign(chromEnd, chromEnd + n_rows);
+  h.coverage.assign(coverage, coverage + n_rows);
+  finish_problem(h);
+  psd_plan_invalidate(plan);
+  return (int)v.size() - 1;
+}
+
+int psd_plan_size(const psd_plan* plan) { return plan ? (int)psd_plan_problems_c(plan).size() : 0; }
+
+int psd_plan_set_penalty(psd_plan* plan, int id, double penalty, int penalty_is_inf) {
+  if (!plan) return PSD_ERR_ARG;
+  std::vector<HostProblem>& v = psd_plan_problems(plan);
+  if (id < 0 || id >= (int)v.size()) return PSD_ERR_ARG;
+  if (!penalty_is_inf) {
+    if (!std::isfinite(penalty)) return PSD_ERR_PENALTY_NOT_FINITE;
+    if (penalty < 0) return PSD_ERR_PENALTY_NEGATIVE;
+  }
+  HostProblem& h = v[id];
+  const bool was_trivial = h.trivial;
+  h.penalty = penalty; h.penalty_is_inf = penalty_is_inf != 0;
+  h.trivial = h.penalty_is_inf || h.dmin == h.dmax;
+  h.result_status = -1;
+  if (was_trivial != h.trivial) psd_plan_invalidate(plan);   // the set of GPU problems changed
+  else psd_plan_mark_penalty_changed(plan);
+  return 0;
+}
+
+int psd_plan_upload(psd_plan* plan, void* stream) { return plan ? psd_plan_upload_impl(plan, stream) : PSD_ERR_ARG; }
+int psd_plan_solve(psd_plan* plan, void* stream) { return plan ? psd_plan_solve_impl(plan, stream) : PSD_ERR_ARG; }
+int psd_plan_download(psd_plan* plan, void* stream) { return plan ? psd_plan_download_impl(plan, stream) : PSD_ERR_ARG; }
+
+int psd_plan_run(psd_plan* plan, void* stream) {
+  if (!plan) return PSD_ERR_ARG;
+  int rc = psd_plan_upload_impl(plan, stream);
+  if (!rc) rc = psd_plan_solve_impl(plan, stream);
+  if (!rc) rc = psd_plan_download_impl(plan, stream);
+  return rc;
+}
+
+int psd_plan_result(const psd_plan* plan, int id, psd_result* out) {
+  if (!plan || !out) return PSD_ERR_ARG;
+  const std::vector<HostProblem>& v = psd_plan_problems_c(plan);
+  if (id < 0 || id >= (int)v.size()) return PSD_ERR_ARG;
+  const HostProblem& h = v[id];
+  memset(out, 0, sizeof *out);
+  out->n_rows = (int32_t)h.n_rows; out->penalty = h.penalty; out->bases = h.bases; out->trivial = h.trivial ? 1 : 0;
+  if (h.status) { out->status = h.status; return 0; }
+  if (h.trivial) {
+    const double SWZ = h.sum_wz, W = h.bases;
+    const double bc = (SWZ != 0) ? SWZ * (1 - hlog(SWZ) + hlog(W)) : 0;
+    out->status = 0; out->n_segments = 1; out->n_peaks = 0; out->mean_pen_cost = bc / W; out->total_loss = bc;
+    if (h.penalty_is_inf) out->penalty = INFINITY;
+    return 0;
+  }
+  if (h.result_status != 0) { out->status = h.result_status < 0 ? PSD_ERR_ARG : h.result_status; return 0; }
+  const int np = (h.n_segments - 1) / 2;
+  out->n_segments = h.n_segments; out->n_peaks = np; out->n_equality = h.n_equality;
+  out->mean_pen_cost = h.best_cost; out->total_loss = h.best_cost * h.bases - h.penalty * np;
+  out->mean_intervals = h.total_intervals / (double)((int)h.n_rows * 2); out->max_intervals = h.max_intervals;
+  return 0;
+}
+
+int psd_plan_segments(const psd_plan* plan, int id, int32_t* chromStart, int32_t* chromEnd, int32_t* is_peak, double* mean) {
+  if (!plan) return PSD_ERR_ARG;
+  const std::vector<HostProblem>& v = psd_plan_problems_c(plan);
+  if (id < 0 || id >= (int)v.size()) return PSD_ERR_ARG;
+  const HostProblem& h = v[id];
+  const int64_t n = h.n_rows;
+  if (h.status) return h.status;
+  if (h.trivial) {
+    chromStart[0] = h.chrom_start[0]; chromEnd[0] = h.chrom_end[n - 1]; is_peak[0] = 0; mean[0] = h.sum_wz / h.bases;
+    return 0;
+  }
+  if (h.result_status != 0) return h.result_status < 0 ? PSD_ERR_ARG : h.result_status;
+  int prev_end = h.chrom_end[n - 1];
+  for (int s = 0; s < h.n_segments; s++) {
+    const int st = (s < h.n_segments - 1) ? h.chrom_end[h.seg_row[s]] : h.chrom_start[0];
+    chromStart[s] = st; chromEnd[s] = prev_end; is_peak[s] = s & 1; mean[s] = hexp(h.seg_x[s]);
+    prev_end = st;
+  }
+  return 0;
+}
+
+int psd_plan_get_stats(const psd_plan* plan, psd_stats* out) {
+  if (!plan || !out) return PSD_ERR_ARG;
+  *out = psd_plan_stats_ref(plan);
+  return 0;
+}
+
+int psd_set_option(const char* name, double value) { return name ? psd_set_option_impl(name, value) : PSD_ERR_ARG; }
+int psd_device_count(void) { return psd_device_count_impl(); }
+
+}  // extern "C"
+
+// The reference's own entry point, with its C++ linkage (src/PeakSegFPOPLog.h:15 declares it without
+// extern "C"), so an unmodified src/interface.cpp links against this library.
+int PeakSegFPOP_disk(char* bedGraph_file_name, char* penalty_str, char* db_file_name) {
+  return psd_fpop_disk(bedGraph_file_name, penalty_str, db_file_name);
+}

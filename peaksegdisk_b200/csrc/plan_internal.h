@@ -1,0 +1,41 @@
+// plan_internal.h -- host-side types shared by fpop_gpu.cu (device plan) and host_api.cpp (C ABI,
+// bedGraph text I/O).  Not installed; the public surface is include/peaksegdisk_b200.h.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+#include "../../include/peaksegdisk_b200.h"
+
+struct HostProblem {
+  int status = 0;                 // reference-style input status (0 ok)
+  bool trivial = false;           // one-segment model: penalty Inf or constant coverage
+  bool penalty_is_inf = false;
+  double penalty = 0;
+  int64_t n_rows = 0;
+  std::vector<int32_t> chrom_start, chrom_end, coverage, weight;
+  double bases = 0, sum_wz = 0;   // pass-1 totals (src/PeakSegFPOPLog.cpp:187-189)
+  double dmin = 0, dmax = 0;      // log(min coverage), log(max coverage)
+  int64_t row_off = 0;            // offset into the packed device row arrays
+  // results
+  int result_status = -1;         // -1 not solved yet
+  int n_segments = 0, n_equality = 0;
+  double best_cost = 0, total_intervals = 0, max_intervals = 0;
+  std::vector<int> seg_row;       // last row of the previous segment, last segment first (-1 for the first)
+  std::vector<double> seg_x;      // log-mean per segment
+};
+
+struct psd_plan;
+psd_plan* psd_plan_create_impl(int device);
+void psd_plan_destroy_impl(psd_plan* p);
+std::vector<HostProblem>& psd_plan_problems(psd_plan* p);
+const std::vector<HostProblem>& psd_plan_problems_c(const psd_plan* p);
+void psd_plan_invalidate(psd_plan* p);
+void psd_plan_mark_penalty_changed(psd_plan* p);
+const psd_stats& psd_plan_stats_ref(const psd_plan* p);
+int psd_plan_upload_impl(psd_plan* p, void* stream);
+int psd_plan_solve_impl(psd_plan* p, void* stream);
+int psd_plan_download_impl(psd_plan* p, void* stream);
+int psd_device_count_impl();
+int psd_set_option_impl(const char* name, double value);
+void psd_set_last_error(const std::string& s);
+const std::string& psd_get_last_error();

@@ -1,0 +1,52 @@
+import hashlib
+import json
+import os
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def golden(name):
+    return json.load(open(os.path.join(GOLD, name)))
+
+
+def sha(text):
+    return hashlib.sha256(text.encode()).hexdigest()
+
+
+def read_or_none(path):
+    return open(path).read() if os.path.exists(path) else None
+
+
+def outputs(bedgraph, pen):
+    return (read_or_none("%s_penalty=%s_segments.bed" % (bedgraph, pen)),
+            read_or_none("%s_penalty=%s_loss.tsv" % (bedgraph, pen)))
+
+
+def synth_rows(kind, key):
+    from peaksegdisk_b200 import synth
+    if kind == "poisson":
+        return synth.poisson_problem(key[0], key[1])
+    return synth.increasing_problem(key[0])
+
+
+def rows_text(s, e, c, chrom="chrUnknown"):
+    return "".join("%s\t%d\t%d\t%d\n" % (chrom, a, b, d) for a, b, d in zip(s.tolist(), e.tolist(), c.tolist()))
+
+
+def parse_rows(text):
+    """rows of a well-formed bedGraph text"""
+    s, e, c = [], [], []
+    for line in text.splitlines():
+        f = line.split()
+        if len(f) >= 4:
+            s.append(int(f[1])); e.append(int(f[2])); c.append(int(f[3]))
+    return np.array(s, np.int32), np.array(e, np.int32), np.array(c, np.int32)
+
+
+def loss_fields(line):
+    f = line.rstrip("\n").split("\t")
+    return {"penalty": f[0], "segments": int(f[1]), "peaks": int(f[2]), "bases": int(f[3]), "lines": int(f[4]),
+            "mean_pen_cost": float(f[5]), "total_loss": float(f[6]), "equality": int(f[7]),
+            "mean_intervals": float(f[8]), "max_intervals": float(f[9])}

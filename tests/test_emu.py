@@ -1,0 +1,59 @@
+"""The product's device source (peaksegdisk_b200/csrc/fpop_warp.cuh) executed under the CPU warp
+emulator (tests/emu: 32 fibers = 32 lanes; a TEST TOOL, not a product path) must reproduce the oracle
+bit for bit at every row: coefficients, breakpoints and back-pointers of both cost functions.
+Lane scheduling order is run both ascending and descending to expose missing warp syncs."""
+import os
+import subprocess
+import numpy as np
+import pytest
+from helpers import ROOT, golden, parse_rows
+import oracle_bind
+
+
+@pytest.fixture(scope="module")
+def ec():
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "tests", "emu")])
+    oracle_bind.ensure_built()
+    import emu_compare
+    return emu_compare
+
+
+def test_reference_vectors_row_by_row(ec):
+    for case in golden("golden_small.json"):
+        if case["status"] != 0 or case["penalty"] == "Inf":
+            continue
+        s, e, c = parse_rows(case["input"])
+        if len(set(c.tolist())) < 2:
+            continue   # constant coverage: trivial model, never reaches the kernel
+        assert ec.compare(s, e, c, float(case["penalty"]), cap=16, descending=0), (case["name"], case["penalty"])
+        assert ec.compare(s, e, c, float(case["penalty"]), cap=16, descending=1, trace=False), case["name"]
+
+
+@pytest.mark.parametrize("seed,n,pen", [(0, 1500, 0.0), (1, 1500, 4.0), (2, 2000, 100.0), (3, 1200, 1e4), (4, 900, 1e6)])
+def test_poisson_row_by_row(ec, seed, n, pen):
+    from peaksegdisk_b200 import synth
+    s, e, c = synth.poisson_problem(seed, n)
+    assert ec.compare(s, e, c, pen, cap=64, descending=seed & 1)
+
+
+@pytest.mark.parametrize("n,pen", [(100, 0.0), (200, 1e2), (300, 1e4), (300, 1e6)])
+def test_many_pieces_chunked_lists(ec, n, pen):
+    """increasing counts: > 32 pieces per function, exercising the chunked (multi-pass) loops"""
+    from peaksegdisk_b200 import synth
+    s, e, c = synth.increasing_problem(n)
+    assert ec.compare(s, e, c, pen, cap=512)
+
+
+def test_mono27ac_prefix(ec):
+    from peaksegdisk_b200 import synth
+    chrom, s, e, c = synth.read_bedgraph(os.path.join(ROOT, "tests", "golden", "Mono27ac_coverage.bedGraph"))
+    assert ec.compare(s[:2500], e[:2500], c[:2500], 10.5, cap=64)
+    assert ec.compare(s[:2500], e[:2500], c[:2500], 1952.6, cap=64, descending=1)
+
+
+def test_piece_overflow_is_reported(ec):
+    from peaksegdisk_b200 import synth
+    s, e, c = synth.increasing_problem(300)
+    orc, emu = ec.load()
+    st, _, _, _ = ec.run_emu(emu, s, e, c, 1e4, cap=16)
+    assert st == 101

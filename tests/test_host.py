@@ -1,0 +1,102 @@
+"""Host-side logic that needs no GPU: the C ABI exports, the bedGraph/penalty front end's status codes
+and created files, the trivial (one-segment) branch which the reference also solves in closed form
+on the host, and R-compatible number formatting."""
+import ctypes as C
+import os
+import re
+import pytest
+from helpers import ROOT, golden, outputs
+
+
+def test_library_exports_every_declared_symbol():
+    from peaksegdisk_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "peaksegdisk_b200.h")).read()
+    declared = set(re.findall(r"\b(psd_[a-z_]+)\s*\(", hdr))
+    assert declared, "no declarations found"
+    assert declared <= set(_lib.C_ABI_SYMBOLS), declared - set(_lib.C_ABI_SYMBOLS)
+    lib = C.CDLL(_lib.LIB_PATH)
+    for name in _lib.C_ABI_SYMBOLS:
+        assert hasattr(lib, name), name
+
+
+def test_status_messages_match_interface_cpp():
+    from peaksegdisk_b200 import _lib
+    assert _lib.status_text(2, penalty="-1") == "penalty=-1 must be non-negative"
+    assert _lib.status_text(1, penalty="NaN") == "penalty=NaN but must be finite"
+    assert _lib.status_text(3, bedgraph="f") == "unable to open input file for reading f"
+    assert _lib.status_text(4, bedgraph="f") == "each line of input data file f should have exactly four columns"
+    assert _lib.status_text(5, bedgraph="f") == "fourth column of input data file f should be integer"
+    assert _lib.status_text(6, bedgraph="f") == "there should be no gaps (columns 2-3) in input data file f"
+    assert _lib.status_text(7, db="d") == "unable to write to cost function database file d"
+    assert _lib.status_text(9, bedgraph="f") == "input file f contains no data"
+    assert _lib.status_text(10, penalty="foo") == "penalty string 'foo' is not numeric; it should be convertible to double"
+
+
+def test_input_errors_and_trivial_branch_without_gpu(tmp_path, capfd):
+    """Every golden case that ends before the DP (input errors, Inf penalty, constant coverage)."""
+    from peaksegdisk_b200 import _lib
+    dbdir = tmp_path / "dbdir"
+    dbdir.mkdir()
+    n = 0
+    for k, case in enumerate(golden("golden_errors.json")):
+        if case["status"] in (0, 7) and case["penalty"] != "Inf":
+            continue   # reaches the DP: GPU test
+        path = str(tmp_path / ("e%d.bedGraph" % k))
+        if not case["missing"]:
+            open(path, "w").write(case["input"])
+        db = str(dbdir) if case["db"] else path + ".db"
+        st = _lib.lib.psd_fpop_disk(path.encode(), case["penalty"].encode(), db.encode())
+        assert st == case["status"], case["name"]
+        assert outputs(path, case["penalty"]) == (case["segments"], case["loss"]), case["name"]
+        assert not os.path.isfile(path + ".db")
+        n += 1
+    for k, case in enumerate(golden("golden_small.json")):
+        trivial = case["penalty"] == "Inf" or len(set(l.split()[3] for l in case["input"].splitlines())) == 1
+        if not trivial:
+            continue
+        path = str(tmp_path / ("t%d.bedGraph" % k))
+        open(path, "w").write(case["input"])
+        st = _lib.lib.psd_fpop_disk(path.encode(), case["penalty"].encode(), (path + ".db").encode())
+        assert st == 0, case["name"]
+        assert outputs(path, case["penalty"]) == (case["segments"], case["loss"]), (case["name"], case["penalty"])
+        assert not os.path.exists(path + ".db"), "the trivial branch must not touch the db"
+        n += 1
+    assert n > 25
+
+
+def test_not_enough_columns_message(tmp_path, capfd):
+    from peaksegdisk_b200 import _lib
+    path = str(tmp_path / "x.bedGraph")
+    open(path, "w").write("chr1 0 1 5\n\nchr1 1 3 3\n")
+    assert _lib.lib.psd_fpop_disk(path.encode(), b"1", (path + ".db").encode()) == 4
+
+
+def test_r_paste():
+    from peaksegdisk_b200 import r_paste
+    cases = {0.0: "0", 10.5: "10.5", 1e6: "1e+06", 1e5: "1e+05", 10000.0: "10000", 100000.0: "1e+05", 123456.0: "123456",
+             1715.8495636069199918: "1715.84956360692", 157.99473732931699: "157.994737329317",
+             866939314852865280.0: "866939314852865280", 0.1: "0.1", 1e-4: "1e-04", 0.00012345: "0.00012345",
+             float("inf"): "Inf", 1952.6: "1952.6", 3.0: "3", 1e15: "1e+15", 123456789012345680.0: "123456789012345680", 2.0**53: "9007199254740992", 1e22: "1e+22"}
+    for x, want in cases.items():
+        assert r_paste(x) == want, (x, r_paste(x), want)
+
+
+def test_api_argument_errors(tmp_path):
+    import peaksegdisk_b200 as psd
+    with pytest.raises(ValueError, match="must be the name of a data file to segment"):
+        psd.PeakSegFPOP_file(str(tmp_path / "missing.bedGraph"), "1")
+    f = tmp_path / "a.bedGraph"
+    f.write_text("chr1 0 1 5\nchr1 1 3 3\n")
+    with pytest.raises(ValueError, match="pen.str must be a character string"):
+        psd.PeakSegFPOP_file(str(f), 10.5)
+    with pytest.raises(ValueError, match="must be a non-negative numeric scalar"):
+        psd.PeakSegFPOP_file(str(f), "-1")
+    with pytest.raises(ValueError, match="must be the name of a directory"):
+        psd.PeakSegFPOP_dir(str(tmp_path / "nodir"), "1")
+    with pytest.raises(ValueError, match="pen.num must be non-negative numeric scalar"):
+        psd.PeakSegFPOP_vec([1, 2, 3], -1)
+    with pytest.raises(ValueError, match="count.vec must be integer"):
+        psd.PeakSegFPOP_vec([1.5, 2.0], 1)
+    # Inf penalty: closed-form model, identical to the reference's files (test-CRAN-PeakSegFPOP_vec.R:9-15)
+    fit = psd.PeakSegFPOP_vec([1, 3, 0, 4, 2], float("inf"))
+    assert len(fit["segments"]) == 1 and int(fit["loss"]["peaks"][0]) == 0
