@@ -163,7 +163,8 @@ struct psd_plan {
   unsigned long long* d_seg_scratch_off = nullptr;
   int *d_scratch_row = nullptr, *d_seg_row = nullptr;
   double *d_scratch_x = nullptr, *d_seg_x = nullptr;
-  unsigned char* d_pool = nullptr; unsigned long long pool_bytes = 0;
+  unsigned char* d_pool = nullptr; unsigned long long pool_bytes = 0, pool_chunk = 0;
+  size_t d_rows_cap = 0, d_prob_cap = 0, d_seg_cap = 0;
   unsigned char* d_gws = nullptr; unsigned long long gws_bytes = 0;
   // pinned staging
   int32_t *p_weight = nullptr, *p_cov = nullptr;
@@ -189,6 +190,7 @@ struct psd_plan {
     dfree(d_weight); dfree(d_cov); dfree(d_index); dfree(d_problems); dfree(d_results); dfree(d_order);
     dfree(d_queue); dfree(d_cursors); dfree(d_seg_scratch_off); dfree(d_scratch_row); dfree(d_seg_row);
     dfree(d_scratch_x); dfree(d_seg_x); dfree(d_pool); dfree(d_gws);
+    d_rows_cap = d_prob_cap = d_seg_cap = 0; pool_bytes = 0; gws_bytes = 0;
     uploaded = false;
   }
   void release() {
@@ -236,7 +238,7 @@ const psd_stats& psd_plan_stats_ref(const psd_plan* p) { return p->stats; }
 // H2D: pack the rows of the non-trivial problems, allocate index / result / segment buffers.
 int psd_plan_upload_impl(psd_plan* p, void* stream_v) {
   cudaStream_t st = (cudaStream_t)stream_v;
-  if (p->ev_ok) { CK(cudaSetDevice(p->device)); p->release_device(); }
+  if (p->ev_ok) CK(cudaSetDevice(p->device));
   p->gpu_ids.clear();
   int64_t total = 0;
   for (size_t i = 0; i < p->probs.size(); i++) {
@@ -259,19 +261,32 @@ int psd_plan_upload_impl(psd_plan* p, void* stream_v) {
     memcpy(p->p_weight + hp.row_off, hp.weight.data(), sizeof(int32_t) * hp.n_rows);
     memcpy(p->p_cov + hp.row_off, hp.coverage.data(), sizeof(int32_t) * hp.n_rows);
   }
-  CK(cudaMalloc(&p->d_weight, sizeof(int) * total));
-  CK(cudaMalloc(&p->d_cov, sizeof(int) * total));
-  CK(cudaMalloc(&p->d_index, sizeof(unsigned long long) * total));
-  CK(cudaMalloc(&p->d_problems, sizeof(DpProblem) * ng));
-  CK(cudaMalloc(&p->d_results, sizeof(DpResult) * ng));
-  CK(cudaMalloc(&p->d_order, sizeof(int) * ng));
-  CK(cudaMalloc(&p->d_queue, sizeof(int) * 4));
-  CK(cudaMalloc(&p->d_cursors, sizeof(unsigned long long) * 4));
-  CK(cudaMalloc(&p->d_seg_scratch_off, sizeof(unsigned long long) * ng));
-  CK(cudaMalloc(&p->d_scratch_row, sizeof(int) * (total + ng)));
-  CK(cudaMalloc(&p->d_scratch_x, sizeof(double) * (total + ng)));
-  CK(cudaMalloc(&p->d_seg_row, sizeof(int) * (total + ng)));
-  CK(cudaMalloc(&p->d_seg_x, sizeof(double) * (total + ng)));
+  // device buffers are grow-only: a plan that is re-uploaded with the same shapes allocates nothing
+  if ((size_t)total > p->d_rows_cap) {
+    dfree(p->d_weight); dfree(p->d_cov); dfree(p->d_index);
+    CK(cudaMalloc(&p->d_weight, sizeof(int) * total));
+    CK(cudaMalloc(&p->d_cov, sizeof(int) * total));
+    CK(cudaMalloc(&p->d_index, sizeof(unsigned long long) * total));
+    p->d_rows_cap = total;
+  }
+  if (ng > p->d_prob_cap) {
+    dfree(p->d_problems); dfree(p->d_results); dfree(p->d_order); dfree(p->d_seg_scratch_off);
+    CK(cudaMalloc(&p->d_problems, sizeof(DpProblem) * ng));
+    CK(cudaMalloc(&p->d_results, sizeof(DpResult) * ng));
+    CK(cudaMalloc(&p->d_order, sizeof(int) * ng));
+    CK(cudaMalloc(&p->d_seg_scratch_off, sizeof(unsigned long long) * ng));
+    p->d_prob_cap = ng;
+  }
+  if (!p->d_queue) CK(cudaMalloc(&p->d_queue, sizeof(int) * 4));
+  if (!p->d_cursors) CK(cudaMalloc(&p->d_cursors, sizeof(unsigned long long) * 4));
+  if ((size_t)(total + ng) > p->d_seg_cap) {
+    dfree(p->d_scratch_row); dfree(p->d_scratch_x); dfree(p->d_seg_row); dfree(p->d_seg_x);
+    CK(cudaMalloc(&p->d_scratch_row, sizeof(int) * (total + ng)));
+    CK(cudaMalloc(&p->d_scratch_x, sizeof(double) * (total + ng)));
+    CK(cudaMalloc(&p->d_seg_row, sizeof(int) * (total + ng)));
+    CK(cudaMalloc(&p->d_seg_x, sizeof(double) * (total + ng)));
+    p->d_seg_cap = total + ng;
+  }
   if (ng > p->p_res_cap) {
     if (p->p_results) cudaFreeHost(p->p_results);
     CK(cudaMallocHost(&p->p_results, sizeof(DpResult) * ng));
@@ -298,8 +313,16 @@ int psd_plan_upload_impl(psd_plan* p, void* stream_v) {
   const unsigned long long chunk = (unsigned long long)p->opt.chunk_kb << 10;
   want = (want / chunk) * chunk;
   if (want < chunk * 16) want = chunk * 16;
-  CK(cudaMalloc(&p->d_pool, want));
-  p->pool_bytes = want;
+  if (want > p->pool_bytes || p->pool_chunk != chunk) {
+    dfree(p->d_pool); p->pool_bytes = 0;
+    if (p->opt.store_gb <= 0) {   // re-evaluate the clamp now that the old pool is gone
+      CK(cudaMemGetInfo(&free_b, &total_b));
+      const unsigned long long lim = ((unsigned long long)((double)free_b * 0.80) / chunk) * chunk;
+      if (want > lim) want = lim;
+    }
+    CK(cudaMalloc(&p->d_pool, want));
+    p->pool_bytes = want; p->pool_chunk = chunk;
+  }
   // device problem descriptors
   std::vector<DpProblem> hp(ng);
   std::vector<unsigned long long> soff(ng);
