@@ -41,37 +41,30 @@ struct DpKernelParams {
 };
 
 __host__ __device__ inline unsigned long long psd_ws_bytes(int cap, int ccap) {
-  // 4 piece lists + interval scratch + candidate scratch, 16-byte aligned
-  unsigned long long b = 4ull * 44ull * (unsigned)cap + 4ull * 2ull * (unsigned)cap + 12ull * (unsigned)ccap;
+  // header + 4 piece lists + candidate scratch + interval scratch, 16-byte aligned (WarpWs layout)
+  unsigned long long b = PSD_WS_HDR + 4ull * 44ull * (unsigned)cap + 12ull * (unsigned)ccap + 4ull * 2ull * (unsigned)cap;
   return (b + 15ull) & ~15ull;
 }
 
 __global__ void __launch_bounds__(PSD_WARPS_PER_BLOCK * 32)
 fpop_dp_kernel(const DpKernelParams P) {
-  extern __shared__ __align__(16) unsigned char smem[];
-  uint64_t* etab = (uint64_t*)smem;
+  uint64_t* etab = (uint64_t*)psd_smem;     // psd_smem: the block's dynamic shared memory (fpop_warp.cuh)
   uint64_t* ltab = etab + 256;
   for (int i = threadIdx.x; i < 256; i += blockDim.x) { etab[i] = d_exp_tab[i]; ltab[i] = d_log_tab[i]; }
   __syncthreads();
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  unsigned char* ws = P.gws ? P.gws + ((unsigned long long)blockIdx.x * PSD_WARPS_PER_BLOCK + warp) * P.ws_bytes_per_warp
-                            : smem + PSD_TAB_BYTES + (unsigned long long)warp * P.ws_bytes_per_warp;
-  WarpCtx cx;
-  cx.etab = etab; cx.ltab = ltab; cx.cap = P.cap; cx.ccap = P.ccap;
-  double* buf[4];
-  for (int k = 0; k < 4; k++) buf[k] = (double*)(ws + (unsigned long long)k * 44ull * (unsigned)P.cap);
-  cx.cand_x = (double*)(ws + 4ull * 44ull * (unsigned)P.cap);
-  cx.ivl = (int*)(cx.cand_x + P.ccap);
-  cx.cand_s = cx.ivl + 2 * P.cap;
+  WarpWs ws;
+  ws.base = P.gws ? P.gws + ((unsigned long long)blockIdx.x * PSD_WARPS_PER_BLOCK + warp) * P.ws_bytes_per_warp
+                  : psd_smem + PSD_TAB_BYTES + (unsigned long long)warp * P.ws_bytes_per_warp;
+  ws.cap = P.cap; ws.ccap = P.ccap;
   for (;;) {
     int q = 0;
     if (lane == 0) q = atomicAdd(P.queue, 1);
     q = __shfl_sync(0xffffffffu, q, 0);
     if (q >= P.n_order) break;
     const int id = P.order[q];
-    cx.overflow = 0; cx.internal = 0;
-    dp_problem(cx, P.problems[id], buf, P.pool, &P.results[id]);
+    dp_problem(ws, P.problems[id], P.pool, &P.results[id]);
     __syncwarp();
   }
 }

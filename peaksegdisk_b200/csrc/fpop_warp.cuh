@@ -87,24 +87,41 @@ struct PList { double* base; int n; };
 #define PL_I(L, i) (((int*)((L).base + 5 * cap))[(i)])
 #define PSD_LIST_BYTES(cap) ((size_t)(cap) * 44)
 
-struct WarpCtx {
-  const uint64_t* etab;   // exp table (shared memory)
-  const uint64_t* ltab;   // log table (shared memory)
-  int cap;                // capacity (pieces) of every list buffer in the current tier
-  int* ivl;               // scratch: overlap intervals, (i_f | i_g << 16), capacity 2*cap
-  double* cand_x;         // scratch: candidate right ends, capacity ccap
-  int* cand_s;            // scratch: candidate source (bit 30 = from g) | piece index
-  int ccap;
-  int overflow;           // lane-local: set when a write fell outside a capacity
-  int internal;           // lane-local: an impossible branch was taken
-};
+// Per-warp workspace (shared memory in the fast tier, global memory in the overflow tier):
+//   [0,16)  header: int flags (bit 0 = a capacity was exceeded, bit 1 = an impossible branch taken)
+//   4 piece lists of `cap` pieces, then candidate right ends (ccap doubles), interval codes
+//   (2*cap ints: i_f | i_g << 16) and candidate sources (ccap ints: bit 30 = from g | piece index).
+// The handle is three words and is passed BY VALUE so the operators can be real (non-inlined)
+// functions: the DP's code footprint has to stay close to the instruction cache (profiles/).
+struct WarpWs { unsigned char* base; int cap; int ccap; };
+#define PSD_WS_HDR 16
+#define PSD_FLAG_OVERFLOW 1
+#define PSD_FLAG_INTERNAL 2
+PSD_DEV double* ws_list(const WarpWs w, int k) { return (double*)(w.base + PSD_WS_HDR + (unsigned long long)k * 44ull * (unsigned)w.cap); }
+PSD_DEV double* ws_cand_x(const WarpWs w) { return (double*)(w.base + PSD_WS_HDR + 176ull * (unsigned)w.cap); }
+PSD_DEV int* ws_ivl(const WarpWs w) { return (int*)(ws_cand_x(w) + w.ccap); }
+PSD_DEV int* ws_cand_s(const WarpWs w) { return ws_ivl(w) + 2 * w.cap; }
+PSD_DEV volatile int* ws_flags(const WarpWs w) { return (volatile int*)w.base; }
+PSD_DEV void ws_raise(const WarpWs w, int flag) { *ws_flags(w) = *ws_flags(w) | flag; }
+
+// exp/log tables: first 4 KB of the block's dynamic shared memory (host arrays under the emulator)
+#if defined(PSD_EMU)
+#define PSD_ETAB psd_exp_tab_host
+#define PSD_LTAB psd_log_tab_host
+#else
+extern __shared__ __align__(16) unsigned char psd_smem[];
+#define PSD_ETAB ((const uint64_t*)psd_smem)
+#define PSD_LTAB (((const uint64_t*)psd_smem) + 256)
+#endif
+PSD_DEVNI double w_exp(double x) { return psd_exp(x, PSD_ETAB); }
+PSD_DEVNI double w_log(double x) { return psd_log(x, PSD_LTAB); }
 
 // rescale applied while writing an operator's output:  ((v * mul) + add) * inv  per coefficient,
 // i.e. multiply(W_{t-1}); add(w, -z*w, 0); multiply(1/W_t)   (src/PeakSegFPOPLog.cpp:316-321)
 struct Rescale { double mul, add_a, add_b, inv; };
 
-PSD_DEV double pc_cost(double a, double b, double c, double x, const WarpCtx& cx) {
-  const double et = (x == -PSD_INF) ? 0.0 : a * psd_exp(x, cx.etab);
+PSD_DEV double pc_cost(double a, double b, double c, double x) {
+  const double et = (x == -PSD_INF) ? 0.0 : a * w_exp(x);
   const double lt = (b == 0) ? 0.0 : b * x;
   return et + lt + c;
 }
@@ -126,20 +143,20 @@ PSD_DEV double pc_abs(double v) { return v < 0 ? -v : v; }
 // get_smaller_root (:129-190): Newton in log space from argmin-1.
 // x0 = argmin, c0 = cost(x0), cl = cost(lo) are passed in (the reference recomputes the same values).
 PSD_DEVNI double root_left(double a, double b, double c, double lo, double level,
-                           double x0, double c0, double cl, const uint64_t* etab) {
+                           double x0, double c0, double cl) {
   if ((level < cl && cl < c0) || (level > cl && cl > c0)) return lo - 1;
   double x = x0 - 1;
   double f, pos_f = PSD_INF, pos_x = PSD_INF, neg_f = -PSD_INF, neg_x = PSD_INF;
   if (c0 < 0) { neg_f = c0; neg_x = x0; } else { pos_f = c0; pos_x = x0; }
   int step = 0;
   do {
-    const double et = (x == -PSD_INF) ? 0.0 : a * psd_exp(x, etab);
+    const double et = (x == -PSD_INF) ? 0.0 : a * w_exp(x);
     f = (et + b * x + c) - level;
     if (0 < f && f < pos_f) { pos_f = f; pos_x = x; }
     if (neg_f < f && f < 0) { neg_f = f; neg_x = x; }
     if (PSD_MAX_STEPS <= ++step) {
       const double mid = (pos_x + neg_x) / 2;
-      const double em = (mid == -PSD_INF) ? 0.0 : a * psd_exp(mid, etab);
+      const double em = (mid == -PSD_INF) ? 0.0 : a * w_exp(mid);
       const double fm = (em + b * mid + c) - level;
       return (pc_abs(fm) < pc_abs(f)) ? mid : x;
     }
@@ -153,25 +170,25 @@ PSD_DEVNI double root_left(double a, double b, double c, double lo, double level
 // get_larger_root (:69-127): Newton in mean space from argmin_mean+1; returns log(root).
 // m0 = argmin_mean, c0 = PoissonLoss(m0), cr = cost(hi) are passed in.
 PSD_DEVNI double root_right(double a, double b, double c, double hi, double level,
-                            double m0, double c0, double cr, const uint64_t* ltab) {
+                            double m0, double c0, double cr) {
   if ((c0 < cr && cr < level) || (c0 > cr && cr > level)) return hi + 1;
   double m = m0 + 1;
   double f, pos_f = PSD_INF, pos_m = PSD_INF, neg_f = -PSD_INF, neg_m = PSD_INF;
   if (c0 < 0) { neg_f = c0; neg_m = m0; } else { pos_f = c0; pos_m = m0; }
   int step = 0;
   do {
-    f = ((a * m + c) + psd_log(m, ltab) * b) - level;
+    f = ((a * m + c) + w_log(m) * b) - level;
     if (0 < f && f < pos_f) { pos_f = f; pos_m = m; }
     if (neg_f < f && f < 0) { neg_f = f; neg_m = m; }
     if (PSD_MAX_STEPS <= ++step) {
       const double mid = (pos_m + neg_m) / 2;
-      const double fm = ((a * mid + c) + psd_log(mid, ltab) * b) - level;
-      return (pc_abs(fm) < pc_abs(f)) ? psd_log(mid, ltab) : psd_log(m, ltab);
+      const double fm = ((a * mid + c) + w_log(mid) * b) - level;
+      return (pc_abs(fm) < pc_abs(f)) ? w_log(mid) : w_log(m);
     }
     const double d = a + b / m;
     m = m - f / d;
   } while (PSD_EPS < pc_abs(f));
-  return psd_log(m, ltab);
+  return w_log(m);
 }
 
 // has_two_roots (:29-50) from the precomputed optimum costs (log-space c1, mean-space c2)
@@ -184,19 +201,19 @@ PSD_DEV bool same_coefs(double a1, double b1, double c1, double a2, double b2, d
   return a1 == a2 && b1 == b2 && pc_abs(c1 - c2) < PSD_EPS;
 }
 
-PSD_DEV void pl_emit(WarpCtx& cx, PList& out, int k, double a, double b, double c, double hi, double bx, int bi) {
-  const int cap = cx.cap;
+PSD_DEV void pl_emit(const WarpWs ws, const PList out, int k, double a, double b, double c, double hi, double bx, int bi) {
+  const int cap = ws.cap;
   if (k < cap) {
     PL_A(out, k) = a; PL_B(out, k) = b; PL_C(out, k) = c; PL_X(out, k) = hi; PL_P(out, k) = bx; PL_I(out, k) = bi;
   } else {
-    cx.overflow = 1;
+    ws_raise(ws, PSD_FLAG_OVERFLOW);
   }
 }
 
 // ---- set_to_min_less_of, then set_prev_seg_end(stamp) and add(0,0,cshift) --------------------------
-PSD_DEV void min_less_op(WarpCtx& cx, const PList in, PList& out, double dmin, int stamp, double cshift) {
+PSD_DEVNI int min_less_op(const WarpWs ws, const PList in, const PList out, double dmin, int stamp, double cshift) {
   const int lane = psd_lane();
-  const int cap = cx.cap;
+  const int cap = ws.cap;
   const int n = in.n;
   double level = PSD_INF;    // cost of the pending flat piece; +inf while following the input
   double left_edge = dmin;   // where the next output piece starts
@@ -211,19 +228,19 @@ PSD_DEV void min_less_op(WarpCtx& cx, const PList in, PList& out, double dmin, i
     if (valid) {
       a = PL_A(in, i); b = PL_B(in, i); c = PL_C(in, i); hi = PL_X(in, i);
       lo = (i == 0) ? dmin : PL_X(in, i - 1);
-      cl = pc_cost(a, b, c, lo, cx);
-      cr = pc_cost(a, b, c, hi, cx);
+      cl = pc_cost(a, b, c, lo);
+      cr = pc_cost(a, b, c, hi);
       if (b != 0) {
         m = -b / a;
-        mu = psd_log(m, cx.ltab);
-        cmu = pc_cost(a, b, c, mu, cx);
+        mu = w_log(m);
+        cmu = pc_cost(a, b, c, mu);
         c2 = pc_cost_m(a, b, c, m, mu);
       }
     }
     // cost of the next piece at its left end
     double nl = psd_shfl_down_d(cl, 1);
     const bool has_next = i + 1 < n;
-    if (lane == 31 && has_next) nl = pc_cost(PL_A(in, i + 1), PL_B(in, i + 1), PL_C(in, i + 1), hi, cx);
+    if (lane == 31 && has_next) nl = pc_cost(PL_A(in, i + 1), PL_B(in, i + 1), PL_C(in, i + 1), hi);
     // what this piece does when reached while following the input:
     // 0 = copied whole, 1 = a flat stretch starts at its left end, 2 = its minimum is interior
     int kind = 0;
@@ -243,7 +260,7 @@ PSD_DEV void min_less_op(WarpCtx& cx, const PList in, PList& out, double dmin, i
       if (level == PSD_INF) {
         const unsigned mask = psd_ballot(valid && i >= pos && kind != 0);
         const int first = mask ? base + psd_ffs(mask) - 1 : end;
-        if (valid && i >= pos && i < first) pl_emit(cx, out, out_n + (i - pos), a + 0.0, b + 0.0, c + cshift, hi, PSD_INF, stamp);
+        if (valid && i >= pos && i < first) pl_emit(ws, out, out_n + (i - pos), a + 0.0, b + 0.0, c + cshift, hi, PSD_INF, stamp);
         const int src = (first < end) ? first - base : 0;
         const int kf = psd_shfl_i(kind, src);
         const double lo_f = psd_shfl_d(lo, src), cl_f = psd_shfl_d(cl, src);
@@ -255,7 +272,7 @@ PSD_DEV void min_less_op(WarpCtx& cx, const PList in, PList& out, double dmin, i
         if (kf == 1) { level = cl_f; arg_at = lo_f; }
         else {
           if (left_edge < mu_f) {
-            if (lane == src) pl_emit(cx, out, out_n, a + 0.0, b + 0.0, c + cshift, mu_f, PSD_INF, stamp);
+            if (lane == src) pl_emit(ws, out, out_n, a + 0.0, b + 0.0, c + cshift, mu_f, PSD_INF, stamp);
             out_n++;
           }
           left_edge = mu_f; arg_at = mu_f; level = cmu_f;
@@ -268,7 +285,7 @@ PSD_DEV void min_less_op(WarpCtx& cx, const PList in, PList& out, double dmin, i
           if (b == 0) { if (a < 0) flag = 3; }   // the reference throws here ("should never happen")
           else {
             if (two_roots(a, cmu, c2, level)) {
-              r = root_left(a, b, c, lo, level, mu, cmu, cl, cx.etab);
+              r = root_left(a, b, c, lo, level, mu, cmu, cl);
               if (lo < r && r < hi) flag = 1;
             }
             if (!flag && cr <= level + PSD_EPS) flag = 2;
@@ -279,9 +296,9 @@ PSD_DEV void min_less_op(WarpCtx& cx, const PList in, PList& out, double dmin, i
         const int src = psd_ffs(mask) - 1;
         const int fl = psd_shfl_i(flag, src);
         const double r_s = psd_shfl_d(r, src), hi_s = psd_shfl_d(hi, src);
-        if (fl == 3) { cx.internal = 1; pos = end; level = PSD_INF; break; }
+        if (fl == 3) { ws_raise(ws, PSD_FLAG_INTERNAL); pos = end; level = PSD_INF; break; }
         const double xe = (fl == 1) ? r_s : hi_s;
-        if (lane == 0) pl_emit(cx, out, out_n, 0.0 + 0.0, 0.0 + 0.0, level + cshift, xe, arg_at, stamp);
+        if (lane == 0) pl_emit(ws, out, out_n, 0.0 + 0.0, 0.0 + 0.0, level + cshift, xe, arg_at, stamp);
         out_n++;
         level = PSD_INF; left_edge = xe;
         pos = base + src + (fl == 1 ? 0 : 1);
@@ -289,17 +306,17 @@ PSD_DEV void min_less_op(WarpCtx& cx, const PList in, PList& out, double dmin, i
     }
   }
   if (level < PSD_INF) {
-    if (lane == 0) pl_emit(cx, out, out_n, 0.0 + 0.0, 0.0 + 0.0, level + cshift, PL_X(in, n - 1), arg_at, stamp);
+    if (lane == 0) pl_emit(ws, out, out_n, 0.0 + 0.0, 0.0 + 0.0, level + cshift, PL_X(in, n - 1), arg_at, stamp);
     out_n++;
   }
-  out.n = out_n;
   psd_syncwarp();
+  return out_n;
 }
 
 // ---- set_to_min_more_of, then set_prev_seg_end(stamp) ---------------------------------------------
-PSD_DEV void min_more_op(WarpCtx& cx, const PList in, PList& out, double dmin, int stamp) {
+PSD_DEVNI int min_more_op(const WarpWs ws, const PList in, const PList out, double dmin, int stamp) {
   const int lane = psd_lane();
-  const int cap = cx.cap;
+  const int cap = ws.cap;
   const int n = in.n;
   double level = PSD_INF;
   double right_edge = PL_X(in, n - 1);
@@ -313,19 +330,19 @@ PSD_DEV void min_more_op(WarpCtx& cx, const PList in, PList& out, double dmin, i
     if (valid) {
       a = PL_A(in, i); b = PL_B(in, i); c = PL_C(in, i); hi = PL_X(in, i);
       lo = (i == 0) ? dmin : PL_X(in, i - 1);
-      cl = pc_cost(a, b, c, lo, cx);
-      cr = pc_cost(a, b, c, hi, cx);
+      cl = pc_cost(a, b, c, lo);
+      cr = pc_cost(a, b, c, hi);
       if (b != 0) {
         m = -b / a;
-        mu = psd_log(m, cx.ltab);
-        cmu = pc_cost(a, b, c, mu, cx);
+        mu = w_log(m);
+        cmu = pc_cost(a, b, c, mu);
         c2 = pc_cost_m(a, b, c, m, mu);
       }
     }
     // cost of the previous piece at its right end
     double pr = psd_shfl_up_d(cr, 1);
     const bool has_prev = i > 0;
-    if (lane == 0 && has_prev && valid) pr = pc_cost(PL_A(in, i - 1), PL_B(in, i - 1), PL_C(in, i - 1), lo, cx);
+    if (lane == 0 && has_prev && valid) pr = pc_cost(PL_A(in, i - 1), PL_B(in, i - 1), PL_C(in, i - 1), lo);
     int kind = 0;  // 0 = copied whole, 1 = flat stretch starts at its right end, 2 = interior minimum
     if (valid && b != 0) {
       const bool prev_ok = !has_prev || PSD_EPS < pr - cmu;
@@ -337,7 +354,7 @@ PSD_DEV void min_more_op(WarpCtx& cx, const PList in, PList& out, double dmin, i
       if (level == PSD_INF) {
         const unsigned mask = psd_ballot(valid && i <= pos && kind != 0);
         const int first = mask ? base + 31 - psd_clz(mask) : base - 1;
-        if (valid && i <= pos && i > first) pl_emit(cx, out, out_n + (pos - i), a, b, c, (i == pos) ? right_edge : hi, PSD_INF, stamp);
+        if (valid && i <= pos && i > first) pl_emit(ws, out, out_n + (pos - i), a, b, c, (i == pos) ? right_edge : hi, PSD_INF, stamp);
         const int src = (first >= base) ? first - base : 0;
         const int kf = psd_shfl_i(kind, src);
         const double hi_f = psd_shfl_d(hi, src), cr_f = psd_shfl_d(cr, src);
@@ -349,7 +366,7 @@ PSD_DEV void min_more_op(WarpCtx& cx, const PList in, PList& out, double dmin, i
         if (kf == 1) { level = cr_f; arg_at = hi_f; }
         else {
           if (mu_f < right_edge) {
-            if (lane == src) pl_emit(cx, out, out_n, a, b, c, right_edge, PSD_INF, stamp);
+            if (lane == src) pl_emit(ws, out, out_n, a, b, c, right_edge, PSD_INF, stamp);
             out_n++;
           }
           right_edge = mu_f; arg_at = mu_f; level = cmu_f;
@@ -359,8 +376,8 @@ PSD_DEV void min_more_op(WarpCtx& cx, const PList in, PList& out, double dmin, i
         int flag = 0;
         double r = PSD_INF;
         if (valid && i <= pos) {
-          if (b == 0) r = psd_log((level - c) / a, cx.ltab);
-          else if (two_roots(a, cmu, c2, level)) r = root_right(a, b, c, hi, level, m, c2, cr, cx.ltab);
+          if (b == 0) r = w_log((level - c) / a);
+          else if (two_roots(a, cmu, c2, level)) r = root_right(a, b, c, hi, level, m, c2, cr);
           if (lo < r && r < hi) flag = 1;
           else if (cl <= level + PSD_EPS) flag = 2;
         }
@@ -369,7 +386,7 @@ PSD_DEV void min_more_op(WarpCtx& cx, const PList in, PList& out, double dmin, i
         const int src = 31 - psd_clz(mask);
         const int fl = psd_shfl_i(flag, src);
         const double r_s = psd_shfl_d(r, src), lo_s = psd_shfl_d(lo, src);
-        if (lane == 0) pl_emit(cx, out, out_n, 0.0, 0.0, level, right_edge, arg_at, stamp);
+        if (lane == 0) pl_emit(ws, out, out_n, 0.0, 0.0, level, right_edge, arg_at, stamp);
         out_n++;
         level = PSD_INF;
         if (fl == 1) { right_edge = r_s; pos = base + src; }
@@ -378,7 +395,7 @@ PSD_DEV void min_more_op(WarpCtx& cx, const PList in, PList& out, double dmin, i
     }
   }
   if (level < PSD_INF) {
-    if (lane == 0) pl_emit(cx, out, out_n, 0.0, 0.0, level, right_edge, arg_at, stamp);
+    if (lane == 0) pl_emit(ws, out, out_n, 0.0, 0.0, level, right_edge, arg_at, stamp);
     out_n++;
   }
   psd_syncwarp();
@@ -396,8 +413,8 @@ PSD_DEV void min_more_op(WarpCtx& cx, const PList in, PList& out, double dmin, i
       const int ti = PL_I(out, k); PL_I(out, k) = PL_I(out, j); PL_I(out, j) = ti;
     }
   }
-  out.n = out_n;
   psd_syncwarp();
+  return out_n;
 }
 
 // ---- push_min_pieces (:870-1259) for one overlap interval, one lane --------------------------------
@@ -405,9 +422,8 @@ PSD_DEV void min_more_op(WarpCtx& cx, const PList in, PList& out, double dmin, i
 // alternate sources; split points x1 (and x2).   [s0] | x1 | [!s0] | x2 | [s0]
 struct PairOut { int nc; int s0; double x1, x2; };
 
-PSD_DEV PairOut pair_rule(const WarpCtx& cx, const PList f, const PList g, int i, int j, double dmin,
+PSD_DEV PairOut pair_rule(const int cap, const PList f, const PList g, int i, int j, double dmin,
                           double* lo_out, double* hi_out) {
-  const int cap = cx.cap;
   PairOut o; o.nc = 1; o.s0 = 0; o.x1 = 0; o.x2 = 0;
   const double pa = PL_A(f, i), pb = PL_B(f, i), pcst = PL_C(f, i);
   const double qa = PL_A(g, j), qb = PL_B(g, j), qcst = PL_C(g, j);
@@ -433,28 +449,28 @@ PSD_DEV PairOut pair_rule(const WarpCtx& cx, const PList f, const PList g, int i
   if (lo == hi) { o.nc = 0; return o; }
   if (same_coefs(pa, pb, pcst, qa, qb, qcst)) { o.s0 = 0; return o; }
   const double da = pa - qa, db = pb - qb, dc = pcst - qcst;
-  const double ehi = psd_exp(hi, cx.etab), elo = psd_exp(lo, cx.etab);
+  const double ehi = w_exp(hi), elo = w_exp(lo);
   const double mid_m = (ehi + elo) / 2;
-  const double dmid = pc_cost(da, db, dc, psd_log(mid_m, cx.ltab), cx);
+  const double dmid = pc_cost(da, db, dc, w_log(mid_m));
   const int by_mid = (dmid < 0) ? 0 : 1;
   if (eq_left && eq_right) { o.s0 = by_mid; return o; }
   if (db == 0) {
     if (da == 0) { o.s0 = (dc < 0) ? 0 : 1; return o; }
     if (dc == 0) { o.s0 = (da < 0) ? 0 : 1; return o; }
-    const double x = psd_log(-dc / da, cx.ltab);
+    const double x = w_log(-dc / da);
     if (lo < x && x < hi) { o.nc = 2; o.x1 = x; o.s0 = (0 < da) ? 0 : 1; return o; }
     o.s0 = by_mid; return o;
   }
   const double dl = pc_cost_e(da, db, dc, lo, elo), dr = pc_cost_e(da, db, dc, hi, ehi);
   const double m = -db / da;
-  const double xo = psd_log(m, cx.ltab);
-  const double c1 = pc_cost(da, db, dc, xo, cx);
+  const double xo = w_log(m);
+  const double c1 = pc_cost(da, db, dc, xo);
   const double c2 = pc_cost_m(da, db, dc, m, xo);
   const bool two = two_roots(da, c1, c2, 0.0);
   double rs = PSD_INF, rl = PSD_INF;
   if (two) {
-    rs = root_left(da, db, dc, lo, 0.0, xo, c1, dl, cx.etab);
-    rl = root_right(da, db, dc, hi, 0.0, m, c2, dr, cx.ltab);
+    rs = root_left(da, db, dc, lo, 0.0, xo, c1, dl);
+    rl = root_right(da, db, dc, hi, 0.0, m, c2, dr);
   }
   if (eq_right) {
     if (two) {
@@ -475,23 +491,23 @@ PSD_DEV PairOut pair_rule(const WarpCtx& cx, const PList f, const PList g, int i
   double x1 = PSD_INF, x2 = PSD_INF;
   if (two) {
     const bool l_in = lo < rl && rl < hi;
-    const bool s_in = lo < rs && 0 < psd_exp(rs, cx.etab) && rs < hi;
+    const bool s_in = lo < rs && 0 < w_exp(rs) && rs < hi;
     if (l_in) { if (s_in && rs < rl) { x1 = rs; x2 = rl; } else x1 = rl; }
     else if (s_in) x1 = rs;
   }
   if (x2 != PSD_INF) {
     bool f_first;
     if (x2 - x1 < x1 - lo) {
-      const double bm = (elo + psd_exp(x1, cx.etab)) / 2;
-      f_first = pc_cost(da, db, dc, psd_log(bm, cx.ltab), cx) < 0;
+      const double bm = (elo + w_exp(x1)) / 2;
+      f_first = pc_cost(da, db, dc, w_log(bm)) < 0;
     } else {
-      f_first = !(pc_cost(da, db, dc, (x1 + x2) / 2, cx) < 0);
+      f_first = !(pc_cost(da, db, dc, (x1 + x2) / 2) < 0);
     }
     o.nc = 3; o.x1 = x1; o.x2 = x2; o.s0 = f_first ? 0 : 1;
   } else if (x1 != PSD_INF) {
-    const double bm = (elo + psd_exp(x1, cx.etab)) / 2;
-    const double before = pc_cost(da, db, dc, psd_log(bm, cx.ltab), cx);
-    const double after = pc_cost(da, db, dc, (hi + x1) / 2, cx);
+    const double bm = (elo + w_exp(x1)) / 2;
+    const double before = pc_cost(da, db, dc, w_log(bm));
+    const double after = pc_cost(da, db, dc, (hi + x1) / 2);
     if (before < 0) {
       if (after < 0) o.s0 = 0;
       else { o.nc = 2; o.x1 = x1; o.s0 = 0; }
@@ -510,9 +526,12 @@ PSD_DEV PairOut pair_rule(const WarpCtx& cx, const PList f, const PList g, int i
 
 // ---- set_to_min_env_of(f, g) followed by the row rescale -------------------------------------------
 // f is the freshly built min-less/min-more function, g the previous cost function.
-PSD_DEV void min_env_op(WarpCtx& cx, const PList f, const PList g, PList& out, double dmin, const Rescale rs) {
+PSD_DEVNI int min_env_op(const WarpWs ws, const PList f, const PList g, const PList out, double dmin, const Rescale rs) {
   const int lane = psd_lane();
-  const int cap = cx.cap;
+  const int cap = ws.cap, ccap = ws.ccap;
+  int* const ivl = ws_ivl(ws);
+  double* const cand_x = ws_cand_x(ws);
+  int* const cand_s = ws_cand_s(ws);
   const int nf = f.n, ng = g.n;
   // 1. enumerate overlap intervals, one g piece per lane: f pieces s..e overlap g[j]
   int K = 0;
@@ -541,7 +560,7 @@ PSD_DEV void min_env_op(WarpCtx& cx, const PList f, const PList g, PList& out, d
       for (int d = 1; d < 32; d <<= 1) { const int t = psd_shfl_up_i(incl, d); if (lane >= d) incl += t; }
       const int off = K + incl - cnt;
       for (int q = 0; q < cnt; q++) {
-        if (off + q < 2 * cap) cx.ivl[off + q] = (s + q) | (j << 16); else cx.overflow = 1;
+        if (off + q < 2 * cap) ivl[off + q] = (s + q) | (j << 16); else ws_raise(ws, PSD_FLAG_OVERFLOW);
       }
       K += psd_shfl_i(incl, 31);
       carry_next = psd_shfl_i(e + tie, (ng - base < 32) ? ng - base - 1 : 31);
@@ -558,9 +577,9 @@ PSD_DEV void min_env_op(WarpCtx& cx, const PList f, const PList g, PList& out, d
     double lo = 0, hi = 0;
     int i = 0, j = 0;
     if (valid) {
-      const int code = cx.ivl[q];
+      const int code = ivl[q];
       i = code & 0xffff; j = code >> 16;
-      o = pair_rule(cx, f, g, i, j, dmin, &lo, &hi);
+      o = pair_rule(cap, f, g, i, j, dmin, &lo, &hi);
     }
     int incl = o.nc;
     for (int d = 1; d < 32; d <<= 1) { const int t = psd_shfl_up_i(incl, d); if (lane >= d) incl += t; }
@@ -568,16 +587,16 @@ PSD_DEV void min_env_op(WarpCtx& cx, const PList f, const PList g, PList& out, d
     if (o.nc > 0) {
       const int sf = i, sg = j | PSD_SRC_G;
       const int c0 = o.s0 ? sg : sf, c1 = o.s0 ? sf : sg;
-      if (off + o.nc <= cx.ccap) {
-        cx.cand_s[off] = c0; cx.cand_x[off] = (o.nc > 1) ? o.x1 : hi;
-        if (o.nc > 1) { cx.cand_s[off + 1] = c1; cx.cand_x[off + 1] = (o.nc > 2) ? o.x2 : hi; }
-        if (o.nc > 2) { cx.cand_s[off + 2] = c0; cx.cand_x[off + 2] = hi; }
-      } else cx.overflow = 1;
+      if (off + o.nc <= ccap) {
+        cand_s[off] = c0; cand_x[off] = (o.nc > 1) ? o.x1 : hi;
+        if (o.nc > 1) { cand_s[off + 1] = c1; cand_x[off + 1] = (o.nc > 2) ? o.x2 : hi; }
+        if (o.nc > 2) { cand_s[off + 2] = c0; cand_x[off + 2] = hi; }
+      } else ws_raise(ws, PSD_FLAG_OVERFLOW);
     }
     T += psd_shfl_i(incl, 31);
   }
   psd_syncwarp();
-  if (T > cx.ccap) T = cx.ccap;
+  if (T > ccap) T = ccap;
   // 3. push_piece: merge each candidate into the current run when it equals the run's head
   int out_n = 0;
   bool carry_ok = false;
@@ -588,8 +607,8 @@ PSD_DEV void min_env_op(WarpCtx& cx, const PList f, const PList g, PList& out, d
     const bool valid = q < T;
     double a = 0, b = 0, c = 0, p = 0, x = 0; int bi = 0;
     if (valid) {
-      const int code = cx.cand_s[q];
-      x = cx.cand_x[q];
+      const int code = cand_s[q];
+      x = cand_x[q];
       const int k = code & 0xffffff;
       if (code & PSD_SRC_G) { a = PL_A(g, k); b = PL_B(g, k); c = PL_C(g, k); p = PL_P(g, k); bi = PL_I(g, k); }
       else { a = PL_A(f, k); b = PL_B(f, k); c = PL_C(f, k); p = PL_P(f, k); bi = PL_I(f, k); }
@@ -627,10 +646,10 @@ PSD_DEV void min_env_op(WarpCtx& cx, const PList f, const PList g, PList& out, d
       const double nb = ((b * rs.mul) + rs.add_b) * rs.inv;
       const double nc = ((c * rs.mul) + 0.0) * rs.inv;
       if (out_n + rank < cap) {
-        PList& o = out;
+        const PList o = out;
         PL_A(o, out_n + rank) = na; PL_B(o, out_n + rank) = nb; PL_C(o, out_n + rank) = nc;
         PL_P(o, out_n + rank) = p; PL_I(o, out_n + rank) = bi;
-      } else cx.overflow = 1;
+      } else ws_raise(ws, PSD_FLAG_OVERFLOW);
     }
     // the last member of every run (within this chunk) sets the run's right end
     const bool last_valid = valid && (lane == 31 || !((vm >> (lane + 1)) & 1u));
@@ -647,28 +666,28 @@ PSD_DEV void min_env_op(WarpCtx& cx, const PList f, const PList g, PList& out, d
     }
     out_n += n_heads;
   }
-  out.n = out_n;
   psd_syncwarp();
+  return out_n;
 }
 
 // copy with rescale (rows 0/1 of the DP, src/PeakSegFPOPLog.cpp:297-299, 324-328)
-PSD_DEV void copy_rescale_op(WarpCtx& cx, const PList in, PList& out, const Rescale rs) {
+PSD_DEVNI int copy_rescale_op(const WarpWs ws, const PList in, const PList out, const Rescale rs) {
   const int lane = psd_lane();
-  const int cap = cx.cap;
+  const int cap = ws.cap;
   for (int k = lane; k < in.n; k += 32) {
     PL_A(out, k) = ((PL_A(in, k) * rs.mul) + rs.add_a) * rs.inv;
     PL_B(out, k) = ((PL_B(in, k) * rs.mul) + rs.add_b) * rs.inv;
     PL_C(out, k) = ((PL_C(in, k) * rs.mul) + 0.0) * rs.inv;
     PL_X(out, k) = PL_X(in, k); PL_P(out, k) = PL_P(in, k); PL_I(out, k) = PL_I(in, k);
   }
-  out.n = in.n;
   psd_syncwarp();
+  return in.n;
 }
 
 // ---- Minimize (:689-712): first piece with the strictly smallest clamped-argmin cost ---------------
-PSD_DEV void best_piece(WarpCtx& cx, const PList f, double dmin, double* best_c, double* best_x, int* back_i, double* back_x) {
+PSD_DEV void best_piece(const WarpWs ws, const PList f, double dmin, double* best_c, double* best_x, int* back_i, double* back_x) {
   const int lane = psd_lane();
-  const int cap = cx.cap;
+  const int cap = ws.cap;
   double bc = PSD_INF, bx = 0, bpx = 0; int bbi = 0; int bidx = 0x7fffffff;
   for (int base = 0; base < f.n; base += 32) {
     const int i = base + lane;
@@ -676,9 +695,9 @@ PSD_DEV void best_piece(WarpCtx& cx, const PList f, double dmin, double* best_c,
     if (i < f.n) {
       const double a = PL_A(f, i), b = PL_B(f, i), c = PL_C(f, i), hi = PL_X(f, i);
       const double lo = (i == 0) ? dmin : PL_X(f, i - 1);
-      x = psd_log(-b / a, cx.ltab);
+      x = w_log(-b / a);
       if (x < lo) x = lo; else if (hi < x) x = hi;
-      cc = pc_cost(a, b, c, x, cx);
+      cc = pc_cost(a, b, c, x);
       if (!(cc < PSD_INF)) cc = PSD_INF;   // NaN/inf are never selected
     }
     if (cc < bc) { bc = cc; bx = x; bidx = i; bbi = PL_I(f, i); bpx = PL_P(f, i); }
@@ -729,10 +748,9 @@ PSD_DEV unsigned long long store_alloc(const StorePool& sp, StoreWriter& w, unsi
   return off;
 }
 
-PSD_DEV void store_write(WarpCtx& cx, const StorePool& sp, unsigned long long off, int row, const PList up, const PList down) {
+PSD_DEVNI void store_write(const WarpWs ws, unsigned char* rec, int row, const PList up, const PList down) {
   const int lane = psd_lane();
-  const int cap = cx.cap;
-  unsigned char* rec = sp.base + off;
+  const int cap = ws.cap;
   if (lane == 0) psd_st_cs_u4((unsigned*)rec, (unsigned)up.n, (unsigned)down.n, (unsigned)row, 0u);
   double* pairs = (double*)(rec + 16);
   for (int k = lane; k < up.n; k += 32) psd_st_cs_d2(pairs + 2 * k, PL_X(up, k), PL_P(up, k));
@@ -774,19 +792,19 @@ struct DpProblem {
 };
 
 // The DP over all rows of one problem (src/PeakSegFPOPLog.cpp:258-397 + Minimize at :404).
-// buf[0..3] are four list buffers of capacity cx.cap.
-PSD_DEV void dp_problem(WarpCtx& cx, const DpProblem& pb, double* const buf[4], const StorePool& sp, DpResult* res
+PSD_DEV void dp_problem(const WarpWs ws, const DpProblem& pb, const StorePool& sp, DpResult* res
 #if defined(PSD_EMU)
                         , psd_trace_fn trace, void* trace_user
 #endif
 ) {
   const int lane = psd_lane();
-  const int cap = cx.cap;
   const int N = pb.n_rows;
-  // roles: up_prev, down_prev, scratch (min-less/more result), new
+  // roles of the four list buffers: up_{t-1}, down_{t-1}, scratch (min-less/more result), new
   PList upP, downP, tmp, fresh;
-  upP.base = buf[0]; downP.base = buf[1]; tmp.base = buf[2]; fresh.base = buf[3];
+  upP.base = ws_list(ws, 0); downP.base = ws_list(ws, 1); tmp.base = ws_list(ws, 2); fresh.base = ws_list(ws, 3);
   upP.n = 0; downP.n = 0; tmp.n = 0; fresh.n = 0;
+  if (lane == 0) *ws_flags(ws) = 0;
+  psd_syncwarp();
   StoreWriter sw; sw.cur = 0; sw.end = 0;
   double cw = 0.0, cw_prev = -1.0;
   unsigned long long total_iv = 0; int max_iv = 0;
@@ -803,43 +821,37 @@ PSD_DEV void dp_problem(WarpCtx& cx, const DpProblem& pb, double* const buf[4], 
     const double w = (double)wi;
     cw += w;
     Rescale rs; rs.mul = cw_prev; rs.add_a = w; rs.add_b = (double)(-z) * w; rs.inv = 1 / cw;
-    PList up_new, down_new;
     if (t == 0) {
-      if (lane == 0) pl_emit(cx, downP, 0, 1.0, (double)(-z), 0.0, pb.dmax, -5.0, -1);
+      if (lane == 0) pl_emit(ws, downP, 0, 1.0, (double)(-z), 0.0, pb.dmax, -5.0, -1);
       downP.n = 1; upP.n = 0;
       psd_syncwarp();
-      up_new = upP; down_new = downP;
     } else {
-      min_less_op(cx, downP, tmp, pb.dmin, t - 1, pb.penalty / cw_prev);
-      if (t == 1) { copy_rescale_op(cx, tmp, fresh, rs); }
-      else { min_env_op(cx, tmp, upP, fresh, pb.dmin, rs); }
-      // fresh = up_t.  down_t goes where up_{t-1} lived once min_more has consumed it.
+      tmp.n = min_less_op(ws, downP, tmp, pb.dmin, t - 1, pb.penalty / cw_prev);
       if (t == 1) {
-        copy_rescale_op(cx, downP, upP, rs);
+        fresh.n = copy_rescale_op(ws, tmp, fresh, rs);      // up_1
+        upP.n = copy_rescale_op(ws, downP, upP, rs);        // down_1 (upP's buffer is free: up_0 is empty)
       } else {
-        min_more_op(cx, upP, tmp, pb.dmin, t - 1);
-        // min_env reads tmp and downP, writes into upP's buffer: safe, upP is dead now
-        PList dst; dst.base = upP.base; dst.n = 0;
-        min_env_op(cx, tmp, downP, dst, pb.dmin, rs);
-        upP = dst;
+        fresh.n = min_env_op(ws, tmp, upP, fresh, pb.dmin, rs);   // up_t
+        tmp.n = min_more_op(ws, upP, tmp, pb.dmin, t - 1);
+        // down_t goes where up_{t-1} lived: min_more has consumed it
+        upP.n = min_env_op(ws, tmp, downP, upP, pb.dmin, rs);
       }
-      // rotate roles: up_prev <- fresh, down_prev <- (old upP buffer), free <- old downP
-      PList old_down = downP;
+      // rotate roles: up_prev <- fresh, down_prev <- old upP buffer, free <- old downP buffer
+      const PList old_down = downP;
       downP = upP; upP = fresh; fresh = old_down; fresh.n = 0;
-      up_new = upP; down_new = downP;
     }
-    if (psd_ballot(cx.overflow)) { status = PSD_ST_PIECE_OVERFLOW; break; }
-    if (psd_ballot(cx.internal)) { status = PSD_ST_INTERNAL; break; }
+    const int flags = *ws_flags(ws);
+    if (flags) { status = (flags & PSD_FLAG_OVERFLOW) ? PSD_ST_PIECE_OVERFLOW : PSD_ST_INTERNAL; break; }
     cw_prev = cw;
-    total_iv += (unsigned long long)(up_new.n + down_new.n);
-    if (max_iv < up_new.n) max_iv = up_new.n;
-    if (max_iv < down_new.n) max_iv = down_new.n;
+    total_iv += (unsigned long long)(upP.n + downP.n);
+    if (max_iv < upP.n) max_iv = upP.n;
+    if (max_iv < downP.n) max_iv = downP.n;
 #if defined(PSD_EMU)
-    if (trace && lane == 0) { trace(trace_user, t, 0, up_new.n, cap, up_new.base); trace(trace_user, t, 1, down_new.n, cap, down_new.base); }
+    if (trace && lane == 0) { trace(trace_user, t, 0, upP.n, ws.cap, upP.base); trace(trace_user, t, 1, downP.n, ws.cap, downP.base); }
 #endif
-    const unsigned long long off = store_alloc(sp, sw, store_record_bytes(up_new.n, down_new.n));
+    const unsigned long long off = store_alloc(sp, sw, store_record_bytes(upP.n, downP.n));
     if (off == ~0ull) { status = PSD_ST_STORE_EXHAUSTED; break; }
-    store_write(cx, sp, off, t, up_new, down_new);
+    store_write(ws, sp.base + off, t, upP, downP);
     if (lane == (t & 31)) my_off = off;
     if ((t & 31) == 31 || t == N - 1) {
       const int r = (t & ~31) + lane;
@@ -847,7 +859,7 @@ PSD_DEV void dp_problem(WarpCtx& cx, const DpProblem& pb, double* const buf[4], 
     }
   }
   double bc = 0, bx = 0, bpx = 0; int bbi = -1;
-  if (status == PSD_ST_OK) best_piece(cx, downP, pb.dmin, &bc, &bx, &bbi, &bpx);
+  if (status == PSD_ST_OK) best_piece(ws, downP, pb.dmin, &bc, &bx, &bbi, &bpx);
   if (lane == 0) {
     res->status = status; res->back_i = bbi; res->best_cost = bc; res->best_x = bx; res->back_x = bpx;
     res->total_intervals = total_iv; res->max_intervals = max_iv; res->n_segments = 0; res->n_equality = 0;

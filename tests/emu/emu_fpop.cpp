@@ -9,14 +9,13 @@
 
 namespace {
 struct Job {
-  DpProblem pb; WarpCtx cx_proto; double* buf[4]; StorePool sp; DpResult* res;
+  DpProblem pb; WarpWs ws; StorePool sp; DpResult* res;
   psd_trace_fn trace; void* trace_user;
   int* seg_row; double* seg_x;
 };
 void lane_main(void* arg) {
   Job* J = (Job*)arg;
-  WarpCtx cx = J->cx_proto;   // lane-local copy (overflow/internal flags are per lane)
-  dp_problem(cx, J->pb, J->buf, J->sp, J->res, J->trace, J->trace_user);
+  dp_problem(J->ws, J->pb, J->sp, J->res, J->trace, J->trace_user);
   psd_syncwarp();
   backtrack_problem(J->sp.base, J->pb.index, J->pb.n_rows, J->res, J->seg_row, J->seg_x);
 }
@@ -42,14 +41,10 @@ int emu_fpop_rows(int n_rows, const int* chrom_start, const int* chrom_end, cons
   std::vector<unsigned long long> index(n_rows);
   J.pb.weight = w.data(); J.pb.coverage = coverage; J.pb.n_rows = n_rows; J.pb.penalty = penalty;
   J.pb.dmin = dmin; J.pb.dmax = dmax; J.pb.index = index.data();
-  std::vector<double> lists((size_t)4 * cap * 44 / 8 + 8);
-  for (int k = 0; k < 4; k++) J.buf[k] = lists.data() + (size_t)k * cap * 44 / 8;
-  std::vector<int> ivl(2 * cap);
   const int ccap = 3 * cap;
-  std::vector<double> cand_x(ccap); std::vector<int> cand_s(ccap);
-  J.cx_proto.etab = psd_exp_tab_host; J.cx_proto.ltab = psd_log_tab_host; J.cx_proto.cap = cap;
-  J.cx_proto.ivl = ivl.data(); J.cx_proto.cand_x = cand_x.data(); J.cx_proto.cand_s = cand_s.data();
-  J.cx_proto.ccap = ccap; J.cx_proto.overflow = 0; J.cx_proto.internal = 0;
+  const size_t ws_bytes = PSD_WS_HDR + (size_t)4 * 44 * cap + (size_t)12 * ccap + (size_t)8 * cap + 64;
+  std::vector<double> wsmem(ws_bytes / 8 + 8);
+  J.ws.base = (unsigned char*)wsmem.data(); J.ws.cap = cap; J.ws.ccap = ccap;
   const unsigned long long chunk = 1 << 16;
   std::vector<unsigned char> pool;
   unsigned long long cursor = 0;
