@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpeaksegdisk_b200.so")
+LIB_PATH = os.environ.get("PSD_LIB") or os.path.join(_HERE, "libpeaksegdisk_b200.so")   # PSD_LIB: kernel-variant experiments
 
 
 class PsdResult(C.Structure):

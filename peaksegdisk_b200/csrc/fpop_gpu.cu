@@ -22,7 +22,9 @@
 #include "fpop_warp.cuh"
 #include "plan_internal.h"
 
-#define PSD_WARPS_PER_BLOCK 4
+#ifndef PSD_WARPS_PER_BLOCK
+#define PSD_WARPS_PER_BLOCK 12   /* one phase-locked block per SM at 168 registers/thread */
+#endif
 #define PSD_TAB_BYTES 4096
 
 __device__ const uint64_t d_exp_tab[256] = PSD_EXP_TAB_INIT;
@@ -53,20 +55,13 @@ fpop_dp_kernel(const DpKernelParams P) {
   for (int i = threadIdx.x; i < 256; i += blockDim.x) { etab[i] = d_exp_tab[i]; ltab[i] = d_log_tab[i]; }
   __syncthreads();
   const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
   WarpWs ws;
   ws.base = P.gws ? P.gws + ((unsigned long long)blockIdx.x * PSD_WARPS_PER_BLOCK + warp) * P.ws_bytes_per_warp
                   : psd_smem + PSD_TAB_BYTES + (unsigned long long)warp * P.ws_bytes_per_warp;
   ws.cap = P.cap; ws.ccap = P.ccap;
-  for (;;) {
-    int q = 0;
-    if (lane == 0) q = atomicAdd(P.queue, 1);
-    q = __shfl_sync(0xffffffffu, q, 0);
-    if (q >= P.n_order) break;
-    const int id = P.order[q];
-    dp_problem(ws, P.problems[id], P.pool, &P.results[id]);
-    __syncwarp();
-  }
+  DpQueue Q;
+  Q.problems = P.problems; Q.order = P.order; Q.n_order = P.n_order; Q.cursor = P.queue; Q.results = P.results;
+  dp_run_queue(ws, Q, P.pool);
 }
 
 struct BtKernelParams {

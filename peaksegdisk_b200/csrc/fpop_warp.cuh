@@ -685,7 +685,7 @@ PSD_DEVNI int copy_rescale_op(const WarpWs ws, const PList in, const PList out, 
 }
 
 // ---- Minimize (:689-712): first piece with the strictly smallest clamped-argmin cost ---------------
-PSD_DEV void best_piece(const WarpWs ws, const PList f, double dmin, double* best_c, double* best_x, int* back_i, double* back_x) {
+PSD_DEVNI void best_piece(const WarpWs ws, const PList f, double dmin, double* best_c, double* best_x, int* back_i, double* back_x) {
   const int lane = psd_lane();
   const int cap = ws.cap;
   double bc = PSD_INF, bx = 0, bpx = 0; int bbi = 0; int bidx = 0x7fffffff;
@@ -791,78 +791,141 @@ struct DpProblem {
   unsigned long long* index;  // n_rows record offsets
 };
 
-// The DP over all rows of one problem (src/PeakSegFPOPLog.cpp:258-397 + Minimize at :404).
-PSD_DEV void dp_problem(const WarpWs ws, const DpProblem& pb, const StorePool& sp, DpResult* res
+// ---- the DP driver: a block of warps works through a queue of problems in PHASE LOCK ----------------
+// Each warp owns one problem at a time (src/PeakSegFPOPLog.cpp:258-397 + Minimize at :404) and pops
+// the next one from an atomic queue when it finishes.  The warps of a block are independent, but
+// they cross a block barrier between the four operators of a row, so that at any moment all warps
+// of the SM execute the SAME operator: the DP's code (~110 KB of SASS) is several times the
+// instruction cache, and without the phase lock 84 % of all stall samples were instruction fetch
+// (profiles/README.md).  Rows need not be aligned across warps, only phases.
 #if defined(PSD_EMU)
-                        , psd_trace_fn trace, void* trace_user
+#define psd_block_sync() do {} while (0)
+#define psd_block_or(x) (x)
+#else
+#define psd_block_sync() __syncthreads()
+#define psd_block_or(x) __syncthreads_or(x)
+#endif
+
+struct DpQueue {
+  const DpProblem* problems;
+  const int* order;      // problem ids, longest first
+  int n_order;
+  int* cursor;           // atomic cursor into order
+  DpResult* results;
+};
+
+PSD_DEV void dp_run_queue(const WarpWs ws, const DpQueue Q, const StorePool sp
+#if defined(PSD_EMU)
+                          , psd_trace_fn trace, void* trace_user
 #endif
 ) {
   const int lane = psd_lane();
-  const int N = pb.n_rows;
-  // roles of the four list buffers: up_{t-1}, down_{t-1}, scratch (min-less/more result), new
+  // per-warp state (uniform across lanes)
+  int have = 0, id = 0, t = 0, N = 0, status = PSD_ST_OK, max_iv = 0, w_l = 0, z_l = 0;
+  const int* weight = nullptr; const int* coverage = nullptr; unsigned long long* index = nullptr;
+  double penalty = 0, dmin = 0, dmax = 0, cw = 0, cw_prev = -1.0;
+  unsigned long long total_iv = 0, my_off = 0;
   PList upP, downP, tmp, fresh;
   upP.base = ws_list(ws, 0); downP.base = ws_list(ws, 1); tmp.base = ws_list(ws, 2); fresh.base = ws_list(ws, 3);
-  upP.n = 0; downP.n = 0; tmp.n = 0; fresh.n = 0;
-  if (lane == 0) *ws_flags(ws) = 0;
-  psd_syncwarp();
+  upP.n = downP.n = tmp.n = fresh.n = 0;
   StoreWriter sw; sw.cur = 0; sw.end = 0;
-  double cw = 0.0, cw_prev = -1.0;
-  unsigned long long total_iv = 0; int max_iv = 0;
-  int status = PSD_ST_OK;
-  unsigned long long my_off = 0;   // lane (t & 31) keeps row t's record offset until the batch is flushed
-  int w_l = 0, z_l = 0;
-  for (int t = 0; t < N; t++) {
-    if ((t & 31) == 0) {   // coalesced load of the next 32 rows
-      const int r = t + lane;
-      w_l = (r < N) ? pb.weight[r] : 0;
-      z_l = (r < N) ? pb.coverage[r] : 0;
-    }
-    const int wi = psd_shfl_i(w_l, t & 31), z = psd_shfl_i(z_l, t & 31);
-    const double w = (double)wi;
-    cw += w;
-    Rescale rs; rs.mul = cw_prev; rs.add_a = w; rs.add_b = (double)(-z) * w; rs.inv = 1 / cw;
-    if (t == 0) {
-      if (lane == 0) pl_emit(ws, downP, 0, 1.0, (double)(-z), 0.0, pb.dmax, -5.0, -1);
-      downP.n = 1; upP.n = 0;
-      psd_syncwarp();
-    } else {
-      tmp.n = min_less_op(ws, downP, tmp, pb.dmin, t - 1, pb.penalty / cw_prev);
-      if (t == 1) {
-        fresh.n = copy_rescale_op(ws, tmp, fresh, rs);      // up_1
-        upP.n = copy_rescale_op(ws, downP, upP, rs);        // down_1 (upP's buffer is free: up_0 is empty)
-      } else {
-        fresh.n = min_env_op(ws, tmp, upP, fresh, pb.dmin, rs);   // up_t
-        tmp.n = min_more_op(ws, upP, tmp, pb.dmin, t - 1);
-        // down_t goes where up_{t-1} lived: min_more has consumed it
-        upP.n = min_env_op(ws, tmp, downP, upP, pb.dmin, rs);
+  Rescale rs; rs.mul = rs.add_a = rs.add_b = rs.inv = 0;
+  bool fetch = true;
+  for (;;) {
+    // ---- phase A: (next problem,) next row, min_less ------------------------------------------------
+    if (fetch) {
+      int q = 0;
+      if (lane == 0) q = psd_atomic_add_int(Q.cursor, 1);
+      q = psd_shfl_i(q, 0);
+      have = q < Q.n_order;
+      fetch = false;
+      if (have) {
+        id = Q.order[q];
+        const DpProblem pb = Q.problems[id];
+        weight = pb.weight; coverage = pb.coverage; index = pb.index; N = pb.n_rows;
+        penalty = pb.penalty; dmin = pb.dmin; dmax = pb.dmax;
+        t = 0; status = PSD_ST_OK; max_iv = 0; total_iv = 0; cw = 0.0; cw_prev = -1.0;
+        // the four buffers keep rotating between problems; only the counts restart
+        upP.n = downP.n = tmp.n = fresh.n = 0;
+        if (lane == 0) *ws_flags(ws) = 0;
+        psd_syncwarp();
       }
+    }
+    if (have) {
+      if ((t & 31) == 0) {   // coalesced load of the next 32 rows
+        const int r = t + lane;
+        w_l = (r < N) ? weight[r] : 0;
+        z_l = (r < N) ? coverage[r] : 0;
+      }
+      const int wi = psd_shfl_i(w_l, t & 31), z = psd_shfl_i(z_l, t & 31);
+      const double w = (double)wi;
+      cw += w;
+      rs.mul = cw_prev; rs.add_a = w; rs.add_b = (double)(-z) * w; rs.inv = 1 / cw;
+      if (t == 0) {
+        if (lane == 0) pl_emit(ws, downP, 0, 1.0, (double)(-z), 0.0, dmax, -5.0, -1);
+        downP.n = 1; upP.n = 0;
+        psd_syncwarp();
+      } else {
+        tmp.n = min_less_op(ws, downP, tmp, dmin, t - 1, penalty / cw_prev);
+      }
+    }
+    psd_block_sync();
+    // ---- phase B: up_t = min_env(min_less + penalty, up_{t-1}) ----------------------------------------
+    if (have && t >= 1) {
+      if (t == 1) fresh.n = copy_rescale_op(ws, tmp, fresh, rs);
+      else fresh.n = min_env_op(ws, tmp, upP, fresh, dmin, rs);
+    }
+    psd_block_sync();
+    // ---- phase C: min_more(up_{t-1}) ------------------------------------------------------------------
+    if (have && t >= 2) tmp.n = min_more_op(ws, upP, tmp, dmin, t - 1);
+    psd_block_sync();
+    // ---- phase D: down_t = min_env(min_more, down_{t-1}), written where up_{t-1} lived ---------------------
+    if (have && t >= 1) {
+      if (t == 1) upP.n = copy_rescale_op(ws, downP, upP, rs);
+      else upP.n = min_env_op(ws, tmp, downP, upP, dmin, rs);
       // rotate roles: up_prev <- fresh, down_prev <- old upP buffer, free <- old downP buffer
       const PList old_down = downP;
       downP = upP; upP = fresh; fresh = old_down; fresh.n = 0;
     }
-    const int flags = *ws_flags(ws);
-    if (flags) { status = (flags & PSD_FLAG_OVERFLOW) ? PSD_ST_PIECE_OVERFLOW : PSD_ST_INTERNAL; break; }
-    cw_prev = cw;
-    total_iv += (unsigned long long)(upP.n + downP.n);
-    if (max_iv < upP.n) max_iv = upP.n;
-    if (max_iv < downP.n) max_iv = downP.n;
+    psd_block_sync();
+    // ---- phase E: counters, store record, end of problem ------------------------------------------------
+    if (have) {
+      const int flags = *ws_flags(ws);
+      if (flags) status = (flags & PSD_FLAG_OVERFLOW) ? PSD_ST_PIECE_OVERFLOW : PSD_ST_INTERNAL;
+      if (status == PSD_ST_OK) {
+        cw_prev = cw;
+        total_iv += (unsigned long long)(upP.n + downP.n);
+        if (max_iv < upP.n) max_iv = upP.n;
+        if (max_iv < downP.n) max_iv = downP.n;
 #if defined(PSD_EMU)
-    if (trace && lane == 0) { trace(trace_user, t, 0, upP.n, ws.cap, upP.base); trace(trace_user, t, 1, downP.n, ws.cap, downP.base); }
+        if (trace && lane == 0) { trace(trace_user, t, 0, upP.n, ws.cap, upP.base); trace(trace_user, t, 1, downP.n, ws.cap, downP.base); }
 #endif
-    const unsigned long long off = store_alloc(sp, sw, store_record_bytes(upP.n, downP.n));
-    if (off == ~0ull) { status = PSD_ST_STORE_EXHAUSTED; break; }
-    store_write(ws, sp.base + off, t, upP, downP);
-    if (lane == (t & 31)) my_off = off;
-    if ((t & 31) == 31 || t == N - 1) {
-      const int r = (t & ~31) + lane;
-      if (r <= t) psd_st_cs_u64(pb.index + r, my_off);
+        const unsigned long long off = store_alloc(sp, sw, store_record_bytes(upP.n, downP.n));
+        if (off == ~0ull) status = PSD_ST_STORE_EXHAUSTED;
+        else {
+          store_write(ws, sp.base + off, t, upP, downP);
+          if (lane == (t & 31)) my_off = off;
+          if ((t & 31) == 31 || t == N - 1) {
+            const int r = (t & ~31) + lane;
+            if (r <= t) psd_st_cs_u64(index + r, my_off);
+          }
+        }
+      }
+      t++;
+      if (status != PSD_ST_OK || t == N) {
+        double bc = 0, bx = 0, bpx = 0; int bbi = -1;
+        if (status == PSD_ST_OK) best_piece(ws, downP, dmin, &bc, &bx, &bbi, &bpx);
+        if (lane == 0) {
+          DpResult* res = &Q.results[id];
+          res->status = status; res->back_i = bbi; res->best_cost = bc; res->best_x = bx; res->back_x = bpx;
+          res->total_intervals = total_iv; res->max_intervals = max_iv; res->n_segments = 0; res->n_equality = 0;
+        }
+        fetch = true;
+      }
     }
-  }
-  double bc = 0, bx = 0, bpx = 0; int bbi = -1;
-  if (status == PSD_ST_OK) best_piece(ws, downP, pb.dmin, &bc, &bx, &bbi, &bpx);
-  if (lane == 0) {
-    res->status = status; res->back_i = bbi; res->best_cost = bc; res->best_x = bx; res->back_x = bpx;
-    res->total_intervals = total_iv; res->max_intervals = max_iv; res->n_segments = 0; res->n_equality = 0;
+    // a warp that is about to fetch may still get work: keep the block alive until every warp has
+    // seen an empty queue
+    if (!psd_block_or(have)) break;
   }
 }
 
