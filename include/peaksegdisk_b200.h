@@ -117,7 +117,7 @@ int psd_plan_get_stats(const psd_plan *plan, psd_stats *out);
 /* Replaces problem id's penalty (used by the sequential search to re-solve the same rows). */
 int psd_plan_set_penalty(psd_plan *plan, int id, double penalty, int penalty_is_inf);
 
-/* Tunables (call before psd_plan_create): "piece_cap" (shared-memory tier, default 64),
+/* Tunables (call before psd_plan_create): "piece_cap" (shared-memory tier, default 48),
  * "overflow_cap" (global tier, default 8192), "store_gb" (HBM pool, default 0 = auto),
  * "chunk_kb" (store chunk, default 64), "warps_per_block" is fixed at 4. */
 int psd_set_option(const char *name, double value);

@@ -23,7 +23,7 @@
 #include "plan_internal.h"
 
 #ifndef PSD_WARPS_PER_BLOCK
-#define PSD_WARPS_PER_BLOCK 12   /* one phase-locked block per SM at 168 registers/thread */
+#define PSD_WARPS_PER_BLOCK 20   /* one phase-locked block per SM; built with -maxrregcount=96 (Makefile) */
 #endif
 #define PSD_TAB_BYTES 4096
 
@@ -106,7 +106,7 @@ fpop_backtrack_kernel(const BtKernelParams P) {
 namespace {
 thread_local std::string g_last_error;
 std::mutex g_opt_mutex;
-struct Options { int piece_cap = 64; int overflow_cap = 8192; double store_gb = 0; int chunk_kb = 64; int max_warps_per_sm = 0; } g_opt;
+struct Options { int piece_cap = 48; int overflow_cap = 8192; double store_gb = 0; int chunk_kb = 64; int max_warps_per_sm = 0; } g_opt;
 
 bool cuda_ok(cudaError_t e, const char* what) {
   if (e == cudaSuccess) return true;
@@ -196,6 +196,9 @@ psd_plan* psd_plan_create_impl(int device) {
   psd_plan* p = new psd_plan();
   p->device = device;
   { std::lock_guard<std::mutex> lk(g_opt_mutex); p->opt = g_opt; }
+  // environment overrides (tuning experiments): PSD_PIECE_CAP, PSD_STORE_GB
+  if (const char* e = getenv("PSD_PIECE_CAP")) p->opt.piece_cap = atoi(e);
+  if (const char* e = getenv("PSD_STORE_GB")) p->opt.store_gb = atof(e);
   memset(&p->stats, 0, sizeof p->stats);
   return p;
 }

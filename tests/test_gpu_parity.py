@@ -266,7 +266,7 @@ def test_store_waves_and_small_piece_tier_give_identical_results(psd):
         plan, ids2 = psd.solve_batch(probs)
     finally:
         lib.psd_set_option(b"store_gb", 0.0)
-        lib.psd_set_option(b"piece_cap", 64.0)
+        lib.psd_set_option(b"piece_cap", 48.0)
     st = plan.stats()
     assert st["n_waves"] > 1 and st["n_overflow_tier"] > 0, st
     for i, (loss, seg) in zip(ids2, want):
