@@ -61,6 +61,7 @@ fpop_dp_kernel(const DpKernelParams P) {
   ws.cap = P.cap; ws.ccap = P.ccap;
   DpQueue Q;
   Q.problems = P.problems; Q.order = P.order; Q.n_order = P.n_order; Q.cursor = P.queue; Q.results = P.results;
+  Q.first_slot = warp * (int)gridDim.x + (int)blockIdx.x;
   dp_run_queue(ws, Q, P.pool);
 }
 
@@ -159,6 +160,7 @@ struct psd_plan {
   DpResult* p_results = nullptr;
   int* p_seg_row = nullptr; double* p_seg_x = nullptr;
   unsigned long long* p_cursors = nullptr;
+  int* p_queue_init = nullptr;
   size_t p_rows_cap = 0, p_res_cap = 0, p_seg_cap = 0;
   // bookkeeping
   std::vector<int> gpu_ids;                    // problem ids that go to the GPU
@@ -185,7 +187,8 @@ struct psd_plan {
     release_device();
     if (p_weight) cudaFreeHost(p_weight); if (p_cov) cudaFreeHost(p_cov);
     if (p_results) cudaFreeHost(p_results); if (p_seg_row) cudaFreeHost(p_seg_row);
-    if (p_seg_x) cudaFreeHost(p_seg_x); if (p_cursors) cudaFreeHost(p_cursors);
+    if (p_seg_x) cudaFreeHost(p_seg_x); if (p_cursors) cudaFreeHost(p_cursors); if (p_queue_init) cudaFreeHost(p_queue_init);
+    p_queue_init = nullptr;
     p_weight = p_cov = nullptr; p_results = nullptr; p_seg_row = nullptr; p_seg_x = nullptr; p_cursors = nullptr;
     if (ev_ok) { for (auto& e : ev) cudaEventDestroy(e); ev_ok = false; }
   }
@@ -290,6 +293,7 @@ int psd_plan_upload_impl(psd_plan* p, void* stream_v) {
     p->p_seg_cap = total + ng;
   }
   if (!p->p_cursors) CK(cudaMallocHost(&p->p_cursors, sizeof(unsigned long long) * 4));
+  if (!p->p_queue_init) CK(cudaMallocHost(&p->p_queue_init, sizeof(int) * 4));
   // store pool: sized from free memory unless the option pins it
   size_t free_b = 0, total_b = 0;
   CK(cudaMemGetInfo(&free_b, &total_b));
@@ -436,14 +440,15 @@ int psd_plan_solve_impl(psd_plan* p, void* stream_v) {
       CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fpop_dp_kernel, PSD_WARPS_PER_BLOCK * 32, smem));
       grid = p->prop.multiProcessorCount * std::max(1, nb);
     }
-    grid = std::max(1, std::min(grid, (n + PSD_WARPS_PER_BLOCK - 1) / PSD_WARPS_PER_BLOCK));
+    grid = std::max(1, std::min(grid, n));   // a small batch spreads one warp per SM
     if (global_tier) {
       const unsigned long long need = (unsigned long long)grid * PSD_WARPS_PER_BLOCK * K.ws_bytes_per_warp;
       if (need > p->gws_bytes) { dfree(p->d_gws); CK(cudaMalloc(&p->d_gws, need)); p->gws_bytes = need; }
       K.gws = p->d_gws;
     }
     CK(cudaMemcpyAsync(p->d_order, todo.data(), sizeof(int) * n, cudaMemcpyHostToDevice, st));
-    CK(cudaMemsetAsync(p->d_queue, 0, sizeof(int) * 4, st));
+    p->p_queue_init[0] = grid * PSD_WARPS_PER_BLOCK;   // slots below this are assigned statically
+    CK(cudaMemcpyAsync(p->d_queue, p->p_queue_init, sizeof(int), cudaMemcpyHostToDevice, st));
     CK(cudaMemsetAsync(p->d_cursors, 0, sizeof(unsigned long long), st));   // recycle the store pool
     CK(cudaEventRecord(p->ev[2], st));
     fpop_dp_kernel<<<grid, PSD_WARPS_PER_BLOCK * 32, smem, st>>>(K);

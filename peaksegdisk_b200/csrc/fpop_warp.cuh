@@ -806,12 +806,17 @@ struct DpProblem {
 #define psd_block_or(x) __syncthreads_or(x)
 #endif
 
+// order[] lists problem ids longest first.  Slot q = warp_in_block * n_blocks + block is taken
+// statically by that warp (so the longest problems land one per SM and a small batch spreads over
+// all SMs instead of filling a few blocks); the rest are popped from the atomic cursor, which the
+// host initialises to n_blocks * warps_per_block.
 struct DpQueue {
   const DpProblem* problems;
-  const int* order;      // problem ids, longest first
+  const int* order;
   int n_order;
-  int* cursor;           // atomic cursor into order
+  int* cursor;
   DpResult* results;
+  int first_slot;        // this warp's static slot
 };
 
 PSD_DEV void dp_run_queue(const WarpWs ws, const DpQueue Q, const StorePool sp
@@ -831,12 +836,16 @@ PSD_DEV void dp_run_queue(const WarpWs ws, const DpQueue Q, const StorePool sp
   StoreWriter sw; sw.cur = 0; sw.end = 0;
   Rescale rs; rs.mul = rs.add_a = rs.add_b = rs.inv = 0;
   bool fetch = true;
+  int first_q = Q.first_slot;
   for (;;) {
     // ---- phase A: (next problem,) next row, min_less ------------------------------------------------
     if (fetch) {
-      int q = 0;
-      if (lane == 0) q = psd_atomic_add_int(Q.cursor, 1);
-      q = psd_shfl_i(q, 0);
+      int q = first_q;   // the first problem of every warp is assigned statically (see DpQueue)
+      first_q = -1;
+      if (q < 0) {
+        if (lane == 0) q = psd_atomic_add_int(Q.cursor, 1);
+        q = psd_shfl_i(q, 0);
+      }
       have = q < Q.n_order;
       fetch = false;
       if (have) {

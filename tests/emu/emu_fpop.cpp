@@ -12,12 +12,12 @@ struct Job {
   DpProblem pb; WarpWs ws; StorePool sp; DpResult* res;
   psd_trace_fn trace; void* trace_user;
   int* seg_row; double* seg_x;
-  int order0 = 0; int cursor = 0;
+  int order0 = 0; int cursor = 1;
 };
 void lane_main(void* arg) {
   Job* J = (Job*)arg;
   DpQueue Q;
-  Q.problems = &J->pb; Q.order = &J->order0; Q.n_order = 1; Q.cursor = &J->cursor; Q.results = J->res;
+  Q.problems = &J->pb; Q.order = &J->order0; Q.n_order = 1; Q.cursor = &J->cursor; Q.results = J->res; Q.first_slot = 0;
   dp_run_queue(J->ws, Q, J->sp, J->trace, J->trace_user);
   psd_syncwarp();
   backtrack_problem(J->sp.base, J->pb.index, J->pb.n_rows, J->res, J->seg_row, J->seg_x);
