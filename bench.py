@@ -30,10 +30,9 @@ UNIT = "rows*penalties/s"
 
 
 def build_workload(rank, n_vectors, quick):
-    from peaksegdisk_b200 import synth
+    from peaksegdisk_b200 import synth, shard
     probs = []
-    for k in range(n_vectors):
-        seed = rank * 1024 + k
+    for seed in shard.rank_seeds(rank, n_vectors):
         s, e, c = synth.poisson_problem(seed, 4000 if quick else None)
         for pen in synth.C2_PENALTIES:
             probs.append((s, e, c, pen))
@@ -191,6 +190,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     import peaksegdisk_b200 as psd
+    from peaksegdisk_b200 import shard
 
     probs = build_workload(rank, args.vectors, args.quick)
     plan = psd.Plan(local_rank)
@@ -219,21 +219,15 @@ def main():
         ev1.record()
         barrier()
         clocks = sampler.stop() if sampler else None
-        ms = torch.tensor([ev0.elapsed_time(ev1)], device="cuda", dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item()), clocks
+        ms, _ = shard.reduce_time_and_rows(ev0.elapsed_time(ev1), 0, dist if world > 1 else None, "cuda")
+        return ms, clocks
 
     # device-resident: rows uploaded once, only DP + backtrack inside the timed region
     plan.upload(stream)
     ms_total, clocks = timed(lambda: plan.solve(stream), args.warmup, args.steps, True)
     st = plan.stats()
     ms_per_step = ms_total / args.steps
-    total_rows = rows_per_step * world
-    if world > 1:
-        t = torch.tensor([rows_per_step], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t)
-        total_rows = float(t.item())
+    _, total_rows = shard.reduce_time_and_rows(0.0, rows_per_step, dist if world > 1 else None, "cuda")
     value = total_rows / (ms_per_step / 1e3)
     # end to end: pinned host rows -> H2D -> solve -> D2H segments, every step
     e2e_warm = 1 if args.warmup > 0 else 0
