@@ -22,9 +22,10 @@
 #include "fpop_warp.cuh"
 #include "plan_internal.h"
 
-#ifndef PSD_WARPS_PER_BLOCK
-#define PSD_WARPS_PER_BLOCK 20   /* one phase-locked block per SM; built with -maxrregcount=96 (Makefile) */
+#ifndef PSD_MAX_WARPS_PER_BLOCK
+#define PSD_MAX_WARPS_PER_BLOCK 20   /* one phase-locked block per SM; built with -maxrregcount=96 (Makefile) */
 #endif
+#define PSD_BT_WARPS_PER_BLOCK 4
 #define PSD_TAB_BYTES 4096
 
 __device__ const uint64_t d_exp_tab[256] = PSD_EXP_TAB_INIT;
@@ -42,13 +43,9 @@ struct DpKernelParams {
   unsigned long long ws_bytes_per_warp;
 };
 
-__host__ __device__ inline unsigned long long psd_ws_bytes(int cap, int ccap) {
-  // header + 4 piece lists + candidate scratch + interval scratch, 16-byte aligned (WarpWs layout)
-  unsigned long long b = PSD_WS_HDR + 4ull * 44ull * (unsigned)cap + 12ull * (unsigned)ccap + 4ull * 2ull * (unsigned)cap;
-  return (b + 15ull) & ~15ull;
-}
+static inline unsigned long long psd_ws_bytes(int cap, int ccap) { return PSD_WS_BYTES(cap, ccap); }
 
-__global__ void __launch_bounds__(PSD_WARPS_PER_BLOCK * 32)
+__global__ void __launch_bounds__(PSD_MAX_WARPS_PER_BLOCK * 32)
 fpop_dp_kernel(const DpKernelParams P) {
   uint64_t* etab = (uint64_t*)psd_smem;     // psd_smem: the block's dynamic shared memory (fpop_warp.cuh)
   uint64_t* ltab = etab + 256;
@@ -56,9 +53,9 @@ fpop_dp_kernel(const DpKernelParams P) {
   __syncthreads();
   const int warp = threadIdx.x >> 5;
   WarpWs ws;
-  ws.base = P.gws ? P.gws + ((unsigned long long)blockIdx.x * PSD_WARPS_PER_BLOCK + warp) * P.ws_bytes_per_warp
+  ws.base = P.gws ? P.gws + ((unsigned long long)blockIdx.x * (blockDim.x >> 5) + warp) * P.ws_bytes_per_warp
                   : psd_smem + PSD_TAB_BYTES + (unsigned long long)warp * P.ws_bytes_per_warp;
-  ws.cap = P.cap; ws.ccap = P.ccap;
+  ws.scratch = nullptr; ws.cap = P.cap; ws.ccap = P.ccap;
   DpQueue Q;
   Q.problems = P.problems; Q.order = P.order; Q.n_order = P.n_order; Q.cursor = P.queue; Q.results = P.results;
   Q.first_slot = warp * (int)gridDim.x + (int)blockIdx.x;
@@ -77,7 +74,7 @@ struct BtKernelParams {
   unsigned long long* seg_cursor;
 };
 
-__global__ void __launch_bounds__(PSD_WARPS_PER_BLOCK * 32)
+__global__ void __launch_bounds__(PSD_BT_WARPS_PER_BLOCK * 32)
 fpop_backtrack_kernel(const BtKernelParams P) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -172,7 +169,7 @@ struct psd_plan {
   psd_stats stats;
   cudaEvent_t ev[8];
   bool ev_ok = false;
-  int blocks_per_sm = 0, cap = 0, ccap = 0;
+  int warps_per_block = 0, cap = 0, ccap = 0;
   size_t smem_bytes = 0;
 
   ~psd_plan() { release(); }
@@ -343,20 +340,23 @@ int psd_plan_upload_impl(psd_plan* p, void* stream_v) {
 }
 
 static int configure_kernel(psd_plan* p) {
-  if (p->blocks_per_sm) return 0;
+  if (p->warps_per_block) return 0;
   int cap = p->opt.piece_cap;
   if (cap < 8) cap = 8;
   cap = (cap + 1) & ~1;
   for (;;) {
     const int ccap = 2 * cap;
-    const size_t smem = PSD_TAB_BYTES + PSD_WARPS_PER_BLOCK * psd_ws_bytes(cap, ccap);
-    if (smem <= (size_t)p->prop.sharedMemPerBlockOptin) {
+    const size_t per_warp = psd_ws_bytes(cap, ccap);
+    int w = (int)(((size_t)p->prop.sharedMemPerBlockOptin - PSD_TAB_BYTES) / per_warp);
+    w = std::min(w, PSD_MAX_WARPS_PER_BLOCK);
+    if (p->opt.max_warps_per_sm > 0) w = std::min(w, p->opt.max_warps_per_sm);
+    for (; w >= 1; w--) {   // registers may allow fewer warps than shared memory does
+      const size_t smem = PSD_TAB_BYTES + (size_t)w * per_warp;
       CK(cudaFuncSetAttribute(fpop_dp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       int nb = 0;
-      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fpop_dp_kernel, PSD_WARPS_PER_BLOCK * 32, smem));
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fpop_dp_kernel, w * 32, smem));
       if (nb >= 1) {
-        if (p->opt.max_warps_per_sm > 0) nb = std::max(1, std::min(nb, p->opt.max_warps_per_sm / PSD_WARPS_PER_BLOCK));
-        p->blocks_per_sm = nb; p->cap = cap; p->ccap = ccap; p->smem_bytes = smem;
+        p->warps_per_block = w; p->cap = cap; p->ccap = ccap; p->smem_bytes = smem;
         return 0;
       }
     }
@@ -379,7 +379,7 @@ int psd_plan_solve_impl(psd_plan* p, void* stream_v) {
   if (ng == 0) { p->solved = true; return 0; }
   int rc = configure_kernel(p);
   if (rc) return rc;
-  S.piece_cap = p->cap; S.warps_per_sm = p->blocks_per_sm * PSD_WARPS_PER_BLOCK; S.n_sm = p->prop.multiProcessorCount;
+  S.piece_cap = p->cap; S.warps_per_sm = p->warps_per_block; S.n_sm = p->prop.multiProcessorCount;
   // penalties may have changed since upload (sequential search): refresh the descriptors' penalty
   {
     std::vector<DpProblem> hp(ng);
@@ -428,37 +428,33 @@ int psd_plan_solve_impl(psd_plan* p, void* stream_v) {
     DpKernelParams K;
     K.problems = p->d_problems; K.order = p->d_order; K.n_order = n; K.queue = p->d_queue; K.results = p->d_results;
     K.pool.base = p->d_pool; K.pool.cursor = p->d_cursors; K.pool.n_chunks = p->pool_bytes / chunk; K.pool.chunk_bytes = chunk;
-    int grid; size_t smem;
+    int grid; size_t smem; int wpb;
     if (!global_tier) {
       K.cap = p->cap; K.ccap = p->ccap; K.gws = nullptr; K.ws_bytes_per_warp = psd_ws_bytes(K.cap, K.ccap);
-      smem = p->smem_bytes;
-      grid = p->prop.multiProcessorCount * p->blocks_per_sm;
+      smem = p->smem_bytes; wpb = p->warps_per_block;
     } else {
       K.cap = gcap; K.ccap = 3 * gcap; K.ws_bytes_per_warp = psd_ws_bytes(K.cap, K.ccap);
-      smem = PSD_TAB_BYTES;
-      int nb = 0;
-      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fpop_dp_kernel, PSD_WARPS_PER_BLOCK * 32, smem));
-      grid = p->prop.multiProcessorCount * std::max(1, nb);
+      smem = PSD_TAB_BYTES; wpb = std::min(8, PSD_MAX_WARPS_PER_BLOCK);
     }
-    grid = std::max(1, std::min(grid, n));   // a small batch spreads one warp per SM
+    grid = std::max(1, std::min(p->prop.multiProcessorCount, n));   // one block per SM; a small batch spreads one warp per SM
     if (global_tier) {
-      const unsigned long long need = (unsigned long long)grid * PSD_WARPS_PER_BLOCK * K.ws_bytes_per_warp;
+      const unsigned long long need = (unsigned long long)grid * wpb * K.ws_bytes_per_warp;
       if (need > p->gws_bytes) { dfree(p->d_gws); CK(cudaMalloc(&p->d_gws, need)); p->gws_bytes = need; }
       K.gws = p->d_gws;
     }
     CK(cudaMemcpyAsync(p->d_order, todo.data(), sizeof(int) * n, cudaMemcpyHostToDevice, st));
-    p->p_queue_init[0] = grid * PSD_WARPS_PER_BLOCK;   // slots below this are assigned statically
+    p->p_queue_init[0] = grid * wpb;   // slots below this are assigned statically
     CK(cudaMemcpyAsync(p->d_queue, p->p_queue_init, sizeof(int), cudaMemcpyHostToDevice, st));
     CK(cudaMemsetAsync(p->d_cursors, 0, sizeof(unsigned long long), st));   // recycle the store pool
     CK(cudaEventRecord(p->ev[2], st));
-    fpop_dp_kernel<<<grid, PSD_WARPS_PER_BLOCK * 32, smem, st>>>(K);
+    fpop_dp_kernel<<<grid, wpb * 32, smem, st>>>(K);
     CK(cudaGetLastError());
     CK(cudaEventRecord(p->ev[3], st));
     BtKernelParams B;
     B.problems = p->d_problems; B.order = p->d_order; B.n_order = n; B.results = p->d_results; B.pool = p->d_pool;
     B.seg_scratch_off = p->d_seg_scratch_off; B.scratch_row = p->d_scratch_row; B.scratch_x = p->d_scratch_x;
     B.seg_row = p->d_seg_row; B.seg_x = p->d_seg_x; B.seg_cursor = p->d_cursors + 1;
-    fpop_backtrack_kernel<<<(n + PSD_WARPS_PER_BLOCK - 1) / PSD_WARPS_PER_BLOCK, PSD_WARPS_PER_BLOCK * 32, 0, st>>>(B);
+    fpop_backtrack_kernel<<<(n + PSD_BT_WARPS_PER_BLOCK - 1) / PSD_BT_WARPS_PER_BLOCK, PSD_BT_WARPS_PER_BLOCK * 32, 0, st>>>(B);
     CK(cudaGetLastError());
     CK(cudaEventRecord(p->ev[4], st));
     S.n_launches += 2; S.n_waves++;

@@ -42,6 +42,16 @@
 #define PSD_DEV __device__ __forceinline__
 #define PSD_DEVNI __device__ __noinline__
 PSD_DEV int psd_lane() { return (int)(threadIdx.x & 31u); }
+// 16-lane groups: the two half-warps of a problem's warp run the up- and the down-recursion
+PSD_DEV int psd_glane() { return (int)(threadIdx.x & 15u); }
+PSD_DEV unsigned psd_gmask_() { return 0xffffu << (threadIdx.x & 16u); }
+PSD_DEV double psd_g_shfl_d(double v, int src) { return __shfl_sync(psd_gmask_(), v, src, 16); }
+PSD_DEV int psd_g_shfl_i(int v, int src) { return __shfl_sync(psd_gmask_(), v, src, 16); }
+PSD_DEV double psd_g_shfl_up_d(double v, int d) { return __shfl_up_sync(psd_gmask_(), v, d, 16); }
+PSD_DEV double psd_g_shfl_down_d(double v, int d) { return __shfl_down_sync(psd_gmask_(), v, d, 16); }
+PSD_DEV int psd_g_shfl_up_i(int v, int d) { return __shfl_up_sync(psd_gmask_(), v, d, 16); }
+PSD_DEV unsigned psd_g_ballot(int p) { return (__ballot_sync(psd_gmask_(), p) >> (threadIdx.x & 16u)) & 0xffffu; }
+PSD_DEV void psd_g_sync() { __syncwarp(psd_gmask_()); }
 PSD_DEV double psd_shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 PSD_DEV int psd_shfl_i(int v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 PSD_DEV unsigned long long psd_shfl_u64(unsigned long long v, int src) { return __shfl_sync(0xffffffffu, v, src); }
@@ -64,6 +74,7 @@ PSD_DEV void psd_st_cs_u64(unsigned long long* p, unsigned long long v) { __stcs
 PSD_DEV void psd_st_cs_u4(unsigned* p, unsigned a, unsigned b, unsigned c, unsigned d) { __stcs((uint4*)p, make_uint4(a, b, c, d)); }
 #endif
 
+#define PSD_G 16             /* lanes per operator group (half a warp) */
 #define PSD_EPS 1e-12        /* NEWTON_EPSILON, src/funPieceListLog.cpp:9 */
 #define PSD_MAX_STEPS 100    /* NEWTON_STEPS,   src/funPieceListLog.cpp:10 */
 
@@ -89,16 +100,23 @@ struct PList { double* base; int n; };
 
 // Per-warp workspace (shared memory in the fast tier, global memory in the overflow tier):
 //   [0,16)  header: int flags (bit 0 = a capacity was exceeded, bit 1 = an impossible branch taken)
-//   4 piece lists of `cap` pieces, then candidate right ends (ccap doubles), interval codes
-//   (2*cap ints: i_f | i_g << 16) and candidate sources (ccap ints: bit 30 = from g | piece index).
-// The handle is three words and is passed BY VALUE so the operators can be real (non-inlined)
+//   6 piece lists of `cap` pieces: up_{t-1}, down_{t-1}, up_t, down_t, min-less result, min-more result
+//   2 x scratch (one per half-warp group): candidate right ends (ccap doubles), interval codes
+//   (2*cap ints: i_f | i_g << 16), candidate sources (ccap ints: bit 30 = from g | piece index).
+// The handle is passed BY VALUE (`scratch` already points at the calling group's scratch) so the operators can be real (non-inlined)
 // functions: the DP's code footprint has to stay close to the instruction cache (profiles/).
-struct WarpWs { unsigned char* base; int cap; int ccap; };
+struct WarpWs { unsigned char* base; unsigned char* scratch; int cap; int ccap; };
 #define PSD_WS_HDR 16
+#define PSD_WS_LISTS 6
 #define PSD_FLAG_OVERFLOW 1
 #define PSD_FLAG_INTERNAL 2
+// one group's scratch: candidate right ends (ccap doubles), interval codes (2*cap ints), candidate
+// sources (ccap ints)
+#define PSD_WS_SCRATCH_BYTES(cap, ccap) (12ull * (unsigned)(ccap) + 8ull * (unsigned)(cap))
+#define PSD_WS_BYTES(cap, ccap) ((PSD_WS_HDR + (unsigned long long)PSD_WS_LISTS * 44ull * (unsigned)(cap) + 2ull * PSD_WS_SCRATCH_BYTES(cap, ccap) + 15ull) & ~15ull)
 PSD_DEV double* ws_list(const WarpWs w, int k) { return (double*)(w.base + PSD_WS_HDR + (unsigned long long)k * 44ull * (unsigned)w.cap); }
-PSD_DEV double* ws_cand_x(const WarpWs w) { return (double*)(w.base + PSD_WS_HDR + 176ull * (unsigned)w.cap); }
+PSD_DEV unsigned char* ws_scratch0(const WarpWs w) { return w.base + PSD_WS_HDR + (unsigned long long)PSD_WS_LISTS * 44ull * (unsigned)w.cap; }
+PSD_DEV double* ws_cand_x(const WarpWs w) { return (double*)w.scratch; }
 PSD_DEV int* ws_ivl(const WarpWs w) { return (int*)(ws_cand_x(w) + w.ccap); }
 PSD_DEV int* ws_cand_s(const WarpWs w) { return ws_ivl(w) + 2 * w.cap; }
 PSD_DEV volatile int* ws_flags(const WarpWs w) { return (volatile int*)w.base; }
@@ -212,17 +230,17 @@ PSD_DEV void pl_emit(const WarpWs ws, const PList out, int k, double a, double b
 
 // ---- set_to_min_less_of, then set_prev_seg_end(stamp) and add(0,0,cshift) --------------------------
 PSD_DEVNI int min_less_op(const WarpWs ws, const PList in, const PList out, double dmin, int stamp, double cshift) {
-  const int lane = psd_lane();
+  const int lane = psd_glane();   // lane within this 16-lane group
   const int cap = ws.cap;
   const int n = in.n;
   double level = PSD_INF;    // cost of the pending flat piece; +inf while following the input
   double left_edge = dmin;   // where the next output piece starts
   double arg_at = PSD_INF;   // where the flat piece's minimum is attained
   int out_n = 0;
-  for (int base = 0; base < n; base += 32) {
+  for (int base = 0; base < n; base += PSD_G) {
     const int i = base + lane;
     const bool valid = i < n;
-    const int end = (n - base < 32) ? n : base + 32;
+    const int end = (n - base < PSD_G) ? n : base + PSD_G;
     double a = 0, b = 0, c = 0, hi = 0, lo = 0;
     double cl = 0, cr = 0, m = 0, mu = 0, cmu = 0, c2 = 0;
     if (valid) {
@@ -238,9 +256,9 @@ PSD_DEVNI int min_less_op(const WarpWs ws, const PList in, const PList out, doub
       }
     }
     // cost of the next piece at its left end
-    double nl = psd_shfl_down_d(cl, 1);
+    double nl = psd_g_shfl_down_d(cl, 1);
     const bool has_next = i + 1 < n;
-    if (lane == 31 && has_next) nl = pc_cost(PL_A(in, i + 1), PL_B(in, i + 1), PL_C(in, i + 1), hi);
+    if (lane == PSD_G - 1 && has_next) nl = pc_cost(PL_A(in, i + 1), PL_B(in, i + 1), PL_C(in, i + 1), hi);
     // what this piece does when reached while following the input:
     // 0 = copied whole, 1 = a flat stretch starts at its left end, 2 = its minimum is interior
     int kind = 0;
@@ -258,14 +276,14 @@ PSD_DEVNI int min_less_op(const WarpWs ws, const PList in, const PList out, doub
     int pos = base;
     while (pos < end) {
       if (level == PSD_INF) {
-        const unsigned mask = psd_ballot(valid && i >= pos && kind != 0);
+        const unsigned mask = psd_g_ballot(valid && i >= pos && kind != 0);
         const int first = mask ? base + psd_ffs(mask) - 1 : end;
         if (valid && i >= pos && i < first) pl_emit(ws, out, out_n + (i - pos), a + 0.0, b + 0.0, c + cshift, hi, PSD_INF, stamp);
         const int src = (first < end) ? first - base : 0;
-        const int kf = psd_shfl_i(kind, src);
-        const double lo_f = psd_shfl_d(lo, src), cl_f = psd_shfl_d(cl, src);
-        const double mu_f = psd_shfl_d(mu, src), cmu_f = psd_shfl_d(cmu, src);
-        const double hi_last = psd_shfl_d(hi, end - 1 - base);
+        const int kf = psd_g_shfl_i(kind, src);
+        const double lo_f = psd_g_shfl_d(lo, src), cl_f = psd_g_shfl_d(cl, src);
+        const double mu_f = psd_g_shfl_d(mu, src), cmu_f = psd_g_shfl_d(cmu, src);
+        const double hi_last = psd_g_shfl_d(hi, end - 1 - base);
         if (first > pos) left_edge = (first < end) ? lo_f : hi_last;
         out_n += first - pos;
         if (first >= end) { pos = end; break; }
@@ -291,11 +309,11 @@ PSD_DEVNI int min_less_op(const WarpWs ws, const PList in, const PList out, doub
             if (!flag && cr <= level + PSD_EPS) flag = 2;
           }
         }
-        const unsigned mask = psd_ballot(flag != 0);
+        const unsigned mask = psd_g_ballot(flag != 0);
         if (!mask) { pos = end; break; }
         const int src = psd_ffs(mask) - 1;
-        const int fl = psd_shfl_i(flag, src);
-        const double r_s = psd_shfl_d(r, src), hi_s = psd_shfl_d(hi, src);
+        const int fl = psd_g_shfl_i(flag, src);
+        const double r_s = psd_g_shfl_d(r, src), hi_s = psd_g_shfl_d(hi, src);
         if (fl == 3) { ws_raise(ws, PSD_FLAG_INTERNAL); pos = end; level = PSD_INF; break; }
         const double xe = (fl == 1) ? r_s : hi_s;
         if (lane == 0) pl_emit(ws, out, out_n, 0.0 + 0.0, 0.0 + 0.0, level + cshift, xe, arg_at, stamp);
@@ -309,20 +327,20 @@ PSD_DEVNI int min_less_op(const WarpWs ws, const PList in, const PList out, doub
     if (lane == 0) pl_emit(ws, out, out_n, 0.0 + 0.0, 0.0 + 0.0, level + cshift, PL_X(in, n - 1), arg_at, stamp);
     out_n++;
   }
-  psd_syncwarp();
+  psd_g_sync();
   return out_n;
 }
 
 // ---- set_to_min_more_of, then set_prev_seg_end(stamp) ---------------------------------------------
 PSD_DEVNI int min_more_op(const WarpWs ws, const PList in, const PList out, double dmin, int stamp) {
-  const int lane = psd_lane();
+  const int lane = psd_glane();   // lane within this 16-lane group
   const int cap = ws.cap;
   const int n = in.n;
   double level = PSD_INF;
   double right_edge = PL_X(in, n - 1);
   double arg_at = PSD_INF;
   int out_n = 0;   // pieces are emitted right to left, reversed at the end
-  for (int base = ((n - 1) >> 5) << 5; base >= 0; base -= 32) {
+  for (int base = ((n - 1) / PSD_G) * PSD_G; base >= 0; base -= PSD_G) {
     const int i = base + lane;
     const bool valid = i < n;
     double a = 0, b = 0, c = 0, hi = 0, lo = 0;
@@ -340,7 +358,7 @@ PSD_DEVNI int min_more_op(const WarpWs ws, const PList in, const PList out, doub
       }
     }
     // cost of the previous piece at its right end
-    double pr = psd_shfl_up_d(cr, 1);
+    double pr = psd_g_shfl_up_d(cr, 1);
     const bool has_prev = i > 0;
     if (lane == 0 && has_prev && valid) pr = pc_cost(PL_A(in, i - 1), PL_B(in, i - 1), PL_C(in, i - 1), lo);
     int kind = 0;  // 0 = copied whole, 1 = flat stretch starts at its right end, 2 = interior minimum
@@ -349,17 +367,17 @@ PSD_DEVNI int min_more_op(const WarpWs ws, const PList in, const PList out, doub
       if (hi <= mu) kind = (PSD_EPS < cl - cr) ? 1 : 0;
       else if (lo < mu && PSD_EPS < cl - cmu && prev_ok) kind = 2;
     }
-    int pos = (n - 1 - base < 31) ? n - 1 : base + 31;   // highest unprocessed piece
+    int pos = (n - 1 - base < PSD_G - 1) ? n - 1 : base + PSD_G - 1;   // highest unprocessed piece
     while (pos >= base) {
       if (level == PSD_INF) {
-        const unsigned mask = psd_ballot(valid && i <= pos && kind != 0);
+        const unsigned mask = psd_g_ballot(valid && i <= pos && kind != 0);
         const int first = mask ? base + 31 - psd_clz(mask) : base - 1;
         if (valid && i <= pos && i > first) pl_emit(ws, out, out_n + (pos - i), a, b, c, (i == pos) ? right_edge : hi, PSD_INF, stamp);
         const int src = (first >= base) ? first - base : 0;
-        const int kf = psd_shfl_i(kind, src);
-        const double hi_f = psd_shfl_d(hi, src), cr_f = psd_shfl_d(cr, src);
-        const double mu_f = psd_shfl_d(mu, src), cmu_f = psd_shfl_d(cmu, src);
-        const double lo_b = psd_shfl_d(lo, 0);
+        const int kf = psd_g_shfl_i(kind, src);
+        const double hi_f = psd_g_shfl_d(hi, src), cr_f = psd_g_shfl_d(cr, src);
+        const double mu_f = psd_g_shfl_d(mu, src), cmu_f = psd_g_shfl_d(cmu, src);
+        const double lo_b = psd_g_shfl_d(lo, 0);
         if (first < pos) right_edge = (first >= base) ? hi_f : lo_b;
         out_n += pos - first;
         if (first < base) { pos = base - 1; break; }
@@ -381,11 +399,11 @@ PSD_DEVNI int min_more_op(const WarpWs ws, const PList in, const PList out, doub
           if (lo < r && r < hi) flag = 1;
           else if (cl <= level + PSD_EPS) flag = 2;
         }
-        const unsigned mask = psd_ballot(flag != 0);
+        const unsigned mask = psd_g_ballot(flag != 0);
         if (!mask) { pos = base - 1; break; }
         const int src = 31 - psd_clz(mask);
-        const int fl = psd_shfl_i(flag, src);
-        const double r_s = psd_shfl_d(r, src), lo_s = psd_shfl_d(lo, src);
+        const int fl = psd_g_shfl_i(flag, src);
+        const double r_s = psd_g_shfl_d(r, src), lo_s = psd_g_shfl_d(lo, src);
         if (lane == 0) pl_emit(ws, out, out_n, 0.0, 0.0, level, right_edge, arg_at, stamp);
         out_n++;
         level = PSD_INF;
@@ -398,11 +416,11 @@ PSD_DEVNI int min_more_op(const WarpWs ws, const PList in, const PList out, doub
     if (lane == 0) pl_emit(ws, out, out_n, 0.0, 0.0, level, right_edge, arg_at, stamp);
     out_n++;
   }
-  psd_syncwarp();
+  psd_g_sync();
   // reverse into left-to-right order
   const int live = out_n < cap ? out_n : cap;
   if (out_n <= cap) {
-    for (int k = lane; k < (live >> 1); k += 32) {
+    for (int k = lane; k < (live >> 1); k += PSD_G) {
       const int j = live - 1 - k;
       double t;
       t = PL_A(out, k); PL_A(out, k) = PL_A(out, j); PL_A(out, j) = t;
@@ -413,7 +431,7 @@ PSD_DEVNI int min_more_op(const WarpWs ws, const PList in, const PList out, doub
       const int ti = PL_I(out, k); PL_I(out, k) = PL_I(out, j); PL_I(out, j) = ti;
     }
   }
-  psd_syncwarp();
+  psd_g_sync();
   return out_n;
 }
 
@@ -527,7 +545,7 @@ PSD_DEV PairOut pair_rule(const int cap, const PList f, const PList g, int i, in
 // ---- set_to_min_env_of(f, g) followed by the row rescale -------------------------------------------
 // f is the freshly built min-less/min-more function, g the previous cost function.
 PSD_DEVNI int min_env_op(const WarpWs ws, const PList f, const PList g, const PList out, double dmin, const Rescale rs) {
-  const int lane = psd_lane();
+  const int lane = psd_glane();   // lane within this 16-lane group
   const int cap = ws.cap, ccap = ws.ccap;
   int* const ivl = ws_ivl(ws);
   double* const cand_x = ws_cand_x(ws);
@@ -537,7 +555,7 @@ PSD_DEVNI int min_env_op(const WarpWs ws, const PList f, const PList g, const PL
   int K = 0;
   {
     int carry_next = 0;   // first f piece that can overlap the next g piece
-    for (int base = 0; base < ng; base += 32) {
+    for (int base = 0; base < ng; base += PSD_G) {
       const int j = base + lane;
       const bool valid = j < ng;
       int e = 0, tie = 0;
@@ -551,26 +569,26 @@ PSD_DEVNI int min_env_op(const WarpWs ws, const PList f, const PList g, const PL
         e = lo_i;
         tie = (PL_X(f, e) == v) ? 1 : 0;
       }
-      int s = psd_shfl_up_i(e + tie, 1);
+      int s = psd_g_shfl_up_i(e + tie, 1);
       if (lane == 0) s = carry_next;
       int cnt = valid ? (e - s + 1) : 0;
       if (cnt < 0) cnt = 0;
       // exclusive scan of cnt
       int incl = cnt;
-      for (int d = 1; d < 32; d <<= 1) { const int t = psd_shfl_up_i(incl, d); if (lane >= d) incl += t; }
+      for (int d = 1; d < PSD_G; d <<= 1) { const int t = psd_g_shfl_up_i(incl, d); if (lane >= d) incl += t; }
       const int off = K + incl - cnt;
       for (int q = 0; q < cnt; q++) {
         if (off + q < 2 * cap) ivl[off + q] = (s + q) | (j << 16); else ws_raise(ws, PSD_FLAG_OVERFLOW);
       }
-      K += psd_shfl_i(incl, 31);
-      carry_next = psd_shfl_i(e + tie, (ng - base < 32) ? ng - base - 1 : 31);
+      K += psd_g_shfl_i(incl, PSD_G - 1);
+      carry_next = psd_g_shfl_i(e + tie, (ng - base < PSD_G) ? ng - base - 1 : PSD_G - 1);
     }
   }
-  psd_syncwarp();
+  psd_g_sync();
   if (K > 2 * cap) { K = 2 * cap; }
   // 2. crossing rule per interval -> candidate pieces
   int T = 0;
-  for (int base = 0; base < K; base += 32) {
+  for (int base = 0; base < K; base += PSD_G) {
     const int q = base + lane;
     const bool valid = q < K;
     PairOut o; o.nc = 0; o.s0 = 0; o.x1 = 0; o.x2 = 0;
@@ -582,7 +600,7 @@ PSD_DEVNI int min_env_op(const WarpWs ws, const PList f, const PList g, const PL
       o = pair_rule(cap, f, g, i, j, dmin, &lo, &hi);
     }
     int incl = o.nc;
-    for (int d = 1; d < 32; d <<= 1) { const int t = psd_shfl_up_i(incl, d); if (lane >= d) incl += t; }
+    for (int d = 1; d < PSD_G; d <<= 1) { const int t = psd_g_shfl_up_i(incl, d); if (lane >= d) incl += t; }
     const int off = T + incl - o.nc;
     if (o.nc > 0) {
       const int sf = i, sg = j | PSD_SRC_G;
@@ -593,16 +611,16 @@ PSD_DEVNI int min_env_op(const WarpWs ws, const PList f, const PList g, const PL
         if (o.nc > 2) { cand_s[off + 2] = c0; cand_x[off + 2] = hi; }
       } else ws_raise(ws, PSD_FLAG_OVERFLOW);
     }
-    T += psd_shfl_i(incl, 31);
+    T += psd_g_shfl_i(incl, PSD_G - 1);
   }
-  psd_syncwarp();
+  psd_g_sync();
   if (T > ccap) T = ccap;
   // 3. push_piece: merge each candidate into the current run when it equals the run's head
   int out_n = 0;
   bool carry_ok = false;
   double ha = 0, hb = 0, hc = 0, hp = 0; int hi_i = 0;   // head of the run open at the chunk boundary
   int carry_slot = 0;
-  for (int base = 0; base < T; base += 32) {
+  for (int base = 0; base < T; base += PSD_G) {
     const int q = base + lane;
     const bool valid = q < T;
     double a = 0, b = 0, c = 0, p = 0, x = 0; int bi = 0;
@@ -614,29 +632,29 @@ PSD_DEVNI int min_env_op(const WarpWs ws, const PList f, const PList g, const PL
       else { a = PL_A(f, k); b = PL_B(f, k); c = PL_C(f, k); p = PL_P(f, k); bi = PL_I(f, k); }
     }
     // first guess: a candidate continues the run iff it equals its immediate predecessor
-    double pa_ = psd_shfl_up_d(a, 1), pb_ = psd_shfl_up_d(b, 1), pc_ = psd_shfl_up_d(c, 1), pp_ = psd_shfl_up_d(p, 1);
-    int pi_ = psd_shfl_up_i(bi, 1);
+    double pa_ = psd_g_shfl_up_d(a, 1), pb_ = psd_g_shfl_up_d(b, 1), pc_ = psd_g_shfl_up_d(c, 1), pp_ = psd_g_shfl_up_d(p, 1);
+    int pi_ = psd_g_shfl_up_i(bi, 1);
     bool pv = lane > 0;
     if (lane == 0) { pa_ = ha; pb_ = hb; pc_ = hc; pp_ = hp; pi_ = hi_i; pv = carry_ok; }
     bool head = valid && !(pv && same_coefs(pa_, pb_, pc_, a, b, c) && p == pp_ && bi == pi_);
     // verify against the true run heads (push_piece compares with the list's last piece, whose
     // coefficients are those of the run's first member); repair the first disagreement and retry
     for (;;) {
-      const unsigned hm = psd_ballot(head);
+      const unsigned hm = psd_g_ballot(head);
       const unsigned below = hm & ((1u << lane) - 1u);
       const int hl = below ? 31 - psd_clz(below) : -1;   // head of the run candidate q-1 belongs to
-      double ra = psd_shfl_d(a, hl < 0 ? 0 : hl), rb = psd_shfl_d(b, hl < 0 ? 0 : hl), rc = psd_shfl_d(c, hl < 0 ? 0 : hl);
-      double rp = psd_shfl_d(p, hl < 0 ? 0 : hl);
-      int ri = psd_shfl_i(bi, hl < 0 ? 0 : hl);
+      double ra = psd_g_shfl_d(a, hl < 0 ? 0 : hl), rb = psd_g_shfl_d(b, hl < 0 ? 0 : hl), rc = psd_g_shfl_d(c, hl < 0 ? 0 : hl);
+      double rp = psd_g_shfl_d(p, hl < 0 ? 0 : hl);
+      int ri = psd_g_shfl_i(bi, hl < 0 ? 0 : hl);
       bool rv = true;
       if (hl < 0) { ra = ha; rb = hb; rc = hc; rp = hp; ri = hi_i; rv = carry_ok; }
       const bool want_head = valid && !(rv && same_coefs(ra, rb, rc, a, b, c) && p == rp && bi == ri);
-      const unsigned bad = psd_ballot(valid && want_head != head);
+      const unsigned bad = psd_g_ballot(valid && want_head != head);
       if (!bad) break;
       if (lane == psd_ffs(bad) - 1) head = want_head;
     }
-    const unsigned hm = psd_ballot(head);
-    const unsigned vm = psd_ballot(valid);
+    const unsigned hm = psd_g_ballot(head);
+    const unsigned vm = psd_g_ballot(valid);
     const int rank = psd_popc(hm & ((1u << lane) - 1u));
     const unsigned upto = hm & ((2u << lane) - 1u);       // heads at or below this lane
     const int my_head = upto ? 31 - psd_clz(upto) : -1;
@@ -652,35 +670,35 @@ PSD_DEVNI int min_env_op(const WarpWs ws, const PList f, const PList g, const PL
       } else ws_raise(ws, PSD_FLAG_OVERFLOW);
     }
     // the last member of every run (within this chunk) sets the run's right end
-    const bool last_valid = valid && (lane == 31 || !((vm >> (lane + 1)) & 1u));
-    const bool next_is_head = (lane < 31) && ((hm >> (lane + 1)) & 1u);
+    const bool last_valid = valid && (lane == PSD_G - 1 || !((vm >> (lane + 1)) & 1u));
+    const bool next_is_head = (lane < PSD_G - 1) && ((hm >> (lane + 1)) & 1u);
     if (valid && (last_valid || next_is_head)) { if (slot < cap) PL_X(out, slot) = x; }
     // carry the open run into the next chunk
     const int n_heads = psd_popc(hm);
     if (n_heads) {
       const int last_head = 31 - psd_clz(hm);
-      ha = psd_shfl_d(a, last_head); hb = psd_shfl_d(b, last_head); hc = psd_shfl_d(c, last_head);
-      hp = psd_shfl_d(p, last_head); hi_i = psd_shfl_i(bi, last_head);
+      ha = psd_g_shfl_d(a, last_head); hb = psd_g_shfl_d(b, last_head); hc = psd_g_shfl_d(c, last_head);
+      hp = psd_g_shfl_d(p, last_head); hi_i = psd_g_shfl_i(bi, last_head);
       carry_slot = out_n + n_heads - 1;
       carry_ok = true;
     }
     out_n += n_heads;
   }
-  psd_syncwarp();
+  psd_g_sync();
   return out_n;
 }
 
 // copy with rescale (rows 0/1 of the DP, src/PeakSegFPOPLog.cpp:297-299, 324-328)
 PSD_DEVNI int copy_rescale_op(const WarpWs ws, const PList in, const PList out, const Rescale rs) {
-  const int lane = psd_lane();
+  const int lane = psd_glane();   // lane within this 16-lane group
   const int cap = ws.cap;
-  for (int k = lane; k < in.n; k += 32) {
+  for (int k = lane; k < in.n; k += PSD_G) {
     PL_A(out, k) = ((PL_A(in, k) * rs.mul) + rs.add_a) * rs.inv;
     PL_B(out, k) = ((PL_B(in, k) * rs.mul) + rs.add_b) * rs.inv;
     PL_C(out, k) = ((PL_C(in, k) * rs.mul) + 0.0) * rs.inv;
     PL_X(out, k) = PL_X(in, k); PL_P(out, k) = PL_P(in, k); PL_I(out, k) = PL_I(in, k);
   }
-  psd_syncwarp();
+  psd_g_sync();
   return in.n;
 }
 
@@ -793,11 +811,19 @@ struct DpProblem {
 
 // ---- the DP driver: a block of warps works through a queue of problems in PHASE LOCK ----------------
 // Each warp owns one problem at a time (src/PeakSegFPOPLog.cpp:258-397 + Minimize at :404) and pops
-// the next one from an atomic queue when it finishes.  The warps of a block are independent, but
-// they cross a block barrier between the four operators of a row, so that at any moment all warps
-// of the SM execute the SAME operator: the DP's code (~110 KB of SASS) is several times the
-// instruction cache, and without the phase lock 84 % of all stall samples were instruction fetch
-// (profiles/README.md).  Rows need not be aligned across warps, only phases.
+// the next one from an atomic queue when it finishes.
+//
+// Inside a row the two recursions are independent given row t-1:
+//     up_t   = rescale(min_env(min_less(down_{t-1}) + penalty/W, up_{t-1}))      lanes  0-15
+//     down_t = rescale(min_env(min_more(up_{t-1}),               down_{t-1}))    lanes 16-31
+// so the warp's two 16-lane groups run them side by side: the min_env calls of both groups are ONE
+// converged call (same code, different lists), which halves the issue slots and the latency of the
+// most expensive operator; min_less / min_more are different code and overlap only in latency.
+//
+// The warps of a block are independent, but they cross a block barrier between the phases of a row
+// so that at any moment all warps of the SM execute the SAME operators: the DP's code (~110 KB of
+// SASS) is several times the instruction cache, and without the phase lock 84 % of all stall
+// samples were instruction fetch (profiles/README.md).  Rows need not be aligned, only phases.
 #if defined(PSD_EMU)
 #define psd_block_sync() do {} while (0)
 #define psd_block_or(x) (x)
@@ -825,20 +851,24 @@ PSD_DEV void dp_run_queue(const WarpWs ws, const DpQueue Q, const StorePool sp
 #endif
 ) {
   const int lane = psd_lane();
+  const int grp = lane >> 4;          // 0: up chain (min_less), 1: down chain (min_more)
+  WarpWs wg = ws;                     // this group's view: its own scratch
+  wg.scratch = ws_scratch0(ws) + (unsigned long long)grp * PSD_WS_SCRATCH_BYTES(ws.cap, ws.ccap);
   // per-warp state (uniform across lanes)
   int have = 0, id = 0, t = 0, N = 0, status = PSD_ST_OK, max_iv = 0, w_l = 0, z_l = 0;
   const int* weight = nullptr; const int* coverage = nullptr; unsigned long long* index = nullptr;
   double penalty = 0, dmin = 0, dmax = 0, cw = 0, cw_prev = -1.0;
   unsigned long long total_iv = 0, my_off = 0;
-  PList upP, downP, tmp, fresh;
-  upP.base = ws_list(ws, 0); downP.base = ws_list(ws, 1); tmp.base = ws_list(ws, 2); fresh.base = ws_list(ws, 3);
-  upP.n = downP.n = tmp.n = fresh.n = 0;
+  PList upP, downP, upN, downN, tmp;
+  upP.base = ws_list(ws, 0); downP.base = ws_list(ws, 1); upN.base = ws_list(ws, 2); downN.base = ws_list(ws, 3);
+  tmp.base = ws_list(ws, 4 + grp);    // min-less result (group 0) / min-more result (group 1)
+  upP.n = downP.n = upN.n = downN.n = tmp.n = 0;
   StoreWriter sw; sw.cur = 0; sw.end = 0;
   Rescale rs; rs.mul = rs.add_a = rs.add_b = rs.inv = 0;
   bool fetch = true;
   int first_q = Q.first_slot;
   for (;;) {
-    // ---- phase A: (next problem,) next row, min_less ------------------------------------------------
+    // ---- phase A: (next problem,) next row; min_less on group 0 | min_more on group 1 -----------------
     if (fetch) {
       int q = first_q;   // the first problem of every warp is assigned statically (see DpQueue)
       first_q = -1;
@@ -854,8 +884,7 @@ PSD_DEV void dp_run_queue(const WarpWs ws, const DpQueue Q, const StorePool sp
         weight = pb.weight; coverage = pb.coverage; index = pb.index; N = pb.n_rows;
         penalty = pb.penalty; dmin = pb.dmin; dmax = pb.dmax;
         t = 0; status = PSD_ST_OK; max_iv = 0; total_iv = 0; cw = 0.0; cw_prev = -1.0;
-        // the four buffers keep rotating between problems; only the counts restart
-        upP.n = downP.n = tmp.n = fresh.n = 0;
+        upP.n = downP.n = upN.n = downN.n = tmp.n = 0;
         if (lane == 0) *ws_flags(ws) = 0;
         psd_syncwarp();
       }
@@ -874,30 +903,28 @@ PSD_DEV void dp_run_queue(const WarpWs ws, const DpQueue Q, const StorePool sp
         if (lane == 0) pl_emit(ws, downP, 0, 1.0, (double)(-z), 0.0, dmax, -5.0, -1);
         downP.n = 1; upP.n = 0;
         psd_syncwarp();
-      } else {
-        tmp.n = min_less_op(ws, downP, tmp, dmin, t - 1, penalty / cw_prev);
+      } else if (grp == 0) {
+        tmp.n = min_less_op(wg, downP, tmp, dmin, t - 1, penalty / cw_prev);
+      } else if (t >= 2) {
+        tmp.n = min_more_op(wg, upP, tmp, dmin, t - 1);
       }
     }
     psd_block_sync();
-    // ---- phase B: up_t = min_env(min_less + penalty, up_{t-1}) ----------------------------------------
+    // ---- phase B: both min_env's as one converged call; new functions become the previous ones ----------
     if (have && t >= 1) {
-      if (t == 1) fresh.n = copy_rescale_op(ws, tmp, fresh, rs);
-      else fresh.n = min_env_op(ws, tmp, upP, fresh, dmin, rs);
+      const PList prev = grp ? downP : upP;     // previous cost function of my chain
+      const PList dst = grp ? downN : upN;
+      int n_out;
+      if (t == 1) n_out = copy_rescale_op(wg, grp ? downP : tmp, dst, rs);   // :297-299, :324-328
+      else n_out = min_env_op(wg, tmp, prev, dst, dmin, rs);
+      psd_syncwarp();   // both chains done; their lists are visible to the whole warp
+      upN.n = psd_shfl_i(n_out, 0);
+      downN.n = psd_shfl_i(n_out, 16);
+      const PList u = upP, d = downP;
+      upP = upN; downP = downN; upN = u; downN = d;
     }
     psd_block_sync();
-    // ---- phase C: min_more(up_{t-1}) ------------------------------------------------------------------
-    if (have && t >= 2) tmp.n = min_more_op(ws, upP, tmp, dmin, t - 1);
-    psd_block_sync();
-    // ---- phase D: down_t = min_env(min_more, down_{t-1}), written where up_{t-1} lived ---------------------
-    if (have && t >= 1) {
-      if (t == 1) upP.n = copy_rescale_op(ws, downP, upP, rs);
-      else upP.n = min_env_op(ws, tmp, downP, upP, dmin, rs);
-      // rotate roles: up_prev <- fresh, down_prev <- old upP buffer, free <- old downP buffer
-      const PList old_down = downP;
-      downP = upP; upP = fresh; fresh = old_down; fresh.n = 0;
-    }
-    psd_block_sync();
-    // ---- phase E: counters, store record, end of problem ------------------------------------------------
+    // ---- phase C: counters, store record, end of problem ------------------------------------------------
     if (have) {
       const int flags = *ws_flags(ws);
       if (flags) status = (flags & PSD_FLAG_OVERFLOW) ? PSD_ST_PIECE_OVERFLOW : PSD_ST_INTERNAL;

@@ -45,9 +45,9 @@ int emu_fpop_rows(int n_rows, const int* chrom_start, const int* chrom_end, cons
   J.pb.weight = w.data(); J.pb.coverage = coverage; J.pb.n_rows = n_rows; J.pb.penalty = penalty;
   J.pb.dmin = dmin; J.pb.dmax = dmax; J.pb.index = index.data();
   const int ccap = 3 * cap;
-  const size_t ws_bytes = PSD_WS_HDR + (size_t)4 * 44 * cap + (size_t)12 * ccap + (size_t)8 * cap + 64;
+  const size_t ws_bytes = PSD_WS_BYTES(cap, ccap) + 64;
   std::vector<double> wsmem(ws_bytes / 8 + 8);
-  J.ws.base = (unsigned char*)wsmem.data(); J.ws.cap = cap; J.ws.ccap = ccap;
+  J.ws.base = (unsigned char*)wsmem.data(); J.ws.scratch = nullptr; J.ws.cap = cap; J.ws.ccap = ccap;
   const unsigned long long chunk = 1 << 16;
   std::vector<unsigned char> pool;
   unsigned long long cursor = 0;

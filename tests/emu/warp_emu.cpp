@@ -32,9 +32,15 @@ static void trampoline() {
   Warp* w = g_warp;
   w->entry(w->arg);
   Fiber& me = w->f[w->cur];
-  me.done = true;
+  me.state = DONE;
   psd_emu_switch(&me.sp, w->sched_sp);
   abort();  // a finished fiber is never resumed
+}
+
+static void die(Warp& w, const char* what) {
+  fprintf(stderr, "warp_emu: %s\n", what);
+  for (int i = 0; i < 32; i++) fprintf(stderr, "  lane %2d state %d line %d\n", i, w.f[i].state, w.f[i].site);
+  abort();
 }
 
 void run_warp(void (*entry)(void*), void* arg, int descending) {
@@ -51,31 +57,50 @@ void run_warp(void (*entry)(void*), void* arg, int descending) {
     *--sp = (uint64_t)(uintptr_t)&trampoline;
     for (int k = 0; k < 6; k++) *--sp = 0;
     w.f[i].sp = sp;
-    w.f[i].done = false;
+    w.f[i].state = RUNNABLE;
     w.f[i].site = -1;
   }
   Warp* outer = g_warp;
   g_warp = &w;
   for (;;) {
-    int n_done = 0, site = -2;
+    bool progress = false;
     for (int k = 0; k < 32; k++) {
-      int i = descending ? 31 - k : k;
-      if (w.f[i].done) { n_done++; continue; }
+      const int i = descending ? 31 - k : k;
+      if (w.f[i].state != RUNNABLE) continue;
       w.cur = i;
       psd_emu_switch(&w.sched_sp, w.f[i].sp);
-      if (w.f[i].done) { n_done++; continue; }
-      if (site == -2) site = w.f[i].site;
-      else if (site != w.f[i].site) {
-        fprintf(stderr, "warp_emu: divergent collective: lane %d at line %d, others at line %d\n", i, w.f[i].site, site);
-        abort();
+      progress = true;
+    }
+    int n_done = 0;
+    for (int i = 0; i < 32; i++) n_done += w.f[i].state == DONE;
+    if (n_done == 32) break;
+    // release a 16-lane group whose lanes all wait at the same group collective
+    for (int g = 0; g < 2; g++) {
+      bool all = true;
+      const int site = w.f[16 * g].site;
+      for (int i = 16 * g; i < 16 * g + 16; i++) all = all && w.f[i].state == WAIT_GROUP && w.f[i].site == site;
+      if (all) {
+        for (int i = 16 * g; i < 16 * g + 16; i++) w.f[i].state = RUNNABLE;
+        w.phase_g[g]++;
+        progress = true;
+      } else {
+        int n_wait = 0;
+        for (int i = 16 * g; i < 16 * g + 16; i++) n_wait += w.f[i].state == WAIT_GROUP;
+        if (n_wait == 16) die(w, "divergent group collective (lanes of one group wait at different lines)");
       }
     }
-    if (n_done == 32) break;
-    if (n_done != 0) {
-      fprintf(stderr, "warp_emu: %d lanes exited while others wait at line %d\n", n_done, site);
-      abort();
+    // release the warp when all lanes wait at the same whole-warp collective
+    {
+      bool all = true;
+      const int site = w.f[0].site;
+      for (int i = 0; i < 32; i++) all = all && w.f[i].state == WAIT_FULL && w.f[i].site == site;
+      if (all) {
+        for (int i = 0; i < 32; i++) w.f[i].state = RUNNABLE;
+        w.phase_full++;
+        progress = true;
+      }
     }
-    w.phase++;
+    if (!progress) die(w, "deadlock: no lane can run and no collective is complete");
   }
   g_warp = outer;
   for (int i = 0; i < 32; i++) free(w.f[i].stack);

@@ -3,11 +3,13 @@
 // be diffed against the oracle in the GPU-less build container.  Never linked into the product
 // library; the product has no CPU execution path.
 //
-// Model: every warp collective (shuffle, ballot, syncwarp) is a barrier.  The scheduler resumes
-// lanes in ascending or descending order (PSD_EMU_ORDER) until each reaches its next collective;
-// all 32 lanes must arrive at the same call site, otherwise the run aborts (that would be a
-// divergent full-mask collective on the GPU).  Running both orders exposes missing __syncwarp()s
-// between a shared-memory write and a cross-lane read.
+// Model: every warp collective (shuffle, ballot, sync) is a barrier, either over the whole warp or
+// over one 16-lane group (the two half-warps run different operator chains and only meet at
+// whole-warp collectives).  The scheduler resumes runnable lanes in ascending or descending order
+// until each blocks at its next collective; a group (or the warp) is released when all its lanes
+// wait at the SAME call site, otherwise the run aborts (that would be a divergent collective on the
+// GPU).  Running both orders exposes missing syncs between a shared-memory write and a
+// cross-lane read.
 #pragma once
 #include <cstdint>
 #include <cstdio>
@@ -16,13 +18,16 @@
 
 namespace psd_emu {
 
-struct Fiber { void* sp; char* stack; bool done; int site; };
+enum { RUNNABLE = 0, WAIT_GROUP = 1, WAIT_FULL = 2, DONE = 3 };
+struct Fiber { void* sp; char* stack; int state; int site; };
 struct Warp {
   Fiber f[32];
   void* sched_sp;
   int cur;
-  int phase;
-  uint64_t xchg[2][32];
+  int phase_full;
+  int phase_g[2];
+  uint64_t xchg_full[2][32];
+  uint64_t xchg_g[2][2][16];
   void (*entry)(void*);
   void* arg;
   int descending;
@@ -33,29 +38,46 @@ extern "C" void psd_emu_switch(void** save_sp, void* load_sp);
 
 inline int lane() { return g_warp->cur; }
 
-inline void barrier(int site) {
+inline void block(int kind, int site) {
   Warp* w = g_warp;
   Fiber& me = w->f[w->cur];
-  me.site = site;
+  me.state = kind; me.site = site;
   psd_emu_switch(&me.sp, w->sched_sp);
 }
 
 inline uint64_t exchange(uint64_t v, int src_lane, int site) {
   Warp* w = g_warp;
-  const int p = w->phase & 1;
-  const int me = w->cur;
-  w->xchg[p][me] = v;
-  barrier(site);
-  return g_warp->xchg[p][src_lane & 31];
+  const int p = w->phase_full & 1;
+  w->xchg_full[p][w->cur] = v;
+  block(WAIT_FULL, site);
+  return g_warp->xchg_full[p][src_lane & 31];
 }
-
 inline uint32_t ballot(int pred, int site) {
   Warp* w = g_warp;
-  const int p = w->phase & 1;
-  w->xchg[p][w->cur] = pred ? 1 : 0;
-  barrier(site);
+  const int p = w->phase_full & 1;
+  w->xchg_full[p][w->cur] = pred ? 1 : 0;
+  block(WAIT_FULL, site);
   uint32_t m = 0;
-  for (int i = 0; i < 32; i++) m |= (uint32_t)(g_warp->xchg[p][i] & 1) << i;
+  for (int i = 0; i < 32; i++) m |= (uint32_t)(g_warp->xchg_full[p][i] & 1) << i;
+  return m;
+}
+// 16-lane group versions: src is a lane index within the group
+inline uint64_t g_exchange(uint64_t v, int src_local, int site) {
+  Warp* w = g_warp;
+  const int g = w->cur >> 4, gl = w->cur & 15;
+  const int p = w->phase_g[g] & 1;
+  w->xchg_g[g][p][gl] = v;
+  block(WAIT_GROUP, site);
+  return g_warp->xchg_g[g][p][src_local & 15];
+}
+inline uint32_t g_ballot(int pred, int site) {
+  Warp* w = g_warp;
+  const int g = w->cur >> 4, gl = w->cur & 15;
+  const int p = w->phase_g[g] & 1;
+  w->xchg_g[g][p][gl] = pred ? 1 : 0;
+  block(WAIT_GROUP, site);
+  uint32_t m = 0;
+  for (int i = 0; i < 16; i++) m |= (uint32_t)(g_warp->xchg_g[g][p][i] & 1) << i;
   return m;
 }
 
@@ -69,20 +91,26 @@ void run_warp(void (*entry)(void*), void* arg, int descending);
 #define PSD_SITE __LINE__
 
 static inline int psd_lane() { return psd_emu::lane(); }
+static inline int psd_glane() { return psd_emu::lane() & 15; }
 static inline uint64_t psd_bits_(double v) { uint64_t u; memcpy(&u, &v, 8); return u; }
 static inline double psd_dbl_(uint64_t u) { double v; memcpy(&v, &u, 8); return v; }
 
+// whole-warp collectives
 #define psd_shfl_d(v, src) psd_dbl_(psd_emu::exchange(psd_bits_(v), (src), PSD_SITE))
 #define psd_shfl_i(v, src) ((int)(int64_t)psd_emu::exchange((uint64_t)(int64_t)(v), (src), PSD_SITE))
 #define psd_shfl_u64(v, src) (psd_emu::exchange((uint64_t)(v), (src), PSD_SITE))
-// up/down: lanes whose source falls outside the warp keep their own value
-#define psd_shfl_up_d(v, d) psd_dbl_(psd_emu::exchange(psd_bits_(v), (psd_lane() - (d) < 0 ? psd_lane() : psd_lane() - (d)), PSD_SITE))
-#define psd_shfl_down_d(v, d) psd_dbl_(psd_emu::exchange(psd_bits_(v), (psd_lane() + (d) > 31 ? psd_lane() : psd_lane() + (d)), PSD_SITE))
-#define psd_shfl_up_i(v, d) ((int)(int64_t)psd_emu::exchange((uint64_t)(int64_t)(v), (psd_lane() - (d) < 0 ? psd_lane() : psd_lane() - (d)), PSD_SITE))
 #define psd_shfl_xor_d(v, m) psd_dbl_(psd_emu::exchange(psd_bits_(v), psd_lane() ^ (m), PSD_SITE))
 #define psd_shfl_xor_i(v, m) ((int)(int64_t)psd_emu::exchange((uint64_t)(int64_t)(v), psd_lane() ^ (m), PSD_SITE))
 #define psd_ballot(p) psd_emu::ballot((p), PSD_SITE)
-#define psd_syncwarp() psd_emu::barrier(PSD_SITE)
+#define psd_syncwarp() psd_emu::block(psd_emu::WAIT_FULL, PSD_SITE)
+// 16-lane group collectives; up/down: lanes whose source falls outside the group keep their value
+#define psd_g_shfl_d(v, src) psd_dbl_(psd_emu::g_exchange(psd_bits_(v), (src), PSD_SITE))
+#define psd_g_shfl_i(v, src) ((int)(int64_t)psd_emu::g_exchange((uint64_t)(int64_t)(v), (src), PSD_SITE))
+#define psd_g_shfl_up_d(v, d) psd_dbl_(psd_emu::g_exchange(psd_bits_(v), (psd_glane() - (d) < 0 ? psd_glane() : psd_glane() - (d)), PSD_SITE))
+#define psd_g_shfl_down_d(v, d) psd_dbl_(psd_emu::g_exchange(psd_bits_(v), (psd_glane() + (d) > 15 ? psd_glane() : psd_glane() + (d)), PSD_SITE))
+#define psd_g_shfl_up_i(v, d) ((int)(int64_t)psd_emu::g_exchange((uint64_t)(int64_t)(v), (psd_glane() - (d) < 0 ? psd_glane() : psd_glane() - (d)), PSD_SITE))
+#define psd_g_ballot(p) psd_emu::g_ballot((p), PSD_SITE)
+#define psd_g_sync() psd_emu::block(psd_emu::WAIT_GROUP, PSD_SITE)
 
 static inline int psd_ffs(uint32_t m) { return __builtin_ffs((int)m); }
 static inline int psd_clz(uint32_t m) { return m ? __builtin_clz(m) : 32; }
