@@ -104,7 +104,7 @@ fpop_backtrack_kernel(const BtKernelParams P) {
 namespace {
 thread_local std::string g_last_error;
 std::mutex g_opt_mutex;
-struct Options { int piece_cap = 48; int overflow_cap = 8192; double store_gb = 0; int chunk_kb = 64; int max_warps_per_sm = 0; } g_opt;
+struct Options { int piece_cap = 48; int overflow_cap = 8192; double store_gb = 0; int chunk_kb = 64; int max_warps_per_sm = 0; int blocks_per_sm = 1; } g_opt;
 
 bool cuda_ok(cudaError_t e, const char* what) {
   if (e == cudaSuccess) return true;
@@ -127,6 +127,7 @@ int psd_set_option_impl(const char* name, double value) {
   else if (n == "store_gb") g_opt.store_gb = value;
   else if (n == "chunk_kb") g_opt.chunk_kb = (int)value;
   else if (n == "max_warps_per_sm") g_opt.max_warps_per_sm = (int)value;
+  else if (n == "blocks_per_sm") g_opt.blocks_per_sm = std::max(1, (int)value);
   else return PSD_ERR_ARG;
   return 0;
 }
@@ -199,6 +200,8 @@ psd_plan* psd_plan_create_impl(int device) {
   // environment overrides (tuning experiments): PSD_PIECE_CAP, PSD_STORE_GB
   if (const char* e = getenv("PSD_PIECE_CAP")) p->opt.piece_cap = atoi(e);
   if (const char* e = getenv("PSD_STORE_GB")) p->opt.store_gb = atof(e);
+  if (const char* e = getenv("PSD_MAX_WARPS")) p->opt.max_warps_per_sm = atoi(e);
+  if (const char* e = getenv("PSD_BLOCKS_PER_SM")) p->opt.blocks_per_sm = std::max(1, atoi(e));
   memset(&p->stats, 0, sizeof p->stats);
   return p;
 }
@@ -347,15 +350,18 @@ static int configure_kernel(psd_plan* p) {
   for (;;) {
     const int ccap = 2 * cap;
     const size_t per_warp = psd_ws_bytes(cap, ccap);
-    int w = (int)(((size_t)p->prop.sharedMemPerBlockOptin - PSD_TAB_BYTES) / per_warp);
+    const int nblk = p->opt.blocks_per_sm;   // independent phase-locked blocks per SM
+    // each block also costs ~1 KB of reserved shared memory
+    int w = (int)((((size_t)p->prop.sharedMemPerMultiprocessor / nblk) - 1024 - PSD_TAB_BYTES) / per_warp);
+    w = std::min(w, (int)(((size_t)p->prop.sharedMemPerBlockOptin - PSD_TAB_BYTES) / per_warp));
     w = std::min(w, PSD_MAX_WARPS_PER_BLOCK);
-    if (p->opt.max_warps_per_sm > 0) w = std::min(w, p->opt.max_warps_per_sm);
+    if (p->opt.max_warps_per_sm > 0) w = std::min(w, std::max(1, p->opt.max_warps_per_sm / nblk));
     for (; w >= 1; w--) {   // registers may allow fewer warps than shared memory does
       const size_t smem = PSD_TAB_BYTES + (size_t)w * per_warp;
       CK(cudaFuncSetAttribute(fpop_dp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       int nb = 0;
       CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fpop_dp_kernel, w * 32, smem));
-      if (nb >= 1) {
+      if (nb >= nblk) {
         p->warps_per_block = w; p->cap = cap; p->ccap = ccap; p->smem_bytes = smem;
         return 0;
       }
@@ -379,7 +385,7 @@ int psd_plan_solve_impl(psd_plan* p, void* stream_v) {
   if (ng == 0) { p->solved = true; return 0; }
   int rc = configure_kernel(p);
   if (rc) return rc;
-  S.piece_cap = p->cap; S.warps_per_sm = p->warps_per_block; S.n_sm = p->prop.multiProcessorCount;
+  S.piece_cap = p->cap; S.warps_per_sm = p->warps_per_block * p->opt.blocks_per_sm; S.n_sm = p->prop.multiProcessorCount;
   // penalties may have changed since upload (sequential search): refresh the descriptors' penalty
   {
     std::vector<DpProblem> hp(ng);
@@ -436,7 +442,7 @@ int psd_plan_solve_impl(psd_plan* p, void* stream_v) {
       K.cap = gcap; K.ccap = 3 * gcap; K.ws_bytes_per_warp = psd_ws_bytes(K.cap, K.ccap);
       smem = PSD_TAB_BYTES; wpb = std::min(8, PSD_MAX_WARPS_PER_BLOCK);
     }
-    grid = std::max(1, std::min(p->prop.multiProcessorCount, n));   // one block per SM; a small batch spreads one warp per SM
+    grid = std::max(1, std::min(p->prop.multiProcessorCount * (global_tier ? 1 : p->opt.blocks_per_sm), n));   // a small batch spreads one warp per SM
     if (global_tier) {
       const unsigned long long need = (unsigned long long)grid * wpb * K.ws_bytes_per_warp;
       if (need > p->gws_bytes) { dfree(p->d_gws); CK(cudaMalloc(&p->d_gws, need)); p->gws_bytes = need; }

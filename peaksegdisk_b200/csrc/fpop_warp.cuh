@@ -485,6 +485,9 @@ PSD_DEV PairOut pair_rule(const int cap, const PList f, const PList g, int i, in
   const double c1 = pc_cost(da, db, dc, xo);
   const double c2 = pc_cost_m(da, db, dc, m, xo);
   const bool two = two_roots(da, c1, c2, 0.0);
+  // Both crossings are always solved, as in the reference (:1024-1027).  Skipping the one a branch
+  // below does not read (exact, the solvers are pure) was measured 10 % SLOWER: it splits the lanes
+  // of a Newton round into two differently-predicated regions.
   double rs = PSD_INF, rl = PSD_INF;
   if (two) {
     rs = root_left(da, db, dc, lo, 0.0, xo, c1, dl);
@@ -909,7 +912,9 @@ PSD_DEV void dp_run_queue(const WarpWs ws, const DpQueue Q, const StorePool sp
         tmp.n = min_more_op(wg, upP, tmp, dmin, t - 1);
       }
     }
+#if !defined(PSD_BARRIERS) || (PSD_BARRIERS & 1)
     psd_block_sync();
+#endif
     // ---- phase B: both min_env's as one converged call; new functions become the previous ones ----------
     if (have && t >= 1) {
       const PList prev = grp ? downP : upP;     // previous cost function of my chain
@@ -923,7 +928,9 @@ PSD_DEV void dp_run_queue(const WarpWs ws, const DpQueue Q, const StorePool sp
       const PList u = upP, d = downP;
       upP = upN; downP = downN; upN = u; downN = d;
     }
+#if !defined(PSD_BARRIERS) || (PSD_BARRIERS & 2)
     psd_block_sync();
+#endif
     // ---- phase C: counters, store record, end of problem ------------------------------------------------
     if (have) {
       const int flags = *ws_flags(ws);

@@ -14,7 +14,7 @@ plan = psd.Plan(0)
 rows = 0
 for k in range(nv):
     s, e, c = synth.poisson_problem(k, n)
-    for pen in synth.C2_PENALTIES:
+    for pen in ([float(os.environ['PSD_PEN'])] * 5 if os.environ.get('PSD_PEN') else synth.C2_PENALTIES):
         plan.add(s, e, c, pen); rows += len(c)
 plan.upload()
 for _ in range(reps):
