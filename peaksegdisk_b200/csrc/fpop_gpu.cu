@@ -543,3 +543,13 @@ int psd_device_count_impl() {
   if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
   return n;
 }
+
+#if defined(PSD_TIMING)
+extern "C" int psd_debug_read(unsigned long long* out, int n, int reset) {
+  unsigned long long tmp[32];
+  if (cudaMemcpyFromSymbol(tmp, psd_dbg, sizeof tmp) != cudaSuccess) return -1;
+  for (int i = 0; i < n && i < 32; i++) out[i] = tmp[i];
+  if (reset) { memset(tmp, 0, sizeof tmp); cudaMemcpyToSymbol(psd_dbg, tmp, sizeof tmp); }
+  return 0;
+}
+#endif

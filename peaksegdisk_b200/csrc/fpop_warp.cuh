@@ -74,6 +74,20 @@ PSD_DEV void psd_st_cs_u64(unsigned long long* p, unsigned long long v) { __stcs
 PSD_DEV void psd_st_cs_u4(unsigned* p, unsigned a, unsigned b, unsigned c, unsigned d) { __stcs((uint4*)p, make_uint4(a, b, c, d)); }
 #endif
 
+#if defined(PSD_EXPERIMENT_SYNC) && !defined(PSD_EMU)
+#define PSD_XSYNC() __syncthreads()   /* experiment only: valid when every warp runs equal-length problems */
+#else
+#define PSD_XSYNC() do {} while (0)
+#endif
+// PSD_TIMING (experiment builds only): per-section cycle counters, accumulated by lane 0 / lane 16
+#if defined(PSD_TIMING) && !defined(PSD_EMU)
+__device__ unsigned long long psd_dbg[32];
+#define PSD_T0(v) const long long v = clock64()
+#define PSD_T1(v, slot) do { if ((threadIdx.x & 15u) == 0) atomicAdd(&psd_dbg[slot], (unsigned long long)(clock64() - v)); } while (0)
+#else
+#define PSD_T0(v) do {} while (0)
+#define PSD_T1(v, slot) do {} while (0)
+#endif
 #define PSD_G 16             /* lanes per operator group (half a warp) */
 #define PSD_EPS 1e-12        /* NEWTON_EPSILON, src/funPieceListLog.cpp:9 */
 #define PSD_MAX_STEPS 100    /* NEWTON_STEPS,   src/funPieceListLog.cpp:10 */
@@ -131,8 +145,13 @@ extern __shared__ __align__(16) unsigned char psd_smem[];
 #define PSD_ETAB ((const uint64_t*)psd_smem)
 #define PSD_LTAB (((const uint64_t*)psd_smem) + 256)
 #endif
+#if defined(PSD_INLINE_MATH)
+PSD_DEV double w_exp(double x) { return psd_exp(x, PSD_ETAB); }
+PSD_DEV double w_log(double x) { return psd_log(x, PSD_LTAB); }
+#else
 PSD_DEVNI double w_exp(double x) { return psd_exp(x, PSD_ETAB); }
 PSD_DEVNI double w_log(double x) { return psd_log(x, PSD_LTAB); }
+#endif
 
 // rescale applied while writing an operator's output:  ((v * mul) + add) * inv  per coefficient,
 // i.e. multiply(W_{t-1}); add(w, -z*w, 0); multiply(1/W_t)   (src/PeakSegFPOPLog.cpp:316-321)
@@ -442,6 +461,7 @@ struct PairOut { int nc; int s0; double x1, x2; };
 
 PSD_DEV PairOut pair_rule(const int cap, const PList f, const PList g, int i, int j, double dmin,
                           double* lo_out, double* hi_out) {
+  PSD_T0(q0);
   PairOut o; o.nc = 1; o.s0 = 0; o.x1 = 0; o.x2 = 0;
   const double pa = PL_A(f, i), pb = PL_B(f, i), pcst = PL_C(f, i);
   const double qa = PL_A(g, j), qb = PL_B(g, j), qcst = PL_C(g, j);
@@ -464,6 +484,8 @@ PSD_DEV PairOut pair_rule(const int cap, const PList f, const PList g, int i, in
                     : same_coefs(PL_A(f, i + 1), PL_B(f, i + 1), PL_C(f, i + 1), PL_A(g, j + 1), PL_B(g, j + 1), PL_C(g, j + 1));
   }
   *lo_out = lo; *hi_out = hi;
+  PSD_T1(q0, 16);
+  PSD_T0(q1);
   if (lo == hi) { o.nc = 0; return o; }
   if (same_coefs(pa, pb, pcst, qa, qb, qcst)) { o.s0 = 0; return o; }
   const double da = pa - qa, db = pb - qb, dc = pcst - qcst;
@@ -471,6 +493,8 @@ PSD_DEV PairOut pair_rule(const int cap, const PList f, const PList g, int i, in
   const double mid_m = (ehi + elo) / 2;
   const double dmid = pc_cost(da, db, dc, w_log(mid_m));
   const int by_mid = (dmid < 0) ? 0 : 1;
+  PSD_T1(q1, 17);
+  PSD_T0(q2);
   if (eq_left && eq_right) { o.s0 = by_mid; return o; }
   if (db == 0) {
     if (da == 0) { o.s0 = (dc < 0) ? 0 : 1; return o; }
@@ -485,14 +509,20 @@ PSD_DEV PairOut pair_rule(const int cap, const PList f, const PList g, int i, in
   const double c1 = pc_cost(da, db, dc, xo);
   const double c2 = pc_cost_m(da, db, dc, m, xo);
   const bool two = two_roots(da, c1, c2, 0.0);
+  PSD_T1(q2, 18);
   // Both crossings are always solved, as in the reference (:1024-1027).  Skipping the one a branch
   // below does not read (exact, the solvers are pure) was measured 10 % SLOWER: it splits the lanes
   // of a Newton round into two differently-predicated regions.
   double rs = PSD_INF, rl = PSD_INF;
   if (two) {
+    PSD_T0(tn);
     rs = root_left(da, db, dc, lo, 0.0, xo, c1, dl);
+    PSD_T1(tn, 12);
+    PSD_T0(tm);
     rl = root_right(da, db, dc, hi, 0.0, m, c2, dr);
+    PSD_T1(tm, 13);
   }
+  PSD_T0(q3);
   if (eq_right) {
     if (two) {
       if (lo < rs && rs < xo && xo < hi) { o.nc = 2; o.x1 = rs; o.s0 = (dl < 0) ? 0 : 1; return o; }
@@ -540,6 +570,7 @@ PSD_DEV PairOut pair_rule(const int cap, const PList f, const PList g, int i, in
     const double v = (pc_abs(dmid) < PSD_EPS) ? dr : dmid;
     o.s0 = (v < 0) ? 0 : 1;
   }
+  PSD_T1(q3, 19);
   return o;
 }
 
@@ -554,6 +585,7 @@ PSD_DEVNI int min_env_op(const WarpWs ws, const PList f, const PList g, const PL
   double* const cand_x = ws_cand_x(ws);
   int* const cand_s = ws_cand_s(ws);
   const int nf = f.n, ng = g.n;
+  PSD_T0(t1);
   // 1. enumerate overlap intervals, one g piece per lane: f pieces s..e overlap g[j]
   int K = 0;
   {
@@ -588,6 +620,9 @@ PSD_DEVNI int min_env_op(const WarpWs ws, const PList f, const PList g, const PL
     }
   }
   psd_g_sync();
+  PSD_T1(t1, 8);
+  PSD_T0(t2);
+  PSD_XSYNC();
   if (K > 2 * cap) { K = 2 * cap; }
   // 2. crossing rule per interval -> candidate pieces
   int T = 0;
@@ -597,6 +632,10 @@ PSD_DEVNI int min_env_op(const WarpWs ws, const PList f, const PList g, const PL
     PairOut o; o.nc = 0; o.s0 = 0; o.x1 = 0; o.x2 = 0;
     double lo = 0, hi = 0;
     int i = 0, j = 0;
+#if defined(PSD_TIMING) && !defined(PSD_EMU)
+    if ((threadIdx.x & 15u) == 0) atomicAdd(&psd_dbg[20], 1ull);
+    if (valid) atomicAdd(&psd_dbg[21], 1ull);
+#endif
     if (valid) {
       const int code = ivl[q];
       i = code & 0xffff; j = code >> 16;
@@ -617,6 +656,9 @@ PSD_DEVNI int min_env_op(const WarpWs ws, const PList f, const PList g, const PL
     T += psd_g_shfl_i(incl, PSD_G - 1);
   }
   psd_g_sync();
+  PSD_T1(t2, 9);
+  PSD_T0(t3);
+  PSD_XSYNC();
   if (T > ccap) T = ccap;
   // 3. push_piece: merge each candidate into the current run when it equals the run's head
   int out_n = 0;
@@ -688,6 +730,7 @@ PSD_DEVNI int min_env_op(const WarpWs ws, const PList f, const PList g, const PL
     out_n += n_heads;
   }
   psd_g_sync();
+  PSD_T1(t3, 10);
   return out_n;
 }
 
@@ -907,9 +950,13 @@ PSD_DEV void dp_run_queue(const WarpWs ws, const DpQueue Q, const StorePool sp
         downP.n = 1; upP.n = 0;
         psd_syncwarp();
       } else if (grp == 0) {
+        PSD_T0(ta);
         tmp.n = min_less_op(wg, downP, tmp, dmin, t - 1, penalty / cw_prev);
+        PSD_T1(ta, 0);
       } else if (t >= 2) {
+        PSD_T0(ta);
         tmp.n = min_more_op(wg, upP, tmp, dmin, t - 1);
+        PSD_T1(ta, 1);
       }
     }
 #if !defined(PSD_BARRIERS) || (PSD_BARRIERS & 1)
@@ -921,7 +968,7 @@ PSD_DEV void dp_run_queue(const WarpWs ws, const DpQueue Q, const StorePool sp
       const PList dst = grp ? downN : upN;
       int n_out;
       if (t == 1) n_out = copy_rescale_op(wg, grp ? downP : tmp, dst, rs);   // :297-299, :324-328
-      else n_out = min_env_op(wg, tmp, prev, dst, dmin, rs);
+      else { PSD_T0(tb); n_out = min_env_op(wg, tmp, prev, dst, dmin, rs); PSD_T1(tb, 2 + grp); }
       psd_syncwarp();   // both chains done; their lists are visible to the whole warp
       upN.n = psd_shfl_i(n_out, 0);
       downN.n = psd_shfl_i(n_out, 16);
@@ -932,6 +979,7 @@ PSD_DEV void dp_run_queue(const WarpWs ws, const DpQueue Q, const StorePool sp
     psd_block_sync();
 #endif
     // ---- phase C: counters, store record, end of problem ------------------------------------------------
+    PSD_T0(tc);
     if (have) {
       const int flags = *ws_flags(ws);
       if (flags) status = (flags & PSD_FLAG_OVERFLOW) ? PSD_ST_PIECE_OVERFLOW : PSD_ST_INTERNAL;
@@ -966,6 +1014,7 @@ PSD_DEV void dp_run_queue(const WarpWs ws, const DpQueue Q, const StorePool sp
         fetch = true;
       }
     }
+    PSD_T1(tc, 4);
     // a warp that is about to fetch may still get work: keep the block alive until every warp has
     // seen an empty queue
     if (!psd_block_or(have)) break;
