@@ -38,12 +38,14 @@ struct DpKernelParams {
   int* queue;                 // atomic cursor into order
   DpResult* results;
   StorePool pool;
-  int cap, ccap;
-  unsigned char* gws;         // global-tier workspace (null: piece lists live in shared memory)
-  unsigned long long ws_bytes_per_warp;
+  int cap_s, ccap_s;          // shared-memory tier (cap_s = 0: disabled, warps start in the global tier)
+  unsigned long long ws_s_bytes;   // per warp, >= PSD_WS_HDR (the header holds the warp's flag word)
+  unsigned char* gws;         // per-warp global-memory workspaces (null: none)
+  int cap_g, ccap_g;
+  unsigned long long ws_g_bytes;
 };
 
-static inline unsigned long long psd_ws_bytes(int cap, int ccap) { return PSD_WS_BYTES(cap, ccap); }
+static inline unsigned long long psd_ws_bytes(int cap, int ccap) { return cap > 0 ? PSD_WS_BYTES(cap, ccap) : PSD_WS_HDR; }
 
 __global__ void __launch_bounds__(PSD_MAX_WARPS_PER_BLOCK * 32)
 fpop_dp_kernel(const DpKernelParams P) {
@@ -52,14 +54,16 @@ fpop_dp_kernel(const DpKernelParams P) {
   for (int i = threadIdx.x; i < 256; i += blockDim.x) { etab[i] = d_exp_tab[i]; ltab[i] = d_log_tab[i]; }
   __syncthreads();
   const int warp = threadIdx.x >> 5;
-  WarpWs ws;
-  ws.base = P.gws ? P.gws + ((unsigned long long)blockIdx.x * (blockDim.x >> 5) + warp) * P.ws_bytes_per_warp
-                  : psd_smem + PSD_TAB_BYTES + (unsigned long long)warp * P.ws_bytes_per_warp;
-  ws.scratch = nullptr; ws.cap = P.cap; ws.ccap = P.ccap;
+  const int wpb = blockDim.x >> 5;
+  WarpWs ws_s, ws_g;
+  ws_s.base = psd_smem + PSD_TAB_BYTES + (unsigned long long)warp * P.ws_s_bytes;
+  ws_s.scratch = nullptr; ws_s.flags = (int*)ws_s.base; ws_s.cap = P.cap_s; ws_s.ccap = P.ccap_s;
+  ws_g.base = P.gws ? P.gws + ((unsigned long long)blockIdx.x * wpb + warp) * P.ws_g_bytes : nullptr;
+  ws_g.scratch = nullptr; ws_g.flags = ws_s.flags; ws_g.cap = P.gws ? P.cap_g : 0; ws_g.ccap = P.ccap_g;
   DpQueue Q;
   Q.problems = P.problems; Q.order = P.order; Q.n_order = P.n_order; Q.cursor = P.queue; Q.results = P.results;
   Q.first_slot = warp * (int)gridDim.x + (int)blockIdx.x;
-  dp_run_queue(ws, Q, P.pool);
+  dp_run_queue(ws_s, ws_g, Q, P.pool);
 }
 
 struct BtKernelParams {
@@ -104,7 +108,7 @@ fpop_backtrack_kernel(const BtKernelParams P) {
 namespace {
 thread_local std::string g_last_error;
 std::mutex g_opt_mutex;
-struct Options { int piece_cap = 48; int overflow_cap = 8192; double store_gb = 0; int chunk_kb = 64; int max_warps_per_sm = 0; int blocks_per_sm = 1; } g_opt;
+struct Options { int piece_cap = 48; int overflow_cap = 8192; double store_gb = 0; int chunk_kb = 64; int max_warps_per_sm = 0; int blocks_per_sm = 1; int spill_cap = 512; } g_opt;
 
 bool cuda_ok(cudaError_t e, const char* what) {
   if (e == cudaSuccess) return true;
@@ -128,6 +132,7 @@ int psd_set_option_impl(const char* name, double value) {
   else if (n == "chunk_kb") g_opt.chunk_kb = (int)value;
   else if (n == "max_warps_per_sm") g_opt.max_warps_per_sm = (int)value;
   else if (n == "blocks_per_sm") g_opt.blocks_per_sm = std::max(1, (int)value);
+  else if (n == "spill_cap") g_opt.spill_cap = std::max(0, (int)value);
   else return PSD_ERR_ARG;
   return 0;
 }
@@ -202,6 +207,7 @@ psd_plan* psd_plan_create_impl(int device) {
   if (const char* e = getenv("PSD_STORE_GB")) p->opt.store_gb = atof(e);
   if (const char* e = getenv("PSD_MAX_WARPS")) p->opt.max_warps_per_sm = atoi(e);
   if (const char* e = getenv("PSD_BLOCKS_PER_SM")) p->opt.blocks_per_sm = std::max(1, atoi(e));
+  if (const char* e = getenv("PSD_SPILL_CAP")) p->opt.spill_cap = std::max(0, atoi(e));
   memset(&p->stats, 0, sizeof p->stats);
   return p;
 }
@@ -423,8 +429,6 @@ int psd_plan_solve_impl(psd_plan* p, void* stream_v) {
             continue;
           }
           gcap *= 2;
-        } else {
-          S.n_overflow_tier += (int)overflow_acc.size();
         }
         global_tier = true;
         todo.swap(overflow_acc);
@@ -436,16 +440,23 @@ int psd_plan_solve_impl(psd_plan* p, void* stream_v) {
     K.pool.base = p->d_pool; K.pool.cursor = p->d_cursors; K.pool.n_chunks = p->pool_bytes / chunk; K.pool.chunk_bytes = chunk;
     int grid; size_t smem; int wpb;
     if (!global_tier) {
-      K.cap = p->cap; K.ccap = p->ccap; K.gws = nullptr; K.ws_bytes_per_warp = psd_ws_bytes(K.cap, K.ccap);
+      // shared-memory tier, with a per-warp global workspace the kernel moves to (and back from)
+      // when a row's functions outgrow shared memory
+      K.cap_s = p->cap; K.ccap_s = p->ccap; K.ws_s_bytes = psd_ws_bytes(K.cap_s, K.ccap_s);
+      K.cap_g = p->opt.spill_cap; K.ccap_g = 3 * K.cap_g; K.ws_g_bytes = psd_ws_bytes(K.cap_g, K.ccap_g);
       smem = p->smem_bytes; wpb = p->warps_per_block;
     } else {
-      K.cap = gcap; K.ccap = 3 * gcap; K.ws_bytes_per_warp = psd_ws_bytes(K.cap, K.ccap);
-      smem = PSD_TAB_BYTES; wpb = std::min(8, PSD_MAX_WARPS_PER_BLOCK);
+      // host-level re-run of problems that outgrew even that: global lists only
+      K.cap_s = 0; K.ccap_s = 0; K.ws_s_bytes = psd_ws_bytes(0, 0);
+      K.cap_g = gcap; K.ccap_g = 3 * gcap; K.ws_g_bytes = psd_ws_bytes(K.cap_g, K.ccap_g);
+      wpb = std::min(8, PSD_MAX_WARPS_PER_BLOCK);
+      smem = PSD_TAB_BYTES + (size_t)wpb * K.ws_s_bytes;
     }
     grid = std::max(1, std::min(p->prop.multiProcessorCount * (global_tier ? 1 : p->opt.blocks_per_sm), n));   // a small batch spreads one warp per SM
-    if (global_tier) {
-      const unsigned long long need = (unsigned long long)grid * wpb * K.ws_bytes_per_warp;
-      if (need > p->gws_bytes) { dfree(p->d_gws); CK(cudaMalloc(&p->d_gws, need)); p->gws_bytes = need; }
+    K.gws = nullptr;
+    if (K.cap_g > 0) {
+      const unsigned long long need = (unsigned long long)grid * wpb * K.ws_g_bytes;
+      if (need > p->gws_bytes) { dfree(p->d_gws); p->gws_bytes = 0; CK(cudaMalloc(&p->d_gws, need)); p->gws_bytes = need; }
       K.gws = p->d_gws;
     }
     CK(cudaMemcpyAsync(p->d_order, todo.data(), sizeof(int) * n, cudaMemcpyHostToDevice, st));
@@ -477,7 +488,7 @@ int psd_plan_solve_impl(psd_plan* p, void* stream_v) {
       const DpResult& r = p->p_results[g];
       if (r.status == PSD_ST_PIECE_OVERFLOW) overflow_acc.push_back(g);
       else if (r.status == PSD_ST_STORE_EXHAUSTED) exhausted.push_back(g);
-      else p->results[g] = r;
+      else { p->results[g] = r; if (r.pad_ > 0) S.n_overflow_tier++; }
     }
     if (!exhausted.empty() && (int)exhausted.size() == n) {   // the pool held none of them
       if (n == 1) { p->results[exhausted[0]] = p->p_results[exhausted[0]]; exhausted.clear(); }

@@ -119,7 +119,7 @@ struct PList { double* base; int n; };
 //   (2*cap ints: i_f | i_g << 16), candidate sources (ccap ints: bit 30 = from g | piece index).
 // The handle is passed BY VALUE (`scratch` already points at the calling group's scratch) so the operators can be real (non-inlined)
 // functions: the DP's code footprint has to stay close to the instruction cache (profiles/).
-struct WarpWs { unsigned char* base; unsigned char* scratch; int cap; int ccap; };
+struct WarpWs { unsigned char* base; unsigned char* scratch; int* flags; int cap; int ccap; };
 #define PSD_WS_HDR 16
 #define PSD_WS_LISTS 6
 #define PSD_FLAG_OVERFLOW 1
@@ -133,7 +133,7 @@ PSD_DEV unsigned char* ws_scratch0(const WarpWs w) { return w.base + PSD_WS_HDR 
 PSD_DEV double* ws_cand_x(const WarpWs w) { return (double*)w.scratch; }
 PSD_DEV int* ws_ivl(const WarpWs w) { return (int*)(ws_cand_x(w) + w.ccap); }
 PSD_DEV int* ws_cand_s(const WarpWs w) { return ws_ivl(w) + 2 * w.cap; }
-PSD_DEV volatile int* ws_flags(const WarpWs w) { return (volatile int*)w.base; }
+PSD_DEV volatile int* ws_flags(const WarpWs w) { return (volatile int*)w.flags; }
 PSD_DEV void ws_raise(const WarpWs w, int flag) { *ws_flags(w) = *ws_flags(w) | flag; }
 
 // exp/log tables: first 4 KB of the block's dynamic shared memory (host arrays under the emulator)
@@ -891,24 +891,44 @@ struct DpQueue {
   int first_slot;        // this warp's static slot
 };
 
-PSD_DEV void dp_run_queue(const WarpWs ws, const DpQueue Q, const StorePool sp
+// Copies list `src` (n pieces, capacity scap) into list `dst` (capacity dcap); all 32 lanes.
+PSD_DEV void pl_move(const double* src, int scap, double* dst, int dcap, int n) {
+  for (int k = psd_lane(); k < n; k += 32) {
+    for (int a = 0; a < 5; a++) dst[a * dcap + k] = src[a * scap + k];
+    ((int*)(dst + 5 * dcap))[k] = ((const int*)(src + 5 * scap))[k];
+  }
+}
+
+// ws_s: the warp's shared-memory workspace (cap 0 = disabled), ws_g: its global-memory workspace
+// (cap 0 = none).  A problem runs from shared memory; when a row's functions outgrow it the warp
+// moves the two previous functions to the global workspace and REPEATS THAT ROW there (the
+// operators never write their inputs), and moves back once both functions fit comfortably again.
+PSD_DEV void dp_run_queue(const WarpWs ws_s, const WarpWs ws_g, const DpQueue Q, const StorePool sp
 #if defined(PSD_EMU)
                           , psd_trace_fn trace, void* trace_user
 #endif
 ) {
   const int lane = psd_lane();
   const int grp = lane >> 4;          // 0: up chain (min_less), 1: down chain (min_more)
-  WarpWs wg = ws;                     // this group's view: its own scratch
-  wg.scratch = ws_scratch0(ws) + (unsigned long long)grp * PSD_WS_SCRATCH_BYTES(ws.cap, ws.ccap);
   // per-warp state (uniform across lanes)
-  int have = 0, id = 0, t = 0, N = 0, status = PSD_ST_OK, max_iv = 0, w_l = 0, z_l = 0;
+  int have = 0, id = 0, t = 0, N = 0, status = PSD_ST_OK, max_iv = 0, w_l = 0, z_l = 0, n_spill = 0;
   const int* weight = nullptr; const int* coverage = nullptr; unsigned long long* index = nullptr;
-  double penalty = 0, dmin = 0, dmax = 0, cw = 0, cw_prev = -1.0;
+  double penalty = 0, dmin = 0, dmax = 0, cw = 0, cw_done = 0.0;
   unsigned long long total_iv = 0, my_off = 0;
+  bool in_g = ws_s.cap == 0;          // current tier
+  WarpWs ws = in_g ? ws_g : ws_s;
+  WarpWs wg = ws;                     // this group's view: its own scratch
   PList upP, downP, upN, downN, tmp;
-  upP.base = ws_list(ws, 0); downP.base = ws_list(ws, 1); upN.base = ws_list(ws, 2); downN.base = ws_list(ws, 3);
-  tmp.base = ws_list(ws, 4 + grp);    // min-less result (group 0) / min-more result (group 1)
   upP.n = downP.n = upN.n = downN.n = tmp.n = 0;
+#define PSD_BIND_TIER()                                                                              \
+  do {                                                                                               \
+    ws = in_g ? ws_g : ws_s;                                                                         \
+    wg = ws;                                                                                         \
+    wg.scratch = ws_scratch0(ws) + (unsigned long long)grp * PSD_WS_SCRATCH_BYTES(ws.cap, ws.ccap);  \
+    upP.base = ws_list(ws, 0); downP.base = ws_list(ws, 1); upN.base = ws_list(ws, 2);               \
+    downN.base = ws_list(ws, 3); tmp.base = ws_list(ws, 4 + grp);                                    \
+  } while (0)
+  PSD_BIND_TIER();
   StoreWriter sw; sw.cur = 0; sw.end = 0;
   Rescale rs; rs.mul = rs.add_a = rs.add_b = rs.inv = 0;
   bool fetch = true;
@@ -929,7 +949,9 @@ PSD_DEV void dp_run_queue(const WarpWs ws, const DpQueue Q, const StorePool sp
         const DpProblem pb = Q.problems[id];
         weight = pb.weight; coverage = pb.coverage; index = pb.index; N = pb.n_rows;
         penalty = pb.penalty; dmin = pb.dmin; dmax = pb.dmax;
-        t = 0; status = PSD_ST_OK; max_iv = 0; total_iv = 0; cw = 0.0; cw_prev = -1.0;
+        t = 0; status = PSD_ST_OK; max_iv = 0; total_iv = 0; cw = 0.0; cw_done = 0.0; n_spill = 0;
+        in_g = ws_s.cap == 0;
+        PSD_BIND_TIER();
         upP.n = downP.n = upN.n = downN.n = tmp.n = 0;
         if (lane == 0) *ws_flags(ws) = 0;
         psd_syncwarp();
@@ -943,15 +965,15 @@ PSD_DEV void dp_run_queue(const WarpWs ws, const DpQueue Q, const StorePool sp
       }
       const int wi = psd_shfl_i(w_l, t & 31), z = psd_shfl_i(z_l, t & 31);
       const double w = (double)wi;
-      cw += w;
-      rs.mul = cw_prev; rs.add_a = w; rs.add_b = (double)(-z) * w; rs.inv = 1 / cw;
+      cw = cw_done + w;
+      rs.mul = cw_done; rs.add_a = w; rs.add_b = (double)(-z) * w; rs.inv = 1 / cw;
       if (t == 0) {
         if (lane == 0) pl_emit(ws, downP, 0, 1.0, (double)(-z), 0.0, dmax, -5.0, -1);
         downP.n = 1; upP.n = 0;
         psd_syncwarp();
       } else if (grp == 0) {
         PSD_T0(ta);
-        tmp.n = min_less_op(wg, downP, tmp, dmin, t - 1, penalty / cw_prev);
+        tmp.n = min_less_op(wg, downP, tmp, dmin, t - 1, penalty / cw_done);
         PSD_T1(ta, 0);
       } else if (t >= 2) {
         PSD_T0(ta);
@@ -962,56 +984,84 @@ PSD_DEV void dp_run_queue(const WarpWs ws, const DpQueue Q, const StorePool sp
 #if !defined(PSD_BARRIERS) || (PSD_BARRIERS & 1)
     psd_block_sync();
 #endif
-    // ---- phase B: both min_env's as one converged call; new functions become the previous ones ----------
+    // ---- phase B: both min_env's as one converged call --------------------------------------------------
+    int n_out = 0;
     if (have && t >= 1) {
       const PList prev = grp ? downP : upP;     // previous cost function of my chain
       const PList dst = grp ? downN : upN;
-      int n_out;
       if (t == 1) n_out = copy_rescale_op(wg, grp ? downP : tmp, dst, rs);   // :297-299, :324-328
       else { PSD_T0(tb); n_out = min_env_op(wg, tmp, prev, dst, dmin, rs); PSD_T1(tb, 2 + grp); }
       psd_syncwarp();   // both chains done; their lists are visible to the whole warp
-      upN.n = psd_shfl_i(n_out, 0);
-      downN.n = psd_shfl_i(n_out, 16);
-      const PList u = upP, d = downP;
-      upP = upN; downP = downN; upN = u; downN = d;
     }
 #if !defined(PSD_BARRIERS) || (PSD_BARRIERS & 2)
     psd_block_sync();
 #endif
-    // ---- phase C: counters, store record, end of problem ------------------------------------------------
+    // ---- phase C: tier switch or: counters, store record, end of problem --------------------------------
     PSD_T0(tc);
     if (have) {
       const int flags = *ws_flags(ws);
-      if (flags) status = (flags & PSD_FLAG_OVERFLOW) ? PSD_ST_PIECE_OVERFLOW : PSD_ST_INTERNAL;
-      if (status == PSD_ST_OK) {
-        cw_prev = cw;
-        total_iv += (unsigned long long)(upP.n + downP.n);
-        if (max_iv < upP.n) max_iv = upP.n;
-        if (max_iv < downP.n) max_iv = downP.n;
-#if defined(PSD_EMU)
-        if (trace && lane == 0) { trace(trace_user, t, 0, upP.n, ws.cap, upP.base); trace(trace_user, t, 1, downP.n, ws.cap, downP.base); }
-#endif
-        const unsigned long long off = store_alloc(sp, sw, store_record_bytes(upP.n, downP.n));
-        if (off == ~0ull) status = PSD_ST_STORE_EXHAUSTED;
-        else {
-          store_write(ws, sp.base + off, t, upP, downP);
-          if (lane == (t & 31)) my_off = off;
-          if ((t & 31) == 31 || t == N - 1) {
-            const int r = (t & ~31) + lane;
-            if (r <= t) psd_st_cs_u64(index + r, my_off);
-          }
+      bool redo = false;
+      if (flags) {
+        if ((flags & PSD_FLAG_OVERFLOW) && !(flags & PSD_FLAG_INTERNAL) && !in_g && ws_g.cap > 0) {
+          // this row does not fit the shared-memory tier: repeat it from the global workspace
+          psd_syncwarp();
+          pl_move(upP.base, ws_s.cap, ws_list(ws_g, 0), ws_g.cap, upP.n);
+          pl_move(downP.base, ws_s.cap, ws_list(ws_g, 1), ws_g.cap, downP.n);
+          if (lane == 0) *ws_flags(ws) = 0;
+          in_g = true; n_spill++;
+          PSD_BIND_TIER();
+          psd_syncwarp();
+          redo = true;
+        } else {
+          status = (flags & PSD_FLAG_INTERNAL) ? PSD_ST_INTERNAL : PSD_ST_PIECE_OVERFLOW;
         }
       }
-      t++;
-      if (status != PSD_ST_OK || t == N) {
-        double bc = 0, bx = 0, bpx = 0; int bbi = -1;
-        if (status == PSD_ST_OK) best_piece(ws, downP, dmin, &bc, &bx, &bbi, &bpx);
-        if (lane == 0) {
-          DpResult* res = &Q.results[id];
-          res->status = status; res->back_i = bbi; res->best_cost = bc; res->best_x = bx; res->back_x = bpx;
-          res->total_intervals = total_iv; res->max_intervals = max_iv; res->n_segments = 0; res->n_equality = 0;
+      if (!redo) {
+        if (status == PSD_ST_OK) {
+          if (t >= 1) {   // the new functions become the previous ones
+            upN.n = psd_shfl_i(n_out, 0);
+            downN.n = psd_shfl_i(n_out, 16);
+            const PList u = upP, d = downP;
+            upP = upN; downP = downN; upN = u; downN = d;
+          }
+          cw_done = cw;
+          total_iv += (unsigned long long)(upP.n + downP.n);
+          if (max_iv < upP.n) max_iv = upP.n;
+          if (max_iv < downP.n) max_iv = downP.n;
+#if defined(PSD_EMU)
+          if (trace && lane == 0) { trace(trace_user, t, 0, upP.n, ws.cap, upP.base); trace(trace_user, t, 1, downP.n, ws.cap, downP.base); }
+#endif
+          const unsigned long long off = store_alloc(sp, sw, store_record_bytes(upP.n, downP.n));
+          if (off == ~0ull) status = PSD_ST_STORE_EXHAUSTED;
+          else {
+            store_write(ws, sp.base + off, t, upP, downP);
+            if (lane == (t & 31)) my_off = off;
+            if ((t & 31) == 31 || t == N - 1) {
+              const int r = (t & ~31) + lane;
+              if (r <= t) psd_st_cs_u64(index + r, my_off);
+            }
+          }
         }
-        fetch = true;
+        t++;
+        if (status != PSD_ST_OK || t == N) {
+          double bc = 0, bx = 0, bpx = 0; int bbi = -1;
+          if (status == PSD_ST_OK) best_piece(ws, downP, dmin, &bc, &bx, &bbi, &bpx);
+          if (lane == 0) {
+            DpResult* res = &Q.results[id];
+            res->status = status; res->back_i = bbi; res->best_cost = bc; res->best_x = bx; res->back_x = bpx;
+            res->total_intervals = total_iv; res->max_intervals = max_iv; res->n_segments = 0; res->n_equality = 0;
+            res->pad_ = n_spill;
+          }
+          fetch = true;
+        } else if (in_g && ws_s.cap > 0 && 2 * upP.n <= ws_s.cap && 2 * downP.n <= ws_s.cap) {
+          // both functions fit comfortably again: move back to shared memory
+          psd_syncwarp();
+          pl_move(upP.base, ws_g.cap, ws_list(ws_s, 0), ws_s.cap, upP.n);
+          pl_move(downP.base, ws_g.cap, ws_list(ws_s, 1), ws_s.cap, downP.n);
+          in_g = false;
+          PSD_BIND_TIER();
+          psd_syncwarp();
+        }
       }
     }
     PSD_T1(tc, 4);
@@ -1019,6 +1069,7 @@ PSD_DEV void dp_run_queue(const WarpWs ws, const DpQueue Q, const StorePool sp
     // seen an empty queue
     if (!psd_block_or(have)) break;
   }
+#undef PSD_BIND_TIER
 }
 
 // ---- decode (src/PeakSegFPOPLog.cpp:400-442 + findMean :643-653) ------------------------------------

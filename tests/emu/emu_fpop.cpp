@@ -9,7 +9,7 @@
 
 namespace {
 struct Job {
-  DpProblem pb; WarpWs ws; StorePool sp; DpResult* res;
+  DpProblem pb; WarpWs ws; WarpWs ws_g; StorePool sp; DpResult* res;
   psd_trace_fn trace; void* trace_user;
   int* seg_row; double* seg_x;
   int order0 = 0; int cursor = 1;
@@ -18,7 +18,7 @@ void lane_main(void* arg) {
   Job* J = (Job*)arg;
   DpQueue Q;
   Q.problems = &J->pb; Q.order = &J->order0; Q.n_order = 1; Q.cursor = &J->cursor; Q.results = J->res; Q.first_slot = 0;
-  dp_run_queue(J->ws, Q, J->sp, J->trace, J->trace_user);
+  dp_run_queue(J->ws, J->ws_g, Q, J->sp, J->trace, J->trace_user);
   psd_syncwarp();
   backtrack_problem(J->sp.base, J->pb.index, J->pb.n_rows, J->res, J->seg_row, J->seg_x);
 }
@@ -29,9 +29,9 @@ extern "C" {
 // Same outputs as oracle_fpop_rows (non-trivial problems only).  cap = list capacity to emulate.
 // Returns the DpResult status (0 ok, 101 piece overflow, ...).
 int emu_fpop_rows(int n_rows, const int* chrom_start, const int* chrom_end, const int* coverage,
-                  double penalty, int cap, int descending, double* out_summary,
+                  double penalty, int cap, int spill_cap, int descending, double* out_summary,
                   int* seg_start, int* seg_end, int* seg_peak, double* seg_mean,
-                  psd_trace_fn trace, void* trace_user) {
+                  psd_trace_fn trace, void* trace_user, int* n_spills) {
   std::vector<int> w(n_rows);
   double W = 0, dmin = INFINITY, dmax = -INFINITY;
   for (int t = 0; t < n_rows; t++) {
@@ -44,15 +44,18 @@ int emu_fpop_rows(int n_rows, const int* chrom_start, const int* chrom_end, cons
   std::vector<unsigned long long> index(n_rows);
   J.pb.weight = w.data(); J.pb.coverage = coverage; J.pb.n_rows = n_rows; J.pb.penalty = penalty;
   J.pb.dmin = dmin; J.pb.dmax = dmax; J.pb.index = index.data();
+  // shared-memory-tier stand-in (capacity cap) and the global workspace the warp can move to
   const int ccap = 3 * cap;
-  const size_t ws_bytes = PSD_WS_BYTES(cap, ccap) + 64;
-  std::vector<double> wsmem(ws_bytes / 8 + 8);
-  J.ws.base = (unsigned char*)wsmem.data(); J.ws.scratch = nullptr; J.ws.cap = cap; J.ws.ccap = ccap;
+  std::vector<double> wsmem(PSD_WS_BYTES(cap, ccap) / 8 + 16);
+  J.ws.base = (unsigned char*)wsmem.data(); J.ws.scratch = nullptr; J.ws.flags = (int*)J.ws.base; J.ws.cap = cap; J.ws.ccap = ccap;
+  std::vector<double> wsmem_g(spill_cap > 0 ? PSD_WS_BYTES(spill_cap, 3 * spill_cap) / 8 + 16 : 1);
+  J.ws_g.base = spill_cap > 0 ? (unsigned char*)wsmem_g.data() : nullptr; J.ws_g.scratch = nullptr; J.ws_g.flags = J.ws.flags;
+  J.ws_g.cap = spill_cap; J.ws_g.ccap = 3 * spill_cap;
   const unsigned long long chunk = 1 << 16;
   std::vector<unsigned char> pool;
   unsigned long long cursor = 0;
   // generous pool: header + 20 bytes per piece, pieces <= cap per function
-  unsigned long long pool_bytes = (unsigned long long)n_rows * (32ull + 40ull * (unsigned)cap + 64ull) + chunk;
+  unsigned long long pool_bytes = (unsigned long long)n_rows * (32ull + 40ull * (unsigned)(cap > spill_cap ? cap : spill_cap) + 64ull) + chunk;
   if (pool_bytes > (6ull << 30)) pool_bytes = 6ull << 30;
   pool.resize((pool_bytes / chunk + 1) * chunk);
   J.sp.base = pool.data(); J.sp.cursor = &cursor; J.sp.n_chunks = pool.size() / chunk; J.sp.chunk_bytes = chunk;
@@ -66,6 +69,7 @@ int emu_fpop_rows(int n_rows, const int* chrom_start, const int* chrom_end, cons
   out_summary[0] = penalty; out_summary[1] = ns; out_summary[2] = np; out_summary[3] = W; out_summary[4] = n_rows;
   out_summary[5] = res.best_cost; out_summary[6] = res.best_cost * W - penalty * np; out_summary[7] = res.n_equality;
   out_summary[8] = (double)res.total_intervals / (n_rows * 2); out_summary[9] = res.max_intervals;
+  if (n_spills) *n_spills = res.pad_;
   int prev_end = chrom_end[n_rows - 1];
   for (int s = 0; s < ns; s++) {
     const int st = (s < ns - 1) ? chrom_end[seg_row[s]] : chrom_start[0];

@@ -33,7 +33,7 @@ def run_oracle(orc, s, e, c, pen, trace=False, math_mode=1):
     k = int(summ[1])
     return st, summ, (ss[:k].copy(), se[:k].copy(), sp[:k].copy(), sm[:k].copy()), rows
 
-def run_emu(emu, s, e, c, pen, cap=64, descending=0, trace=False):
+def run_emu(emu, s, e, c, pen, cap=64, descending=0, trace=False, spill_cap=0, info=None):
     n = len(c)
     rows = {}
     def tr(user, row, which, npc, cap_, base):
@@ -44,8 +44,11 @@ def run_emu(emu, s, e, c, pen, cap=64, descending=0, trace=False):
         rows[(row, which)] = (a, b, cc, hi, bi, bx)
     cb = EMU_TRACE(tr)
     summ = np.zeros(10); ss = np.zeros(n + 1, np.int32); se = np.zeros(n + 1, np.int32); sp = np.zeros(n + 1, np.int32); sm = np.zeros(n + 1)
-    st = emu.emu_fpop_rows(n, ip(s), ip(e), ip(c), C.c_double(pen), cap, descending, dp(summ), ip(ss), ip(se), ip(sp), dp(sm),
-                           cb if trace else C.cast(None, EMU_TRACE), None)
+    nsp = C.c_int(0)
+    st = emu.emu_fpop_rows(n, ip(s), ip(e), ip(c), C.c_double(pen), cap, spill_cap, descending, dp(summ), ip(ss), ip(se), ip(sp), dp(sm),
+                           cb if trace else C.cast(None, EMU_TRACE), None, C.byref(nsp))
+    if info is not None:
+        info['spills'] = nsp.value
     k = int(summ[1])
     return st, summ, (ss[:k].copy(), se[:k].copy(), sp[:k].copy(), sm[:k].copy()), rows
 
@@ -68,10 +71,10 @@ def first_row_diff(ro, re_, n):
                     return "row %d %s field %s differs\n oracle=%s\n emu   =%s" % (t, "up" if which == 0 else "down", nm, x, y)
     return None
 
-def compare(s, e, c, pen, cap=64, descending=0, trace=True, verbose=True):
+def compare(s, e, c, pen, cap=64, descending=0, trace=True, verbose=True, spill_cap=0, info=None):
     orc, emu = load()
     so, summ_o, seg_o, rows_o = run_oracle(orc, s, e, c, pen, trace)
-    se_, summ_e, seg_e, rows_e = run_emu(emu, s, e, c, pen, cap, descending, trace)
+    se_, summ_e, seg_e, rows_e = run_emu(emu, s, e, c, pen, cap, descending, trace, spill_cap, info)
     ok = so == se_ == 0 and np.array_equal(bits(summ_o), bits(summ_e)) and all(
         np.array_equal(x, y) if x.dtype != np.float64 else np.array_equal(bits(x), bits(y)) for x, y in zip(seg_o, seg_e))
     msg = None

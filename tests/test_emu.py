@@ -57,3 +57,23 @@ def test_piece_overflow_is_reported(ec):
     orc, emu = ec.load()
     st, _, _, _ = ec.run_emu(emu, s, e, c, 1e4, cap=16)
     assert st == 101
+
+
+@pytest.mark.parametrize("cap,pen", [(4, 50.0), (6, 1e3), (8, 1e4), (4, 0.0)])
+def test_tier_switch_is_transparent(ec, cap, pen):
+    """A tiny shared-memory tier forces the warp to move its functions to the global workspace,
+    repeat the row there and move back later; every row must still match the oracle."""
+    from peaksegdisk_b200 import synth
+    s, e, c = synth.poisson_problem(31, 1200)
+    info = {}
+    assert ec.compare(s, e, c, pen, cap=cap, spill_cap=256, info=info)
+    assert info["spills"] >= 1
+    assert ec.compare(s, e, c, pen, cap=cap, spill_cap=256, descending=1, trace=False)
+
+
+def test_spill_tier_overflow_is_reported(ec):
+    from peaksegdisk_b200 import synth
+    s, e, c = synth.increasing_problem(300)
+    orc, emu = ec.load()
+    st, _, _, _ = ec.run_emu(emu, s, e, c, 1e4, cap=16, spill_cap=64)
+    assert st == 101
