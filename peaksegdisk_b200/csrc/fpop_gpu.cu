@@ -23,7 +23,7 @@
 #include "plan_internal.h"
 
 #ifndef PSD_MAX_WARPS_PER_BLOCK
-#define PSD_MAX_WARPS_PER_BLOCK 20   /* one phase-locked block per SM; built with -maxrregcount=96 (Makefile) */
+#define PSD_MAX_WARPS_PER_BLOCK 16   /* __launch_bounds__(512): 128 registers per thread (fewer registers only add spills; 14-16 warps fit shared memory) */
 #endif
 #define PSD_BT_WARPS_PER_BLOCK 4
 #define PSD_TAB_BYTES 4096

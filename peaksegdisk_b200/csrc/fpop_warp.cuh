@@ -10,8 +10,8 @@
 //
 // Reference behaviour being reproduced (file:line into tdhock/PeakSegDisk):
 //   piece algebra, Newton roots     src/funPieceListLog.cpp:29-234
-//   set_to_min_less_of              src/funPieceListLog.cpp:236-437   -> min_less_op
-//   set_to_min_more_of              src/funPieceListLog.cpp:439-616   -> min_more_op
+//   set_to_min_less_of              src/funPieceListLog.cpp:236-437   -> min_mono_op (dir 0)
+//   set_to_min_more_of              src/funPieceListLog.cpp:439-616   -> min_mono_op (dir 1)
 //   set_to_min_env_of / push_min_pieces / push_piece
 //                                   src/funPieceListLog.cpp:832-1285  -> min_env_op (+ pair_rule)
 //   add / multiply / set_prev_seg_end  :618-641  -> fused into the operators' output writes
@@ -247,18 +247,32 @@ PSD_DEV void pl_emit(const WarpWs ws, const PList out, int k, double a, double b
   }
 }
 
-// ---- set_to_min_less_of, then set_prev_seg_end(stamp) and add(0,0,cshift) --------------------------
-PSD_DEVNI int min_less_op(const WarpWs ws, const PList in, const PList out, double dmin, int stamp, double cshift) {
+// ---- set_to_min_less_of (dir 0) / set_to_min_more_of (dir 1), one routine --------------------------
+// Both are the same scan, mirrored: min_less walks the pieces left to right and keeps the running
+// minimum from the left; min_more walks right to left.  In SCAN ORDER (u = 0 is the first piece
+// visited) a piece has an entry edge and an exit edge (less: lo/hi, more: hi/lo), the neighbour
+// test looks at the next piece's cost at ITS entry edge, a flat stretch opens at the entry edge or
+// at the interior argmin and is closed by a root or at an exit edge.  The two half-warps of a warp
+// call this routine TOGETHER (dir is group-uniform data), so everything except the root solvers is
+// one converged instruction stream.  The reference's asymmetries are kept by selects on dir:
+//   * degenerate pieces (b == 0): less may open a flat stretch at one and never closes one on it
+//     (:256-308, :376-384); more always copies it and intersects it in closed form (:458-467, :561-564)
+//   * less opens at the entry edge only if the cost also rises towards the exit and the next piece
+//     (:327-336); more only needs the cost to fall across the piece (:484-510)
+//   * less stamps back_i, adds the penalty to c and +0.0 to a and b (add(0,0,c), :618-625); more only stamps
+// Output pieces are produced in scan order and, for dir 1, reversed at the end.
+PSD_DEVNI int min_mono_op(const WarpWs ws, const PList in, const PList out, double dmin, int stamp, double cshift, int dir) {
   const int lane = psd_glane();   // lane within this 16-lane group
   const int cap = ws.cap;
   const int n = in.n;
-  double level = PSD_INF;    // cost of the pending flat piece; +inf while following the input
-  double left_edge = dmin;   // where the next output piece starts
-  double arg_at = PSD_INF;   // where the flat piece's minimum is attained
+  double level = PSD_INF;                             // cost of the pending flat piece; +inf while following the input
+  double edge = dir ? PL_X(in, n - 1) : dmin;         // where the next output piece starts (scan order)
+  double arg_at = PSD_INF;                            // where the flat piece's minimum is attained
   int out_n = 0;
   for (int base = 0; base < n; base += PSD_G) {
-    const int i = base + lane;
-    const bool valid = i < n;
+    const int u = base + lane;                        // scan position
+    const bool valid = u < n;
+    const int i = dir ? n - 1 - u : u;                // piece index
     const int end = (n - base < PSD_G) ? n : base + PSD_G;
     double a = 0, b = 0, c = 0, hi = 0, lo = 0;
     double cl = 0, cr = 0, m = 0, mu = 0, cmu = 0, c2 = 0;
@@ -274,173 +288,98 @@ PSD_DEVNI int min_less_op(const WarpWs ws, const PList in, const PList out, doub
         c2 = pc_cost_m(a, b, c, m, mu);
       }
     }
-    // cost of the next piece at its left end
-    double nl = psd_g_shfl_down_d(cl, 1);
-    const bool has_next = i + 1 < n;
-    if (lane == PSD_G - 1 && has_next) nl = pc_cost(PL_A(in, i + 1), PL_B(in, i + 1), PL_C(in, i + 1), hi);
+    const double ein = dir ? hi : lo, eout = dir ? lo : hi;      // entry / exit edge
+    const double cin = dir ? cr : cl, cout = dir ? cl : cr;      // cost there
+    // cost of the next piece (scan order) at its entry edge, which is my exit edge
+    double nxt = psd_g_shfl_down_d(cin, 1);
+    const bool has_nxt = u + 1 < n;
+    if (lane == PSD_G - 1 && has_nxt) {
+      const int j = dir ? i - 1 : i + 1;
+      nxt = pc_cost(PL_A(in, j), PL_B(in, j), PL_C(in, j), eout);
+    }
     // what this piece does when reached while following the input:
-    // 0 = copied whole, 1 = a flat stretch starts at its left end, 2 = its minimum is interior
+    // 0 = copied whole, 1 = a flat stretch starts at its entry edge, 2 = its minimum is interior
     int kind = 0;
     if (valid) {
       if (b == 0) {
-        const bool flat = (cr - cl) < PSD_EPS;
-        const bool next_above = !has_next || PSD_EPS < nl - cl;
-        kind = (next_above && !flat) ? 1 : 0;
+        if (!dir) {
+          const bool flat = (cout - cin) < PSD_EPS;
+          const bool next_above = !has_nxt || PSD_EPS < nxt - cin;
+          kind = (next_above && !flat) ? 1 : 0;
+        }
       } else {
-        const bool next_ok = !has_next || PSD_EPS < nl - cmu;
-        const bool ok = PSD_EPS < cr - cmu && next_ok;
-        kind = (mu <= lo && ok) ? 1 : ((mu < hi && ok) ? 2 : 0);
+        const bool next_ok = !has_nxt || PSD_EPS < nxt - cmu;
+        if (!dir) {
+          const bool ok = PSD_EPS < cout - cmu && next_ok;
+          kind = (mu <= ein && ok) ? 1 : ((mu < eout && ok) ? 2 : 0);
+        } else {
+          if (ein <= mu) kind = (PSD_EPS < cout - cin) ? 1 : 0;
+          else if (eout < mu && PSD_EPS < cout - cmu && next_ok) kind = 2;
+        }
       }
     }
+    // coefficients of a copied piece
+    const double ea = dir ? a : a + 0.0, eb = dir ? b : b + 0.0, ec = dir ? c : c + cshift;
     int pos = base;
     while (pos < end) {
       if (level == PSD_INF) {
-        const unsigned mask = psd_g_ballot(valid && i >= pos && kind != 0);
+        const unsigned mask = psd_g_ballot(valid && u >= pos && kind != 0);
         const int first = mask ? base + psd_ffs(mask) - 1 : end;
-        if (valid && i >= pos && i < first) pl_emit(ws, out, out_n + (i - pos), a + 0.0, b + 0.0, c + cshift, hi, PSD_INF, stamp);
+        if (valid && u >= pos && u < first) pl_emit(ws, out, out_n + (u - pos), ea, eb, ec, (dir && u == pos) ? edge : hi, PSD_INF, stamp);
         const int src = (first < end) ? first - base : 0;
         const int kf = psd_g_shfl_i(kind, src);
-        const double lo_f = psd_g_shfl_d(lo, src), cl_f = psd_g_shfl_d(cl, src);
+        const double ein_f = psd_g_shfl_d(ein, src), cin_f = psd_g_shfl_d(cin, src);
         const double mu_f = psd_g_shfl_d(mu, src), cmu_f = psd_g_shfl_d(cmu, src);
-        const double hi_last = psd_g_shfl_d(hi, end - 1 - base);
-        if (first > pos) left_edge = (first < end) ? lo_f : hi_last;
+        const double eout_last = psd_g_shfl_d(eout, end - 1 - base);
+        if (first > pos) edge = (first < end) ? ein_f : eout_last;
         out_n += first - pos;
         if (first >= end) { pos = end; break; }
-        if (kf == 1) { level = cl_f; arg_at = lo_f; }
+        if (kf == 1) { level = cin_f; arg_at = ein_f; }
         else {
-          if (left_edge < mu_f) {
-            if (lane == src) pl_emit(ws, out, out_n, a + 0.0, b + 0.0, c + cshift, mu_f, PSD_INF, stamp);
+          if (dir ? (mu_f < edge) : (edge < mu_f)) {
+            if (lane == src) pl_emit(ws, out, out_n, ea, eb, ec, dir ? edge : mu_f, PSD_INF, stamp);
             out_n++;
           }
-          left_edge = mu_f; arg_at = mu_f; level = cmu_f;
+          edge = mu_f; arg_at = mu_f; level = cmu_f;
         }
         pos = first + 1;
       } else {
         int flag = 0;
-        double r = 0;
-        if (valid && i >= pos) {
-          if (b == 0) { if (a < 0) flag = 3; }   // the reference throws here ("should never happen")
-          else {
-            if (two_roots(a, cmu, c2, level)) {
-              r = root_left(a, b, c, lo, level, mu, cmu, cl);
-              if (lo < r && r < hi) flag = 1;
-            }
-            if (!flag && cr <= level + PSD_EPS) flag = 2;
+        double r = PSD_INF;   // no root: fails the interval test below
+        if (valid && u >= pos) {
+          if (b == 0) {
+            if (dir) r = w_log((level - c) / a);
+            else if (a < 0) flag = 3;   // the reference throws here ("should never happen")
+          } else if (two_roots(a, cmu, c2, level)) {
+            r = dir ? root_right(a, b, c, hi, level, m, c2, cr) : root_left(a, b, c, lo, level, mu, cmu, cl);
+          }
+          if (flag == 0 && (dir || b != 0)) {
+            if (lo < r && r < hi) flag = 1;
+            else if (cout <= level + PSD_EPS) flag = 2;
           }
         }
         const unsigned mask = psd_g_ballot(flag != 0);
         if (!mask) { pos = end; break; }
         const int src = psd_ffs(mask) - 1;
         const int fl = psd_g_shfl_i(flag, src);
-        const double r_s = psd_g_shfl_d(r, src), hi_s = psd_g_shfl_d(hi, src);
+        const double r_s = psd_g_shfl_d(r, src), eout_s = psd_g_shfl_d(eout, src);
         if (fl == 3) { ws_raise(ws, PSD_FLAG_INTERNAL); pos = end; level = PSD_INF; break; }
-        const double xe = (fl == 1) ? r_s : hi_s;
-        if (lane == 0) pl_emit(ws, out, out_n, 0.0 + 0.0, 0.0 + 0.0, level + cshift, xe, arg_at, stamp);
+        const double xe = (fl == 1) ? r_s : eout_s;
+        if (lane == 0) pl_emit(ws, out, out_n, dir ? 0.0 : 0.0 + 0.0, dir ? 0.0 : 0.0 + 0.0, dir ? level : level + cshift, dir ? edge : xe, arg_at, stamp);
         out_n++;
-        level = PSD_INF; left_edge = xe;
+        level = PSD_INF; edge = xe;
         pos = base + src + (fl == 1 ? 0 : 1);
       }
     }
   }
   if (level < PSD_INF) {
-    if (lane == 0) pl_emit(ws, out, out_n, 0.0 + 0.0, 0.0 + 0.0, level + cshift, PL_X(in, n - 1), arg_at, stamp);
+    if (lane == 0) pl_emit(ws, out, out_n, dir ? 0.0 : 0.0 + 0.0, dir ? 0.0 : 0.0 + 0.0, dir ? level : level + cshift, dir ? edge : PL_X(in, n - 1), arg_at, stamp);
     out_n++;
   }
   psd_g_sync();
-  return out_n;
-}
-
-// ---- set_to_min_more_of, then set_prev_seg_end(stamp) ---------------------------------------------
-PSD_DEVNI int min_more_op(const WarpWs ws, const PList in, const PList out, double dmin, int stamp) {
-  const int lane = psd_glane();   // lane within this 16-lane group
-  const int cap = ws.cap;
-  const int n = in.n;
-  double level = PSD_INF;
-  double right_edge = PL_X(in, n - 1);
-  double arg_at = PSD_INF;
-  int out_n = 0;   // pieces are emitted right to left, reversed at the end
-  for (int base = ((n - 1) / PSD_G) * PSD_G; base >= 0; base -= PSD_G) {
-    const int i = base + lane;
-    const bool valid = i < n;
-    double a = 0, b = 0, c = 0, hi = 0, lo = 0;
-    double cl = 0, cr = 0, m = 0, mu = 0, cmu = 0, c2 = 0;
-    if (valid) {
-      a = PL_A(in, i); b = PL_B(in, i); c = PL_C(in, i); hi = PL_X(in, i);
-      lo = (i == 0) ? dmin : PL_X(in, i - 1);
-      cl = pc_cost(a, b, c, lo);
-      cr = pc_cost(a, b, c, hi);
-      if (b != 0) {
-        m = -b / a;
-        mu = w_log(m);
-        cmu = pc_cost(a, b, c, mu);
-        c2 = pc_cost_m(a, b, c, m, mu);
-      }
-    }
-    // cost of the previous piece at its right end
-    double pr = psd_g_shfl_up_d(cr, 1);
-    const bool has_prev = i > 0;
-    if (lane == 0 && has_prev && valid) pr = pc_cost(PL_A(in, i - 1), PL_B(in, i - 1), PL_C(in, i - 1), lo);
-    int kind = 0;  // 0 = copied whole, 1 = flat stretch starts at its right end, 2 = interior minimum
-    if (valid && b != 0) {
-      const bool prev_ok = !has_prev || PSD_EPS < pr - cmu;
-      if (hi <= mu) kind = (PSD_EPS < cl - cr) ? 1 : 0;
-      else if (lo < mu && PSD_EPS < cl - cmu && prev_ok) kind = 2;
-    }
-    int pos = (n - 1 - base < PSD_G - 1) ? n - 1 : base + PSD_G - 1;   // highest unprocessed piece
-    while (pos >= base) {
-      if (level == PSD_INF) {
-        const unsigned mask = psd_g_ballot(valid && i <= pos && kind != 0);
-        const int first = mask ? base + 31 - psd_clz(mask) : base - 1;
-        if (valid && i <= pos && i > first) pl_emit(ws, out, out_n + (pos - i), a, b, c, (i == pos) ? right_edge : hi, PSD_INF, stamp);
-        const int src = (first >= base) ? first - base : 0;
-        const int kf = psd_g_shfl_i(kind, src);
-        const double hi_f = psd_g_shfl_d(hi, src), cr_f = psd_g_shfl_d(cr, src);
-        const double mu_f = psd_g_shfl_d(mu, src), cmu_f = psd_g_shfl_d(cmu, src);
-        const double lo_b = psd_g_shfl_d(lo, 0);
-        if (first < pos) right_edge = (first >= base) ? hi_f : lo_b;
-        out_n += pos - first;
-        if (first < base) { pos = base - 1; break; }
-        if (kf == 1) { level = cr_f; arg_at = hi_f; }
-        else {
-          if (mu_f < right_edge) {
-            if (lane == src) pl_emit(ws, out, out_n, a, b, c, right_edge, PSD_INF, stamp);
-            out_n++;
-          }
-          right_edge = mu_f; arg_at = mu_f; level = cmu_f;
-        }
-        pos = first - 1;
-      } else {
-        int flag = 0;
-        double r = PSD_INF;
-        if (valid && i <= pos) {
-          if (b == 0) r = w_log((level - c) / a);
-          else if (two_roots(a, cmu, c2, level)) r = root_right(a, b, c, hi, level, m, c2, cr);
-          if (lo < r && r < hi) flag = 1;
-          else if (cl <= level + PSD_EPS) flag = 2;
-        }
-        const unsigned mask = psd_g_ballot(flag != 0);
-        if (!mask) { pos = base - 1; break; }
-        const int src = 31 - psd_clz(mask);
-        const int fl = psd_g_shfl_i(flag, src);
-        const double r_s = psd_g_shfl_d(r, src), lo_s = psd_g_shfl_d(lo, src);
-        if (lane == 0) pl_emit(ws, out, out_n, 0.0, 0.0, level, right_edge, arg_at, stamp);
-        out_n++;
-        level = PSD_INF;
-        if (fl == 1) { right_edge = r_s; pos = base + src; }
-        else { right_edge = lo_s; pos = base + src - 1; }
-      }
-    }
-  }
-  if (level < PSD_INF) {
-    if (lane == 0) pl_emit(ws, out, out_n, 0.0, 0.0, level, right_edge, arg_at, stamp);
-    out_n++;
-  }
-  psd_g_sync();
-  // reverse into left-to-right order
-  const int live = out_n < cap ? out_n : cap;
-  if (out_n <= cap) {
-    for (int k = lane; k < (live >> 1); k += PSD_G) {
-      const int j = live - 1 - k;
+  if (dir && out_n <= cap) {   // pieces were produced right to left
+    for (int k = lane; k < (out_n >> 1); k += PSD_G) {
+      const int j = out_n - 1 - k;
       double t;
       t = PL_A(out, k); PL_A(out, k) = PL_A(out, j); PL_A(out, j) = t;
       t = PL_B(out, k); PL_B(out, k) = PL_B(out, j); PL_B(out, j) = t;
@@ -971,14 +910,11 @@ PSD_DEV void dp_run_queue(const WarpWs ws_s, const WarpWs ws_g, const DpQueue Q,
         if (lane == 0) pl_emit(ws, downP, 0, 1.0, (double)(-z), 0.0, dmax, -5.0, -1);
         downP.n = 1; upP.n = 0;
         psd_syncwarp();
-      } else if (grp == 0) {
+      } else if (grp == 0 || t >= 2) {
+        // min_less(down_{t-1}) on group 0 and min_more(up_{t-1}) on group 1: one converged call
         PSD_T0(ta);
-        tmp.n = min_less_op(wg, downP, tmp, dmin, t - 1, penalty / cw_done);
-        PSD_T1(ta, 0);
-      } else if (t >= 2) {
-        PSD_T0(ta);
-        tmp.n = min_more_op(wg, upP, tmp, dmin, t - 1);
-        PSD_T1(ta, 1);
+        tmp.n = min_mono_op(wg, grp ? upP : downP, tmp, dmin, t - 1, penalty / cw_done, grp);
+        PSD_T1(ta, grp);
       }
     }
 #if !defined(PSD_BARRIERS) || (PSD_BARRIERS & 1)
