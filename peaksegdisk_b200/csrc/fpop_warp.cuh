@@ -74,11 +74,6 @@ PSD_DEV void psd_st_cs_u64(unsigned long long* p, unsigned long long v) { __stcs
 PSD_DEV void psd_st_cs_u4(unsigned* p, unsigned a, unsigned b, unsigned c, unsigned d) { __stcs((uint4*)p, make_uint4(a, b, c, d)); }
 #endif
 
-#if defined(PSD_EXPERIMENT_SYNC) && !defined(PSD_EMU)
-#define PSD_XSYNC() __syncthreads()   /* experiment only: valid when every warp runs equal-length problems */
-#else
-#define PSD_XSYNC() do {} while (0)
-#endif
 // PSD_TIMING (experiment builds only): per-section cycle counters, accumulated by lane 0 / lane 16
 #if defined(PSD_TIMING) && !defined(PSD_EMU)
 __device__ unsigned long long psd_dbg[32];
@@ -87,6 +82,10 @@ __device__ unsigned long long psd_dbg[32];
 #else
 #define PSD_T0(v) do {} while (0)
 #define PSD_T1(v, slot) do {} while (0)
+#endif
+// While a flat stretch is open the pieces ahead are tested speculatively, PSD_SPEC lanes per round
+#ifndef PSD_SPEC
+#define PSD_SPEC 16
 #endif
 #define PSD_G 16             /* lanes per operator group (half a warp) */
 #define PSD_EPS 1e-12        /* NEWTON_EPSILON, src/funPieceListLog.cpp:9 */
@@ -346,7 +345,7 @@ PSD_DEVNI int min_mono_op(const WarpWs ws, const PList in, const PList out, doub
       } else {
         int flag = 0;
         double r = PSD_INF;   // no root: fails the interval test below
-        if (valid && u >= pos) {
+        if (valid && u >= pos && u < pos + PSD_SPEC) {
           if (b == 0) {
             if (dir) r = w_log((level - c) / a);
             else if (a < 0) flag = 3;   // the reference throws here ("should never happen")
@@ -359,7 +358,7 @@ PSD_DEVNI int min_mono_op(const WarpWs ws, const PList in, const PList out, doub
           }
         }
         const unsigned mask = psd_g_ballot(flag != 0);
-        if (!mask) { pos = end; break; }
+        if (!mask) { pos = (pos + PSD_SPEC < end) ? pos + PSD_SPEC : end; continue; }   // still flat: next window
         const int src = psd_ffs(mask) - 1;
         const int fl = psd_g_shfl_i(flag, src);
         const double r_s = psd_g_shfl_d(r, src), eout_s = psd_g_shfl_d(eout, src);
@@ -561,7 +560,6 @@ PSD_DEVNI int min_env_op(const WarpWs ws, const PList f, const PList g, const PL
   psd_g_sync();
   PSD_T1(t1, 8);
   PSD_T0(t2);
-  PSD_XSYNC();
   if (K > 2 * cap) { K = 2 * cap; }
   // 2. crossing rule per interval -> candidate pieces
   int T = 0;
@@ -597,7 +595,6 @@ PSD_DEVNI int min_env_op(const WarpWs ws, const PList f, const PList g, const PL
   psd_g_sync();
   PSD_T1(t2, 9);
   PSD_T0(t3);
-  PSD_XSYNC();
   if (T > ccap) T = ccap;
   // 3. push_piece: merge each candidate into the current run when it equals the run's head
   int out_n = 0;
@@ -917,9 +914,9 @@ PSD_DEV void dp_run_queue(const WarpWs ws_s, const WarpWs ws_g, const DpQueue Q,
         PSD_T1(ta, grp);
       }
     }
-#if !defined(PSD_BARRIERS) || (PSD_BARRIERS & 1)
-    psd_block_sync();
-#endif
+    // block barrier 1 of 2; it doubles as the block's termination vote (a warp that just saw an empty
+    // queue has have == 0; the block leaves when every warp has)
+    if (!psd_block_or(have)) break;
     // ---- phase B: both min_env's as one converged call --------------------------------------------------
     int n_out = 0;
     if (have && t >= 1) {
@@ -929,9 +926,7 @@ PSD_DEV void dp_run_queue(const WarpWs ws_s, const WarpWs ws_g, const DpQueue Q,
       else { PSD_T0(tb); n_out = min_env_op(wg, tmp, prev, dst, dmin, rs); PSD_T1(tb, 2 + grp); }
       psd_syncwarp();   // both chains done; their lists are visible to the whole warp
     }
-#if !defined(PSD_BARRIERS) || (PSD_BARRIERS & 2)
-    psd_block_sync();
-#endif
+    psd_block_sync();   // block barrier 2 of 2
     // ---- phase C: tier switch or: counters, store record, end of problem --------------------------------
     PSD_T0(tc);
     if (have) {
@@ -1001,9 +996,7 @@ PSD_DEV void dp_run_queue(const WarpWs ws_s, const WarpWs ws_g, const DpQueue Q,
       }
     }
     PSD_T1(tc, 4);
-    // a warp that is about to fetch may still get work: keep the block alive until every warp has
-    // seen an empty queue
-    if (!psd_block_or(have)) break;
+
   }
 #undef PSD_BIND_TIER
 }
