@@ -491,6 +491,18 @@ int psd_plan_solve_impl(psd_plan* p, void* stream_v) {
       else { p->results[g] = r; if (r.pad_ > 0) S.n_overflow_tier++; }
     }
     if (!exhausted.empty() && (int)exhausted.size() == n) {   // the pool held none of them
+      // first try a bigger pool (the automatic size is an estimate of ~1 KB per row)
+      size_t free_b = 0, total_b = 0;
+      CK(cudaMemGetInfo(&free_b, &total_b));
+      const unsigned long long lim = (((unsigned long long)((double)(free_b + p->pool_bytes) * 0.80)) / chunk) * chunk;
+      if (p->opt.store_gb <= 0 && p->pool_bytes * 2 <= lim) {
+        const unsigned long long want = std::min(lim, p->pool_bytes * 4);
+        dfree(p->d_pool); p->pool_bytes = 0;
+        CK(cudaMalloc(&p->d_pool, want));
+        p->pool_bytes = want;
+        todo.swap(exhausted);
+        continue;
+      }
       if (n == 1) { p->results[exhausted[0]] = p->p_results[exhausted[0]]; exhausted.clear(); }
       else {
         const int h = (n + 1) / 2;

@@ -287,3 +287,54 @@ def test_penalty_update_resolves_same_rows(psd):
     plan.set_penalty(pid, 5.0)
     plan.solve(); plan.download()
     assert plan.loss_row(pid) == first
+
+
+def test_config5_worst_case_piece_counts(psd):
+    """BASELINE config 5 (vignettes/Worst_case.Rmd): strictly increasing counts make the number of
+    pieces per function grow like N/2 (1,575 at N=3000 and penalty 1e6) -- far beyond the shared-memory
+    tier and beyond the per-warp spill workspace, so the host re-runs them from large global lists.
+    Compared with the oracle on the same rows (golden_synth.json pins N<=3000 against the reference)."""
+    from peaksegdisk_b200 import synth
+    probs = []
+    for n, pen in [(1000, 1e6), (2000, 1e4), (3000, 1e6), (600, 0.0)]:
+        probs.append(synth.increasing_problem(n) + (pen,))
+    plan, ids = psd.solve_batch(probs)
+    for pid, (s, e, c, pen) in zip(ids, probs):
+        _check_vs_oracle(plan, pid, s, e, c, pen)
+    assert max(plan.loss_row(i)["max.intervals"] for i in ids) > 1000
+
+
+def test_config3_shape_one_long_problem(psd):
+    """BASELINE config 3 shape: one long bedGraph (here 3e5 count positions, about 2.2e5 rows; the
+    1e6-row original takes the scalar oracle a minute per penalty) solved at the first penalties a
+    sequential search would try; a single warp owns the whole problem."""
+    from peaksegdisk_b200 import synth
+    s, e, c = synth.poisson_problem(2024, 300000)
+    plan = psd.Plan()
+    pid0 = plan.add(s, e, c, 0.0)
+    pidinf = plan.add(s, e, c, math.inf)
+    plan.run()
+    over, under = plan.loss_row(pid0), plan.loss_row(pidinf)
+    _check_vs_oracle(plan, pid0, s, e, c, 0.0)
+    nxt = (over["total.loss"] - under["total.loss"]) / (under["peaks"] - over["peaks"])   # R/sequentialSearch_dir.R:90
+    assert nxt > 0
+    pen = float(psd.r_paste(nxt))          # the search passes the 15-digit string on
+    plan.set_penalty(pid0, pen)
+    plan.run()
+    _check_vs_oracle(plan, pid0, s, e, c, pen)
+
+
+def test_file_batch_with_mixed_errors(psd, tmp_path):
+    """One launch for a batch in which some entries fail validation: each gets its own status, the
+    others are solved."""
+    good = str(tmp_path / "good.bedGraph")
+    open(good, "w").write("chr1\t0\t10\t2\nchr1\t10\t20\t10\nchr1\t20\t30\t14\nchr1\t30\t40\t13\n")
+    gap = str(tmp_path / "gap.bedGraph")
+    open(gap, "w").write("chr1 0 1 5\nchr1 2 3 3\n")
+    st = psd.PeakSegFPOP_file_batch([good, gap, good, str(tmp_path / "missing"), good],
+                                    ["10.5", "1", "-2", "1", "Inf"])
+    assert st == [0, 6, 2, 3, 0]
+    g = [c for c in golden("golden_small.json") if c["name"] == "four"]
+    for pen in ("10.5", "Inf"):
+        want = [c for c in g if c["penalty"] == pen][0]
+        assert outputs(good, pen) == (want["segments"], want["loss"])
