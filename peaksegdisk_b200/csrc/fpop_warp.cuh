@@ -749,17 +749,19 @@ PSD_DEV unsigned long long store_alloc(const StorePool& sp, StoreWriter& w, unsi
 }
 
 PSD_DEVNI void store_write(const WarpWs ws, unsigned char* rec, int row, const PList up, const PList down) {
+  // lanes 0-15 write the up function, lanes 16-31 the down function: one loop, one 128-bit store
+  // {hi, back_x} and one 32-bit store {back_i} per piece
   const int lane = psd_lane();
   const int cap = ws.cap;
+  const int grp = lane >> 4, gl = lane & 15;
   if (lane == 0) psd_st_cs_u4((unsigned*)rec, (unsigned)up.n, (unsigned)down.n, (unsigned)row, 0u);
-  double* pairs = (double*)(rec + 16);
-  for (int k = lane; k < up.n; k += 32) psd_st_cs_d2(pairs + 2 * k, PL_X(up, k), PL_P(up, k));
-  pairs += 2 * up.n;
-  for (int k = lane; k < down.n; k += 32) psd_st_cs_d2(pairs + 2 * k, PL_X(down, k), PL_P(down, k));
-  int* bis = (int*)(pairs + 2 * down.n);
-  for (int k = lane; k < up.n; k += 32) psd_st_cs_i(bis + k, PL_I(up, k));
-  bis += up.n;
-  for (int k = lane; k < down.n; k += 32) psd_st_cs_i(bis + k, PL_I(down, k));
+  const PList L = grp ? down : up;
+  double* pairs = (double*)(rec + 16) + (grp ? 2 * up.n : 0);
+  int* bis = (int*)((double*)(rec + 16) + 2 * (up.n + down.n)) + (grp ? up.n : 0);
+  for (int k = gl; k < L.n; k += PSD_G) {
+    psd_st_cs_d2(pairs + 2 * k, PL_X(L, k), PL_P(L, k));
+    psd_st_cs_i(bis + k, PL_I(L, k));
+  }
 }
 
 // per-problem result of the DP (device -> host), and of the backtrack
