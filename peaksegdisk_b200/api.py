@@ -261,72 +261,125 @@ def PeakSegFPOP_vec(count_vec, pen_num):
     return PeakSegFPOP_df(df, pen_num)
 
 
-def sequentialSearch_dir(problem_dir, peaks_int, verbose=0):
-    """R/sequentialSearch_dir.R:22-103: find the model with peaks_int peaks (or the next simpler one)
-    by a sequence of penalized solves.  The first two penalties (0, Inf) are solved as one batch."""
+def _solve_many(requests):
+    """requests: list of (problem_dir, penalty_str).  Everything that is not already cached goes to
+    the GPU in ONE batched launch; returns the PeakSegFPOP_dir result of every request."""
+    todo = []
+    for d, s in requests:
+        cov = os.path.join(d, "coverage.bedGraph")
+        pre = "%s_penalty=%s" % (cov, s)
+        if os.path.exists(cov) and _already_computed(cov, pre + "_segments.bed", pre + "_loss.tsv", pre + "_timing.tsv") is None:
+            todo.append((cov, s))
+    if len(todo) > 1:
+        t0 = time.time()
+        st = PeakSegFPOP_file_batch([c for c, _ in todo], [s for _, s in todo])
+        seconds = time.time() - t0
+        for (cov, s), code in zip(todo, st):
+            if code == 0:
+                with open("%s_penalty=%s_timing.tsv" % (cov, s), "w") as f:
+                    f.write("%s\t0\t%s\n" % (r_paste(_as_numeric(s)), r_paste(seconds)))
+    return [PeakSegFPOP_dir(d, s) for d, s in requests]
+
+
+class _Search:
+    """The state machine of R/sequentialSearch_dir.R:31-98 for one problem."""
+
+    def __init__(self, problem_dir, peaks_int):
+        self.dir, self.target = problem_dir, peaks_int
+        self.models = {}
+        self.next_pen = [0.0, math.inf]
+        self.iteration = 0
+        self.under = self.over = None
+        self.candidate = None
+
+    def requests(self):
+        return [(self.dir, r_paste(p)) for p in self.next_pen]
+
+    def update(self, fits):
+        self.iteration += 1
+        next_str = [r_paste(p) for p in self.next_pen]
+        for s, L in zip(next_str, fits):
+            L["loss"]["iteration"] = self.iteration
+            L["loss"]["under"] = np.nan if self.under is None else self.under["peaks"]
+            L["loss"]["over"] = np.nan if self.over is None else self.over["peaks"]
+            self.models[s] = L
+        if self.iteration == 1:
+            self.under = self.models["Inf"]["loss"].iloc[0]
+            self.over = self.models["0"]["loss"].iloc[0]
+            max_peaks = math.floor((self.over["bases"] - 1) / 2)
+            if max_peaks < self.target:
+                raise ValueError("peaks.int=%d but max=%d peaks for N=%d data" % (self.target, max_peaks, int(self.over["bases"])))
+        else:
+            m_new = self.models[next_str[0]]["loss"].iloc[0]
+            if m_new["peaks"] in (self.under["peaks"], self.over["peaks"]):   # not a new model
+                self.candidate = self.under
+                self.next_pen = []
+            elif m_new["peaks"] < self.target:
+                self.under = m_new
+            else:
+                self.over = m_new
+        if self.target == self.under["peaks"]:
+            self.candidate = self.under
+            self.next_pen = []
+        if self.target == self.over["peaks"]:
+            self.candidate = self.over
+            self.next_pen = []
+        if self.next_pen:
+            p = (self.over["total.loss"] - self.under["total.loss"]) / (self.under["peaks"] - self.over["peaks"])
+            if p < 0:
+                self.candidate = self.under
+                self.next_pen = []
+            else:
+                self.next_pen = [float(p)]
+
+    def result(self):
+        out = dict(self.models[r_paste(float(self.candidate["penalty"]))])
+        others = pd.concat([m["loss"] for m in self.models.values()], ignore_index=True)
+        out["others"] = others.sort_values("iteration", kind="stable").reset_index(drop=True)
+        return out
+
+
+def _check_search_args(problem_dir, peaks_int):
     if not (isinstance(peaks_int, (int, np.integer)) and not isinstance(peaks_int, bool) and 0 <= peaks_int):
         raise ValueError("is.integer(peaks.int) && length(peaks.int) == 1 && 0 <= peaks.int is not TRUE")
     if not isinstance(problem_dir, str):
         raise ValueError("is.character(problem.dir) is not TRUE")
-    model_list = {}
-    next_pen = [0.0, math.inf]
-    iteration = 0
-    under = over = None
-    candidate = None
-    while next_pen:
+
+
+def sequentialSearch_dir(problem_dir, peaks_int, verbose=0):
+    """R/sequentialSearch_dir.R:22-103: find the model with peaks_int peaks (or the next simpler one)
+    by a sequence of penalized solves.  The first two penalties (0, Inf) are solved as one batch
+    (the reference runs them through future_lapply)."""
+    _check_search_args(problem_dir, peaks_int)
+    st = _Search(problem_dir, peaks_int)
+    while st.next_pen:
         if verbose:
-            print("Next =", ", ".join(r_paste(p) for p in next_pen))
-        next_str = [r_paste(p) for p in next_pen]
-        iteration += 1
-        if len(next_str) > 1:
-            # both solves of the first iteration in one launch (the reference uses future_lapply here)
-            cov = os.path.join(problem_dir, "coverage.bedGraph")
-            todo = [s for s in next_str
-                    if _already_computed(cov, "%s_penalty=%s_segments.bed" % (cov, s), "%s_penalty=%s_loss.tsv" % (cov, s),
-                                         "%s_penalty=%s_timing.tsv" % (cov, s)) is None]
-            if len(todo) > 1 and os.path.exists(cov):
-                t0 = time.time()
-                st = PeakSegFPOP_file_batch([cov] * len(todo), todo)
-                seconds = time.time() - t0
-                for s, code in zip(todo, st):
-                    if code == 0:
-                        with open("%s_penalty=%s_timing.tsv" % (cov, s), "w") as f:
-                            f.write("%s\t0\t%s\n" % (r_paste(_as_numeric(s)), r_paste(seconds)))
-        for s in next_str:
-            L = PeakSegFPOP_dir(problem_dir, s)
-            L["loss"]["iteration"] = iteration
-            L["loss"]["under"] = np.nan if under is None else under["peaks"]
-            L["loss"]["over"] = np.nan if over is None else over["peaks"]
-            model_list[s] = L
-        if iteration == 1:
-            under = model_list["Inf"]["loss"].iloc[0]
-            over = model_list["0"]["loss"].iloc[0]
-            max_peaks = math.floor((over["bases"] - 1) / 2)
-            if max_peaks < peaks_int:
-                raise ValueError("peaks.int=%d but max=%d peaks for N=%d data" % (peaks_int, max_peaks, int(over["bases"])))
-        else:
-            m_new = model_list[next_str[0]]["loss"].iloc[0]
-            if m_new["peaks"] in (under["peaks"], over["peaks"]):
-                candidate = under
-                next_pen = []
-            elif m_new["peaks"] < peaks_int:
-                under = m_new
-            else:
-                over = m_new
-        if peaks_int == under["peaks"]:
-            candidate = under
-            next_pen = []
-        if peaks_int == over["peaks"]:
-            candidate = over
-            next_pen = []
-        if next_pen:
-            p = (over["total.loss"] - under["total.loss"]) / (under["peaks"] - over["peaks"])
-            if p < 0:
-                candidate = under
-                next_pen = []
-            else:
-                next_pen = [float(p)]
-    out = dict(model_list[r_paste(float(candidate["penalty"]))])
-    others = pd.concat([m["loss"] for m in model_list.values()], ignore_index=True)
-    out["others"] = others.sort_values("iteration", kind="stable").reset_index(drop=True)
-    return out
+            print("Next =", ", ".join(r_paste(p) for p in st.next_pen))
+        st.update(_solve_many(st.requests()))
+    return st.result()
+
+
+def sequentialSearch_batch(problem_dirs, peaks_int, verbose=0):
+    """Many sequential searches advanced in lock step: iteration k of every unfinished problem is one
+    batched GPU launch (one warp per (problem, penalty)).  peaks_int: one target or one per problem.
+    Returns the list of sequentialSearch_dir results; each problem follows exactly the chain the
+    single-problem search would."""
+    targets = [peaks_int] * len(problem_dirs) if isinstance(peaks_int, (int, np.integer)) else list(peaks_int)
+    for d, t in zip(problem_dirs, targets):
+        _check_search_args(d, t)
+    states = [_Search(d, t) for d, t in zip(problem_dirs, targets)]
+    while True:
+        active = [s for s in states if s.next_pen]
+        if not active:
+            break
+        reqs, spans = [], []
+        for s in active:
+            r = s.requests()
+            spans.append((len(reqs), len(reqs) + len(r)))
+            reqs.extend(r)
+        if verbose:
+            print("iteration with %d solves for %d problems" % (len(reqs), len(active)))
+        fits = _solve_many(reqs)
+        for s, (a, b) in zip(active, spans):
+            s.update(fits[a:b])
+    return [s.result() for s in states]

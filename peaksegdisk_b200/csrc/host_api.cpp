@@ -19,6 +19,8 @@
 #include <memory>
 #include <stdexcept>
 #include <string>
+#include <thread>
+#include <atomic>
 #include <vector>
 #include "psd_math.h"
 #include "plan_internal.h"
@@ -196,41 +198,68 @@ struct FileJob {
   int status = 0;
   double penalty = 0; bool is_inf = false;
   std::shared_ptr<Parsed> parsed;
-  FILE* loss_f = nullptr; FILE* seg_f = nullptr;
+  bool loss_created = false, seg_created = false;
   int plan_id = -1;
 };
 
-void close_job(FileJob& j) {
-  if (j.loss_f) fclose(j.loss_f);
-  if (j.seg_f) fclose(j.seg_f);
-  j.loss_f = j.seg_f = nullptr;
+// Runs fn(i) for i in [0,n) on up to hardware_concurrency host threads.
+template <class F> void parallel_for(int n, F fn) {
+  int nt = (int)std::thread::hardware_concurrency();
+  if (nt < 1) nt = 1;
+  if (nt > n) nt = n;
+  if (nt <= 1) { for (int i = 0; i < n; i++) fn(i); return; }
+  std::atomic<int> next(0);
+  std::vector<std::thread> pool;
+  for (int t = 0; t < nt; t++) pool.emplace_back([&]() { for (;;) { const int i = next.fetch_add(1); if (i >= n) break; fn(i); } });
+  for (auto& th : pool) th.join();
+}
+
+// creates / truncates a file and closes it again (outputs exist, empty, before the solve)
+bool touch(const std::string& path) {
+  FILE* f = fopen(path.c_str(), "wb");
+  if (!f) return false;
+  return fclose(f) == 0;
+}
+
+bool write_file(const std::string& path, const std::string& text) {
+  FILE* f = fopen(path.c_str(), "wb");
+  if (!f) return false;
+  const bool ok = write_all(f, text);
+  return (fclose(f) == 0) && ok;
 }
 
 int run_file_batch(int n, const char* const* bedgraphs, const char* const* penalties, const char* const* dbs, int* status_out) {
   std::vector<FileJob> jobs(n);
-  std::map<std::string, std::shared_ptr<Parsed>> cache;   // several penalties on one bedGraph parse it once
-  psd_plan* plan = nullptr;
-  int fatal = 0;
+  // several penalties on one bedGraph parse it once; distinct files are parsed on all host cores
+  std::map<std::string, std::shared_ptr<Parsed>> cache;
+  std::vector<std::shared_ptr<Parsed>> to_parse;
+  std::vector<std::string> to_parse_name;
   for (int i = 0; i < n; i++) {
     FileJob& j = jobs[i];
     j.bedgraph = bedgraphs[i]; j.penalty_str = penalties[i]; j.db = dbs[i];
     j.status = parse_penalty(penalties[i], &j.penalty, &j.is_inf);
-    if (j.status) continue;
+    if (j.status) continue;   // penalty errors come before any file access (:152-159)
     auto it = cache.find(j.bedgraph);
     if (it == cache.end()) {
-      auto P = std::make_shared<Parsed>();
-      parse_bedgraph(bedgraphs[i], *P);
-      it = cache.emplace(j.bedgraph, P).first;
+      it = cache.emplace(j.bedgraph, std::make_shared<Parsed>()).first;
+      to_parse.push_back(it->second); to_parse_name.push_back(j.bedgraph);
     }
     j.parsed = it->second;
+  }
+  parallel_for((int)to_parse.size(), [&](int k) { parse_bedgraph(to_parse_name[k].c_str(), *to_parse[k]); });
+  psd_plan* plan = nullptr;
+  int fatal = 0;
+  for (int i = 0; i < n; i++) {
+    FileJob& j = jobs[i];
+    if (j.status) continue;
     j.status = j.parsed->status;
     if (j.status == PSD_ERR_NOT_ENOUGH_COLUMNS)
       printf("problem: %d items on line %d\n", j.parsed->bad_items, j.parsed->bad_line);
     if (j.status) continue;
-    // outputs are created (empty) before anything else can fail, as the reference does
+    // outputs are created (empty) before anything else can fail, as the reference does (:222-223)
     const std::string prefix = j.bedgraph + "_penalty=" + j.penalty_str;
-    j.loss_f = fopen((prefix + "_loss.tsv").c_str(), "wb");
-    j.seg_f = fopen((prefix + "_segments.bed").c_str(), "wb");
+    j.loss_created = touch(prefix + "_loss.tsv");
+    j.seg_created = touch(prefix + "_segments.bed");
   }
   // build the plan
   for (int i = 0; i < n; i++) {
@@ -262,7 +291,8 @@ int run_file_batch(int n, const char* const* bedgraphs, const char* const* penal
     int rc = psd_plan_run(plan, nullptr);
     if (rc) fatal = rc;
   }
-  for (int i = 0; i < n; i++) {
+  // render and write the result files on all host cores
+  parallel_for(n, [&](int i) {
     FileJob& j = jobs[i];
     if (!j.status && fatal) j.status = fatal;
     if (!j.status) {
@@ -271,15 +301,15 @@ int run_file_batch(int n, const char* const* bedgraphs, const char* const* penal
       else {
         std::string seg_txt, loss_txt;
         render(h, j.parsed->chrom, j.penalty_str.c_str(), seg_txt, loss_txt);
-        const bool seg_ok = write_all(j.seg_f, seg_txt);
-        const bool loss_ok = write_all(j.loss_f, loss_txt);
+        const std::string prefix = j.bedgraph + "_penalty=" + j.penalty_str;
+        const bool seg_ok = j.seg_created && write_file(prefix + "_segments.bed", seg_txt);
+        const bool loss_ok = j.loss_created && write_file(prefix + "_loss.tsv", loss_txt);
         if (!loss_ok) j.status = PSD_ERR_WRITING_LOSS_OUTPUT;
         else if (!seg_ok) j.status = PSD_ERR_WRITING_SEGMENTS_OUTPUT;
       }
     }
-    close_job(j);
     status_out[i] = j.status;
-  }
+  });
   if (plan) psd_plan_destroy_impl(plan);
   return fatal;
 }

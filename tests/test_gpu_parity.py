@@ -338,3 +338,24 @@ def test_file_batch_with_mixed_errors(psd, tmp_path):
     for pen in ("10.5", "Inf"):
         want = [c for c in g if c["penalty"] == pen][0]
         assert outputs(good, pen) == (want["segments"], want["loss"])
+
+
+def test_batched_sequential_search_follows_single_chains(psd, tmp_path):
+    """sequentialSearch_batch advances many searches in lock step (one launch per iteration); every
+    problem must end with exactly the model its own sequentialSearch_dir finds."""
+    from peaksegdisk_b200 import synth
+    dirs, targets = [], []
+    for k, (seed, n, target) in enumerate([(40, 6000, 5), (41, 8000, 12), (42, 5000, 0), (43, 7000, 30)]):
+        s, e, c = synth.poisson_problem(seed, n)
+        for tag in ("a", "b"):
+            d = tmp_path / ("%s%d" % (tag, k))
+            d.mkdir()
+            synth.write_bedgraph(str(d / "coverage.bedGraph"), s, e, c)
+        dirs.append(str(tmp_path / ("a%d" % k))); targets.append(target)
+    batch = psd.sequentialSearch_batch(dirs, targets)
+    for k, (fit, target) in enumerate(zip(batch, targets)):
+        single = psd.sequentialSearch_dir(str(tmp_path / ("b%d" % k)), target)
+        assert int(fit["loss"]["peaks"][0]) == int(single["loss"]["peaks"][0]) <= target
+        assert psd.r_paste(float(fit["loss"]["penalty"][0])) == psd.r_paste(float(single["loss"]["penalty"][0]))
+        assert fit["segments"].equals(single["segments"])
+        assert fit["others"]["penalty"].tolist() == single["others"]["penalty"].tolist()
