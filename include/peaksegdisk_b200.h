@@ -83,6 +83,7 @@ typedef struct psd_stats {
   int64_t rows_solved;       /* rows of the non-trivial problems */
   int64_t store_bytes_algorithmic;  /* sum over problems of N*24 + 20*total_intervals */
   int64_t store_bytes_written;      /* bytes of records + index actually written to HBM */
+  int64_t store_bytes_spilled_host; /* record bytes that overflowed into pinned host memory */
   int64_t backtrack_bytes_read;
   int64_t h2d_bytes, d2h_bytes;
   int32_t n_launches;        /* kernels launched by the last solve */
@@ -119,7 +120,8 @@ int psd_plan_set_penalty(psd_plan *plan, int id, double penalty, int penalty_is_
 
 /* Tunables (call before psd_plan_create): "piece_cap" (shared-memory tier, default 48),
  * "overflow_cap" (global tier, default 8192), "store_gb" (HBM pool, default 0 = auto),
- * "chunk_kb" (store chunk, default 64), "warps_per_block" is fixed at 4. */
+ * "chunk_kb" (store chunk, default 64), "spill_cap" (per-warp global workspace, default 512),
+ * "host_spill_gb" (pinned-host overflow of the store: -1 = automatic, 0 = off). */
 int psd_set_option(const char *name, double value);
 
 int psd_device_count(void);

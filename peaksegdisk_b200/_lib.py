@@ -20,6 +20,7 @@ class PsdResult(C.Structure):
 class PsdStats(C.Structure):
     _fields_ = [("dp_ms", C.c_double), ("backtrack_ms", C.c_double), ("h2d_ms", C.c_double), ("d2h_ms", C.c_double),
                 ("rows_solved", C.c_int64), ("store_bytes_algorithmic", C.c_int64), ("store_bytes_written", C.c_int64),
+                ("store_bytes_spilled_host", C.c_int64),
                 ("backtrack_bytes_read", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
                 ("n_launches", C.c_int32), ("n_waves", C.c_int32), ("n_overflow_tier", C.c_int32),
                 ("piece_cap", C.c_int32), ("warps_per_sm", C.c_int32), ("n_sm", C.c_int32)]

@@ -71,7 +71,7 @@ struct BtKernelParams {
   const int* order;
   int n_order;
   DpResult* results;
-  const unsigned char* pool;
+  StorePool pool;
   const unsigned long long* seg_scratch_off;   // per problem: offset of its scratch segment arrays
   int* scratch_row; double* scratch_x;         // n_rows + 1 entries per problem
   int* seg_row; double* seg_x;                 // compacted output
@@ -108,7 +108,7 @@ fpop_backtrack_kernel(const BtKernelParams P) {
 namespace {
 thread_local std::string g_last_error;
 std::mutex g_opt_mutex;
-struct Options { int piece_cap = 48; int overflow_cap = 8192; double store_gb = 0; int chunk_kb = 64; int max_warps_per_sm = 0; int blocks_per_sm = 1; int spill_cap = 512; } g_opt;
+struct Options { int piece_cap = 48; int overflow_cap = 8192; double store_gb = 0; int chunk_kb = 64; int max_warps_per_sm = 0; int blocks_per_sm = 1; int spill_cap = 512; double host_spill_gb = -1; } g_opt;
 
 bool cuda_ok(cudaError_t e, const char* what) {
   if (e == cudaSuccess) return true;
@@ -133,6 +133,7 @@ int psd_set_option_impl(const char* name, double value) {
   else if (n == "max_warps_per_sm") g_opt.max_warps_per_sm = (int)value;
   else if (n == "blocks_per_sm") g_opt.blocks_per_sm = std::max(1, (int)value);
   else if (n == "spill_cap") g_opt.spill_cap = std::max(0, (int)value);
+  else if (n == "host_spill_gb") g_opt.host_spill_gb = value;
   else return PSD_ERR_ARG;
   return 0;
 }
@@ -158,6 +159,7 @@ struct psd_plan {
   unsigned char* d_pool = nullptr; unsigned long long pool_bytes = 0, pool_chunk = 0;
   size_t d_rows_cap = 0, d_prob_cap = 0, d_seg_cap = 0;
   unsigned char* d_gws = nullptr; unsigned long long gws_bytes = 0;
+  unsigned char* h_spill = nullptr; unsigned char* d_spill = nullptr; unsigned long long spill_bytes = 0;   // mapped pinned host region
   // pinned staging
   int32_t *p_weight = nullptr, *p_cov = nullptr;
   DpResult* p_results = nullptr;
@@ -191,6 +193,8 @@ struct psd_plan {
     if (p_weight) cudaFreeHost(p_weight); if (p_cov) cudaFreeHost(p_cov);
     if (p_results) cudaFreeHost(p_results); if (p_seg_row) cudaFreeHost(p_seg_row);
     if (p_seg_x) cudaFreeHost(p_seg_x); if (p_cursors) cudaFreeHost(p_cursors); if (p_queue_init) cudaFreeHost(p_queue_init);
+    if (h_spill) cudaFreeHost(h_spill);
+    h_spill = d_spill = nullptr; spill_bytes = 0;
     p_queue_init = nullptr;
     p_weight = p_cov = nullptr; p_results = nullptr; p_seg_row = nullptr; p_seg_x = nullptr; p_cursors = nullptr;
     if (ev_ok) { for (auto& e : ev) cudaEventDestroy(e); ev_ok = false; }
@@ -208,6 +212,7 @@ psd_plan* psd_plan_create_impl(int device) {
   if (const char* e = getenv("PSD_MAX_WARPS")) p->opt.max_warps_per_sm = atoi(e);
   if (const char* e = getenv("PSD_BLOCKS_PER_SM")) p->opt.blocks_per_sm = std::max(1, atoi(e));
   if (const char* e = getenv("PSD_SPILL_CAP")) p->opt.spill_cap = std::max(0, atoi(e));
+  if (const char* e = getenv("PSD_HOST_SPILL_GB")) p->opt.host_spill_gb = atof(e);
   memset(&p->stats, 0, sizeof p->stats);
   return p;
 }
@@ -385,7 +390,7 @@ int psd_plan_solve_impl(psd_plan* p, void* stream_v) {
   if (ng) CK(cudaSetDevice(p->device));
   psd_stats& S = p->stats;
   S.dp_ms = S.backtrack_ms = 0; S.n_launches = 0; S.n_waves = 0; S.n_overflow_tier = 0;
-  S.rows_solved = 0; S.store_bytes_algorithmic = 0; S.store_bytes_written = 0; S.backtrack_bytes_read = 0;
+  S.rows_solved = 0; S.store_bytes_algorithmic = 0; S.store_bytes_written = 0; S.backtrack_bytes_read = 0; S.store_bytes_spilled_host = 0;
   p->results.assign(ng, DpResult());
   p->n_seg_total = 0;
   if (ng == 0) { p->solved = true; return 0; }
@@ -438,6 +443,7 @@ int psd_plan_solve_impl(psd_plan* p, void* stream_v) {
     DpKernelParams K;
     K.problems = p->d_problems; K.order = p->d_order; K.n_order = n; K.queue = p->d_queue; K.results = p->d_results;
     K.pool.base = p->d_pool; K.pool.cursor = p->d_cursors; K.pool.n_chunks = p->pool_bytes / chunk; K.pool.chunk_bytes = chunk;
+    K.pool.host_base = p->d_spill; K.pool.host_cursor = p->d_cursors + 2; K.pool.host_chunks = p->spill_bytes / chunk;
     int grid; size_t smem; int wpb;
     if (!global_tier) {
       // shared-memory tier, with a per-warp global workspace the kernel moves to (and back from)
@@ -463,12 +469,13 @@ int psd_plan_solve_impl(psd_plan* p, void* stream_v) {
     p->p_queue_init[0] = grid * wpb;   // slots below this are assigned statically
     CK(cudaMemcpyAsync(p->d_queue, p->p_queue_init, sizeof(int), cudaMemcpyHostToDevice, st));
     CK(cudaMemsetAsync(p->d_cursors, 0, sizeof(unsigned long long), st));   // recycle the store pool
+    CK(cudaMemsetAsync(p->d_cursors + 2, 0, sizeof(unsigned long long), st));
     CK(cudaEventRecord(p->ev[2], st));
     fpop_dp_kernel<<<grid, wpb * 32, smem, st>>>(K);
     CK(cudaGetLastError());
     CK(cudaEventRecord(p->ev[3], st));
     BtKernelParams B;
-    B.problems = p->d_problems; B.order = p->d_order; B.n_order = n; B.results = p->d_results; B.pool = p->d_pool;
+    B.problems = p->d_problems; B.order = p->d_order; B.n_order = n; B.results = p->d_results; B.pool = K.pool;
     B.seg_scratch_off = p->d_seg_scratch_off; B.scratch_row = p->d_scratch_row; B.scratch_x = p->d_scratch_x;
     B.seg_row = p->d_seg_row; B.seg_x = p->d_seg_x; B.seg_cursor = p->d_cursors + 1;
     fpop_backtrack_kernel<<<(n + PSD_BT_WARPS_PER_BLOCK - 1) / PSD_BT_WARPS_PER_BLOCK, PSD_BT_WARPS_PER_BLOCK * 32, 0, st>>>(B);
@@ -483,6 +490,7 @@ int psd_plan_solve_impl(psd_plan* p, void* stream_v) {
     cudaEventElapsedTime(&ms, p->ev[2], p->ev[3]); S.dp_ms += ms;
     cudaEventElapsedTime(&ms, p->ev[3], p->ev[4]); S.backtrack_ms += ms;
     S.store_bytes_written += (int64_t)(std::min<unsigned long long>(p->p_cursors[0], K.pool.n_chunks) * chunk);
+    S.store_bytes_spilled_host += (int64_t)(std::min<unsigned long long>(p->p_cursors[2], K.pool.host_chunks) * chunk);
     std::vector<int> exhausted;
     for (int g : todo) {
       const DpResult& r = p->p_results[g];
@@ -502,6 +510,28 @@ int psd_plan_solve_impl(psd_plan* p, void* stream_v) {
         p->pool_bytes = want;
         todo.swap(exhausted);
         continue;
+      }
+      // HBM cannot grow any more: overflow into mapped pinned host memory
+      if (!p->d_spill && p->opt.host_spill_gb != 0) {
+        double gb = p->opt.host_spill_gb;
+        if (gb < 0) {   // automatic: a quarter of the host's available memory, at most 64 GB
+          gb = 8;
+          if (FILE* mf = fopen("/proc/meminfo", "r")) {
+            char line[256];
+            while (fgets(line, sizeof line, mf)) { unsigned long long kb; if (sscanf(line, "MemAvailable: %llu kB", &kb) == 1) gb = (double)kb / (1024.0 * 1024.0) * 0.25; }
+            fclose(mf);
+          }
+          if (gb > 64) gb = 64;
+        }
+        const unsigned long long want = ((unsigned long long)(gb * (double)(1ull << 30)) / chunk) * chunk;
+        if (want >= chunk * 16 && cudaHostAlloc((void**)&p->h_spill, want, cudaHostAllocMapped | cudaHostAllocPortable) == cudaSuccess) {
+          CK(cudaHostGetDevicePointer((void**)&p->d_spill, p->h_spill, 0));
+          p->spill_bytes = want;
+          todo.swap(exhausted);
+          continue;
+        }
+        cudaGetLastError();   // no pinned memory to be had: fall through to smaller waves
+        p->h_spill = nullptr;
       }
       if (n == 1) { p->results[exhausted[0]] = p->p_results[exhausted[0]]; exhausted.clear(); }
       else {

@@ -719,11 +719,17 @@ PSD_DEVNI void best_piece(const WarpWs ws, const PList f, double dmin, double* b
 //            (n_up + n_down) x i32 back_i, padded to 16 bytes
 // index[t] = byte offset of the record in the pool.  The reference's record
 // (src/PeakSegFPOPLog.cpp:12-34) carries the same fields at 8 + 20 bytes per piece per function.
+// When the HBM pool is exhausted and a host region is configured, chunks are taken from mapped
+// pinned host memory instead: records then stream over PCIe with the same 128-bit stores, and the
+// backtrack reads the few records it needs through the same mapping (offsets >= hbm bytes).
 struct StorePool {
-  unsigned char* base;
-  unsigned long long* cursor;     // next free chunk
+  unsigned char* base;            // HBM region
+  unsigned long long* cursor;     // next free HBM chunk
   unsigned long long n_chunks;
   unsigned long long chunk_bytes;
+  unsigned char* host_base;       // device-visible pinned host region (null: no spill)
+  unsigned long long* host_cursor;
+  unsigned long long host_chunks;
 };
 struct StoreWriter { unsigned long long cur, end; };
 
@@ -739,13 +745,25 @@ PSD_DEV unsigned long long store_alloc(const StorePool& sp, StoreWriter& w, unsi
     unsigned long long first = 0;
     if (psd_lane() == 0) first = psd_atomic_add_ull(sp.cursor, need);
     first = psd_shfl_u64(first, 0);
-    if (first + need > sp.n_chunks) return ~0ull;
+    if (first + need > sp.n_chunks) {          // HBM pool exhausted: spill to pinned host memory
+      if (sp.host_chunks == 0) return ~0ull;
+      unsigned long long h = 0;
+      if (psd_lane() == 0) h = psd_atomic_add_ull(sp.host_cursor, need);
+      h = psd_shfl_u64(h, 0);
+      if (h + need > sp.host_chunks) return ~0ull;
+      first = sp.n_chunks + h;
+    }
     w.cur = first * sp.chunk_bytes;
     w.end = w.cur + need * sp.chunk_bytes;
   }
   const unsigned long long off = w.cur;
   w.cur += bytes;
   return off;
+}
+
+PSD_DEV unsigned char* store_ptr(const StorePool& sp, unsigned long long off) {
+  const unsigned long long hbm = sp.n_chunks * sp.chunk_bytes;
+  return off < hbm ? sp.base + off : sp.host_base + (off - hbm);
 }
 
 PSD_DEVNI void store_write(const WarpWs ws, unsigned char* rec, int row, const PList up, const PList down) {
@@ -841,7 +859,10 @@ PSD_DEV void pl_move(const double* src, int scap, double* dst, int dcap, int n) 
 // (cap 0 = none).  A problem runs from shared memory; when a row's functions outgrow it the warp
 // moves the two previous functions to the global workspace and REPEATS THAT ROW there (the
 // operators never write their inputs), and moves back once both functions fit comfortably again.
-PSD_DEV void dp_run_queue(const WarpWs ws_s, const WarpWs ws_g, const DpQueue Q, const StorePool sp
+// NOTE: the aggregates are taken by const reference on purpose.  Taken by value, nvcc 12.9 handed this
+// (force-inlined) function a DpQueue whose last member was garbage once StorePool grew to 56 bytes
+// (the caller's copy was intact); found with device printf, see profiles/README.md.
+PSD_DEV void dp_run_queue(const WarpWs& ws_s, const WarpWs& ws_g, const DpQueue& Q, const StorePool& sp
 #if defined(PSD_EMU)
                           , psd_trace_fn trace, void* trace_user
 #endif
@@ -967,7 +988,7 @@ PSD_DEV void dp_run_queue(const WarpWs ws_s, const WarpWs ws_g, const DpQueue Q,
           const unsigned long long off = store_alloc(sp, sw, store_record_bytes(upP.n, downP.n));
           if (off == ~0ull) status = PSD_ST_STORE_EXHAUSTED;
           else {
-            store_write(ws, sp.base + off, t, upP, downP);
+            store_write(ws, store_ptr(sp, off), t, upP, downP);
             if (lane == (t & 31)) my_off = off;
             if ((t & 31) == 31 || t == N - 1) {
               const int r = (t & ~31) + lane;
@@ -1007,7 +1028,7 @@ PSD_DEV void dp_run_queue(const WarpWs ws_s, const WarpWs ws_g, const DpQueue Q,
 // Walks the stored functions from the last row back.  Output, last segment first:
 //   seg_x[s]   = log-mean of segment s            (s = 0 .. n_segments-1)
 //   seg_row[s] = last row of the segment before s (s = 0 .. n_segments-2)
-PSD_DEV void backtrack_problem(const unsigned char* pool, const unsigned long long* index, int n_rows,
+PSD_DEV void backtrack_problem(const StorePool& sp, const unsigned long long* index, int n_rows,
                                DpResult* res, int* seg_row, double* seg_x) {
   const int lane = psd_lane();
   if (res->status != PSD_ST_OK) return;
@@ -1017,7 +1038,7 @@ PSD_DEV void backtrack_problem(const unsigned char* pool, const unsigned long lo
   int n_seg = 1, n_eq = 0, status = PSD_ST_OK;
   while (0 <= back_i) {
     if (n_seg > n_rows) { status = PSD_ST_BACKTRACK_LOST; break; }
-    const unsigned char* rec = pool + index[back_i];
+    const unsigned char* rec = store_ptr(sp, index[back_i]);
     const unsigned* hdr = (const unsigned*)rec;
     const int n_up = (int)hdr[0], n_down = (int)hdr[1];
     const int n = use_down ? n_down : n_up;

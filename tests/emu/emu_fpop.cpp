@@ -20,7 +20,7 @@ void lane_main(void* arg) {
   Q.problems = &J->pb; Q.order = &J->order0; Q.n_order = 1; Q.cursor = &J->cursor; Q.results = J->res; Q.first_slot = 0;
   dp_run_queue(J->ws, J->ws_g, Q, J->sp, J->trace, J->trace_user);
   psd_syncwarp();
-  backtrack_problem(J->sp.base, J->pb.index, J->pb.n_rows, J->res, J->seg_row, J->seg_x);
+  backtrack_problem(J->sp, J->pb.index, J->pb.n_rows, J->res, J->seg_row, J->seg_x);
 }
 }  // namespace
 
@@ -58,7 +58,12 @@ int emu_fpop_rows(int n_rows, const int* chrom_start, const int* chrom_end, cons
   unsigned long long pool_bytes = (unsigned long long)n_rows * (32ull + 40ull * (unsigned)(cap > spill_cap ? cap : spill_cap) + 64ull) + chunk;
   if (pool_bytes > (6ull << 30)) pool_bytes = 6ull << 30;
   pool.resize((pool_bytes / chunk + 1) * chunk);
-  J.sp.base = pool.data(); J.sp.cursor = &cursor; J.sp.n_chunks = pool.size() / chunk; J.sp.chunk_bytes = chunk;
+  // PSD_EMU_HBM_CHUNKS (test knob): only that many chunks count as "HBM", the rest of the buffer
+  // plays the pinned-host spill region
+  unsigned long long hbm_chunks = pool.size() / chunk, host_cursor = 0;
+  if (const char* e = getenv("PSD_EMU_HBM_CHUNKS")) { const unsigned long long v = strtoull(e, 0, 10); if (v < hbm_chunks) hbm_chunks = v; }
+  J.sp.base = pool.data(); J.sp.cursor = &cursor; J.sp.n_chunks = hbm_chunks; J.sp.chunk_bytes = chunk;
+  J.sp.host_base = pool.data() + hbm_chunks * chunk; J.sp.host_cursor = &host_cursor; J.sp.host_chunks = pool.size() / chunk - hbm_chunks;
   DpResult res; res.status = -1;
   J.res = &res; J.trace = trace; J.trace_user = trace_user;
   std::vector<int> seg_row(n_rows + 1); std::vector<double> seg_x(n_rows + 1);

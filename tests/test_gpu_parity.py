@@ -359,3 +359,26 @@ def test_batched_sequential_search_follows_single_chains(psd, tmp_path):
         assert psd.r_paste(float(fit["loss"]["penalty"][0])) == psd.r_paste(float(single["loss"]["penalty"][0]))
         assert fit["segments"].equals(single["segments"])
         assert fit["others"]["penalty"].tolist() == single["others"]["penalty"].tolist()
+
+
+def test_store_spills_to_pinned_host_memory(psd):
+    """With an HBM pool far too small for the batch (and fixed, so it cannot grow) the cost-function
+    records overflow into mapped pinned host memory; the backtrack reads them back through the same
+    mapping.  Results must be identical to the all-HBM run and no extra wave may be needed."""
+    from peaksegdisk_b200 import synth
+    probs = [synth.poisson_problem(seed, 5000) + (pen,) for seed, pen in [(500, 0.0), (501, 20.0), (502, 1e3), (503, 1e5)]]
+    base, ids = psd.solve_batch(probs)
+    want = [(base.loss_row(i), base.segments(i)) for i in ids]
+    lib = psd._lib.lib
+    try:
+        lib.psd_set_option(b"store_gb", 0.002)       # 2 MB of HBM: a fraction of one problem
+        lib.psd_set_option(b"host_spill_gb", 0.25)
+        plan, ids2 = psd.solve_batch(probs)
+    finally:
+        lib.psd_set_option(b"store_gb", 0.0)
+        lib.psd_set_option(b"host_spill_gb", -1.0)
+    st = plan.stats()
+    assert st["store_bytes_spilled_host"] > 0, st
+    for i, (loss, seg) in zip(ids2, want):
+        assert plan.loss_row(i) == loss
+        assert all(np.array_equal(x, y) for x, y in zip(plan.segments(i), seg))
