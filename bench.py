@@ -104,7 +104,9 @@ def cpu_reference_run(probs, n_threads, target_rows, tmpdir):
         oracle_bind.ensure_built()
         lib_path, kind = oracle_bind.ORACLE_SO, "port"
     # sample: every stride-th problem until the row budget is met
-    stride = max(1, len(probs) // max(1, min(len(probs), 4 * n_threads + 8)))
+    avg_rows = max(1.0, sum(len(p[2]) for p in probs) / len(probs))
+    n_pick = int(min(len(probs), max(2 * n_threads, target_rows / avg_rows + 1)))
+    stride = max(1, len(probs) // n_pick)    # evenly spread over the batch (same mix of sizes / penalties)
     picked, rows = [], 0
     for i in range(0, len(probs), stride):
         picked.append(i); rows += len(probs[i][2])
