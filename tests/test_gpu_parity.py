@@ -382,3 +382,18 @@ def test_store_spills_to_pinned_host_memory(psd):
     for i, (loss, seg) in zip(ids2, want):
         assert plan.loss_row(i) == loss
         assert all(np.array_equal(x, y) for x, y in zip(plan.segments(i), seg))
+
+
+def test_records_larger_than_a_store_chunk(psd):
+    """With 1 KB store chunks almost every record spans several chunks (contiguous multi-chunk
+    allocation); increasing counts give records of tens of KB."""
+    from peaksegdisk_b200 import synth
+    probs = [synth.poisson_problem(610, 3000) + (100.0,), synth.increasing_problem(400) + (1e4,)]
+    lib = psd._lib.lib
+    try:
+        lib.psd_set_option(b"chunk_kb", 1.0)
+        plan, ids = psd.solve_batch(probs)
+    finally:
+        lib.psd_set_option(b"chunk_kb", 64.0)
+    for pid, (s, e, c, pen) in zip(ids, probs):
+        _check_vs_oracle(plan, pid, s, e, c, pen)
