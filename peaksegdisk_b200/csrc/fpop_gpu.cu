@@ -170,7 +170,7 @@ struct psd_plan {
   // bookkeeping
   std::vector<int> gpu_ids;                    // problem ids that go to the GPU
   int64_t total_rows = 0;
-  bool uploaded = false, solved = false;
+  bool uploaded = false, solved = false, packed = false;
   std::vector<DpResult> results;               // per gpu problem (indexed like gpu_ids)
   std::vector<int> seg_row; std::vector<double> seg_x;
   unsigned long long n_seg_total = 0;
@@ -236,7 +236,7 @@ void psd_plan_destroy_impl(psd_plan* p) { if (p) { if (p->ev_ok) cudaSetDevice(p
 
 std::vector<HostProblem>& psd_plan_problems(psd_plan* p) { return p->probs; }
 const std::vector<HostProblem>& psd_plan_problems_c(const psd_plan* p) { return p->probs; }
-void psd_plan_invalidate(psd_plan* p) { p->uploaded = false; p->solved = false; }
+void psd_plan_invalidate(psd_plan* p) { p->uploaded = false; p->solved = false; p->packed = false; }
 void psd_plan_mark_penalty_changed(psd_plan* p) { p->solved = false; }
 const psd_stats& psd_plan_stats_ref(const psd_plan* p) { return p->stats; }
 
@@ -259,12 +259,17 @@ int psd_plan_upload_impl(psd_plan* p, void* stream_v) {
     if (p->p_weight) cudaFreeHost(p->p_weight); if (p->p_cov) cudaFreeHost(p->p_cov);
     CK(cudaMallocHost(&p->p_weight, sizeof(int32_t) * total));
     CK(cudaMallocHost(&p->p_cov, sizeof(int32_t) * total));
-    p->p_rows_cap = total;
+    p->p_rows_cap = total; p->packed = false;
   }
-  for (int id : p->gpu_ids) {
-    const HostProblem& hp = p->probs[id];
-    memcpy(p->p_weight + hp.row_off, hp.weight.data(), sizeof(int32_t) * hp.n_rows);
-    memcpy(p->p_cov + hp.row_off, hp.coverage.data(), sizeof(int32_t) * hp.n_rows);
+  // rows are packed into the pinned staging buffers once per change of the problem set; a repeated
+  // upload of the same plan is then a pure pinned-host -> device copy
+  if (!p->packed) {
+    for (int id : p->gpu_ids) {
+      const HostProblem& hp = p->probs[id];
+      memcpy(p->p_weight + hp.row_off, hp.weight.data(), sizeof(int32_t) * hp.n_rows);
+      memcpy(p->p_cov + hp.row_off, hp.coverage.data(), sizeof(int32_t) * hp.n_rows);
+    }
+    p->packed = true;
   }
   // device buffers are grow-only: a plan that is re-uploaded with the same shapes allocates nothing
   if ((size_t)total > p->d_rows_cap) {
