@@ -28,6 +28,9 @@
 #define PSD_BT_WARPS_PER_BLOCK 4
 #define PSD_TAB_BYTES 4096
 
+#if defined(PSD_TIMING)
+__device__ unsigned long long psd_blk_end[160];
+#endif
 __device__ const uint64_t d_exp_tab[256] = PSD_EXP_TAB_INIT;
 __device__ const uint64_t d_log_tab[256] = PSD_LOG_TAB_INIT;
 
@@ -47,7 +50,10 @@ struct DpKernelParams {
 
 static inline unsigned long long psd_ws_bytes(int cap, int ccap) { return cap > 0 ? PSD_WS_BYTES(cap, ccap) : PSD_WS_HDR; }
 
-__global__ void __launch_bounds__(PSD_MAX_WARPS_PER_BLOCK * 32)
+#ifndef PSD_MIN_BLOCKS_PER_SM
+#define PSD_MIN_BLOCKS_PER_SM 1
+#endif
+__global__ void __launch_bounds__(PSD_MAX_WARPS_PER_BLOCK * 32, PSD_MIN_BLOCKS_PER_SM)
 fpop_dp_kernel(const DpKernelParams P) {
   uint64_t* etab = (uint64_t*)psd_smem;     // psd_smem: the block's dynamic shared memory (fpop_warp.cuh)
   uint64_t* ltab = etab + 256;
@@ -64,6 +70,12 @@ fpop_dp_kernel(const DpKernelParams P) {
   Q.problems = P.problems; Q.order = P.order; Q.n_order = P.n_order; Q.cursor = P.queue; Q.results = P.results;
   Q.first_slot = warp * (int)gridDim.x + (int)blockIdx.x;
   dp_run_queue(ws_s, ws_g, Q, P.pool);
+#if defined(PSD_TIMING)
+  if (threadIdx.x == 0 && blockIdx.x < 160) {   // when did this block run out of work? (ns since kernel start is derived on the host)
+    unsigned long long tns; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tns));
+    psd_blk_end[blockIdx.x] = tns;
+  }
+#endif
 }
 
 struct BtKernelParams {
@@ -603,6 +615,9 @@ int psd_device_count_impl() {
 }
 
 #if defined(PSD_TIMING)
+extern "C" int psd_debug_block_ends(unsigned long long* out) {
+  return cudaMemcpyFromSymbol(out, psd_blk_end, sizeof(unsigned long long) * 160) == cudaSuccess ? 0 : -1;
+}
 extern "C" int psd_debug_read(unsigned long long* out, int n, int reset) {
   unsigned long long tmp[32];
   if (cudaMemcpyFromSymbol(tmp, psd_dbg, sizeof tmp) != cudaSuccess) return -1;

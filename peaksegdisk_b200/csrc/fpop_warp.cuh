@@ -87,6 +87,12 @@ __device__ unsigned long long psd_dbg[32];
 #ifndef PSD_SPEC
 #define PSD_SPEC 16
 #endif
+// a problem running from its global workspace returns to shared memory when both functions have at
+// most PSD_RETURN_NUM/PSD_RETURN_DEN of the shared-memory capacity
+#ifndef PSD_RETURN_NUM
+#define PSD_RETURN_NUM 1
+#define PSD_RETURN_DEN 2
+#endif
 #define PSD_G 16             /* lanes per operator group (half a warp) */
 #define PSD_EPS 1e-12        /* NEWTON_EPSILON, src/funPieceListLog.cpp:9 */
 #define PSD_MAX_STEPS 100    /* NEWTON_STEPS,   src/funPieceListLog.cpp:10 */
@@ -766,7 +772,7 @@ PSD_DEV unsigned char* store_ptr(const StorePool& sp, unsigned long long off) {
   return off < hbm ? sp.base + off : sp.host_base + (off - hbm);
 }
 
-PSD_DEVNI void store_write(const WarpWs ws, unsigned char* rec, int row, const PList up, const PList down) {
+PSD_DEV void store_write(const WarpWs ws, unsigned char* rec, int row, const PList up, const PList down) {
   // lanes 0-15 write the up function, lanes 16-31 the down function: one loop, one 128-bit store
   // {hi, back_x} and one 32-bit store {back_i} per piece
   const int lane = psd_lane();
@@ -1007,7 +1013,7 @@ PSD_DEV void dp_run_queue(const WarpWs& ws_s, const WarpWs& ws_g, const DpQueue&
             res->pad_ = n_spill;
           }
           fetch = true;
-        } else if (in_g && ws_s.cap > 0 && 2 * upP.n <= ws_s.cap && 2 * downP.n <= ws_s.cap) {
+        } else if (in_g && ws_s.cap > 0 && PSD_RETURN_DEN * upP.n <= PSD_RETURN_NUM * ws_s.cap && PSD_RETURN_DEN * downP.n <= PSD_RETURN_NUM * ws_s.cap) {
           // both functions fit comfortably again: move back to shared memory
           psd_syncwarp();
           pl_move(upP.base, ws_g.cap, ws_list(ws_s, 0), ws_s.cap, upP.n);
