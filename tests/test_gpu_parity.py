@@ -397,3 +397,31 @@ def test_records_larger_than_a_store_chunk(psd):
         lib.psd_set_option(b"chunk_kb", 64.0)
     for pid, (s, e, c, pen) in zip(ids, probs):
         _check_vs_oracle(plan, pid, s, e, c, pen)
+
+
+def test_extreme_values_match_oracle(psd):
+    """Counts up to 2e9, weights up to 1e8 bases per row, long zero runs (log-mean domain starting at
+    -inf), penalties from 1e-12 to 1e15: the kernels must follow the oracle through every
+    inf/underflow corner of the reference's arithmetic."""
+    rng = np.random.default_rng(99)
+    probs = []
+    n = 400
+    w = rng.integers(1, 100000000, size=n).astype(np.int64)
+    e = np.cumsum(w) // 64 + np.arange(1, n + 1)          # strictly increasing, below 2^31
+    s = np.concatenate(([0], e[:-1]))
+    big = rng.integers(0, 2000000000, size=n)
+    big[rng.random(n) < 0.3] = 0
+    for pen in (1e-12, 1.0, 1e9, 1e15):
+        probs.append((s.astype(np.int32), e.astype(np.int32), big.astype(np.int32), pen))
+    z = np.zeros(300, np.int32); z[100:103] = 7; z[200] = 1
+    u = np.arange(300, dtype=np.int32)
+    for pen in (0.0, 1e-3, 5.0):
+        probs.append((u, u + 1, z, pen))
+    tiny = rng.poisson(0.01, size=2000).astype(np.int32)
+    tiny[5] = 1
+    from peaksegdisk_b200 import synth
+    t0, t1, tc = synth.rle_rows(tiny)
+    probs.append((t0, t1, tc, 0.5))
+    plan, ids = psd.solve_batch(probs)
+    for pid, (ps, pe, pc, pen) in zip(ids, probs):
+        _check_vs_oracle(plan, pid, ps, pe, pc, pen)
