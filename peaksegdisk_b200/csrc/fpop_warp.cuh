@@ -2,11 +2,13 @@
 //
 // One warp owns one problem (one bedGraph x one penalty).  The two cost functions of the
 // up-down-constrained optimal-partitioning DP are piecewise Poisson-loss functions of the
-// log-mean; each is a structure-of-arrays piece list in shared memory (global memory for the
-// overflow tier), one lane per piece.  Per bedGraph row the warp runs
-//     up_t   = rescale( min_env( min_less(down_{t-1}) + penalty/W_{t-1}, up_{t-1} ) )
-//     down_t = rescale( min_env( min_more(up_{t-1}),                     down_{t-1} ) )
-// and appends the breakpoints/back-pointers of both functions to the HBM cost-function store.
+// log-mean; each is a structure-of-arrays piece list in shared memory (the warp's global-memory
+// workspace when a function outgrows it), one lane per piece.  Per bedGraph row the warp runs
+//     up_t   = rescale( min_env( min_less(down_{t-1}) + penalty/W_{t-1}, up_{t-1} ) )    lanes  0-15
+//     down_t = rescale( min_env( min_more(up_{t-1}),                     down_{t-1} ) )  lanes 16-31
+// (the two recursions are independent given row t-1, so the two half-warps run them side by side
+// through the same code) and appends the breakpoints/back-pointers of both functions to the
+// cost-function store (HBM, overflowing into mapped pinned host memory).
 //
 // Reference behaviour being reproduced (file:line into tdhock/PeakSegDisk):
 //   piece algebra, Newton roots     src/funPieceListLog.cpp:29-234
@@ -16,14 +18,14 @@
 //                                   src/funPieceListLog.cpp:832-1285  -> min_env_op (+ pair_rule)
 //   add / multiply / set_prev_seg_end  :618-641  -> fused into the operators' output writes
 //   Minimize / findMean             :689-712 / :643-653  -> best_piece / backtrack_problem
-//   DP loop, decode                 src/PeakSegFPOPLog.cpp:258-442  -> dp_problem / backtrack_problem
+//   DP loop, decode                 src/PeakSegFPOPLog.cpp:258-442  -> dp_run_queue / backtrack_problem
 //   per-row store                   src/PeakSegFPOPLog.cpp:12-141   -> StoreWriter (HBM chunk arena)
 // Every floating-point expression keeps the reference's operand order and rounding (build with
 // -fmad=false); exp/log are psd_math.h, bit-identical to the libm the reference links.
 //
 // How the sequential operators map onto a warp:
-//   * min_less / min_more: lanes evaluate everything that depends on one piece only (end costs,
-//     argmin, argmin cost); the left-to-right (right-to-left) state machine then advances by
+//   * min_less / min_more (one routine, direction = data): lanes evaluate everything that depends on
+//     one piece only (end costs, argmin, argmin cost); the scan-order state machine then advances by
 //     ballots: "first piece that starts a flat stretch", then "first piece that ends it", the
 //     Newton solves of the second question running speculatively in all candidate lanes.
 //   * min_env: the overlap intervals of the two breakpoint lists are enumerated with a per-lane
@@ -33,6 +35,8 @@
 //
 // This header is compiled by nvcc for the product and, unmodified, by g++ against
 // tests/emu/warp_emu.h (PSD_EMU) where 32 fibers stand in for the lanes -- a test tool only.
+// Experiment switches (never set in the product build): PSD_TIMING (cycle counters), PSD_SPEC,
+// PSD_RETURN_NUM/DEN, PSD_INLINE_MATH; what they showed is in profiles/README.md.
 #pragma once
 #include "psd_math.h"
 
