@@ -100,3 +100,23 @@ def test_api_argument_errors(tmp_path):
     # Inf penalty: closed-form model, identical to the reference's files (test-CRAN-PeakSegFPOP_vec.R:9-15)
     fit = psd.PeakSegFPOP_vec([1, 3, 0, 4, 2], float("inf"))
     assert len(fit["segments"]) == 1 and int(fit["loss"]["peaks"][0]) == 0
+
+
+def test_reference_style_caller_links_against_the_library(tmp_path):
+    """A caller written like the reference's interface.cpp (C++-linkage declaration of
+    PeakSegFPOP_disk, src/PeakSegFPOPLog.h:15) links against the library and runs.  Without a GPU
+    only the closed-form branch (penalty Inf) can be exercised here."""
+    import subprocess
+    from peaksegdisk_b200 import _lib
+    exe = str(tmp_path / "dropin")
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    subprocess.check_call(["/usr/bin/g++", "-O1", "-o", exe, os.path.join(ROOT, "tests", "native", "dropin_link.cpp"),
+                           "-L" + libdir, "-lpeaksegdisk_b200", "-Wl,-rpath," + libdir])
+    bg = str(tmp_path / "two.bedGraph")
+    open(bg, "w").write("chr1 0 1 5\nchr1 1 3 3")
+    out = subprocess.run([exe, bg, "Inf", bg + ".db"], capture_output=True, text=True)
+    assert out.returncode == 0 and "status=0" in out.stdout
+    case = [c for c in golden("golden_small.json") if c["name"] == "two-rows-no-newline" and c["penalty"] == "Inf"][0]
+    assert outputs(bg, "Inf") == (case["segments"], case["loss"])
+    out = subprocess.run([exe, bg, "-1", bg + ".db"], capture_output=True, text=True)
+    assert out.returncode == 2
