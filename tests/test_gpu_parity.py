@@ -425,3 +425,20 @@ def test_extreme_values_match_oracle(psd):
     plan, ids = psd.solve_batch(probs)
     for pid, (ps, pe, pc, pen) in zip(ids, probs):
         _check_vs_oracle(plan, pid, ps, pe, pc, pen)
+
+
+def test_reference_style_caller_runs_the_gpu_solver(psd, tmp_path):
+    """The drop-in path end to end: a C++ caller declared like src/interface.cpp's links against the
+    library's mangled PeakSegFPOP_disk symbol and gets the reference's files (DP branch)."""
+    import subprocess
+    exe = str(tmp_path / "dropin")
+    libdir = os.path.dirname(psd._lib.LIB_PATH)
+    subprocess.check_call(["/usr/bin/g++", "-O1", "-o", exe, os.path.join(ROOT, "tests", "native", "dropin_link.cpp"),
+                           "-L" + libdir, "-lpeaksegdisk_b200", "-Wl,-rpath," + libdir])
+    case = [c for c in golden("golden_small.json") if c["name"] == "four" and c["penalty"] == "10.5"][0]
+    bg = str(tmp_path / "four.bedGraph")
+    open(bg, "w").write(case["input"])
+    out = subprocess.run([exe, bg, "10.5", bg + ".db"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert outputs(bg, "10.5") == (case["segments"], case["loss"])
+    assert os.path.getsize(bg + ".db") > 0      # R reports its size as `megabytes` and deletes it
