@@ -263,6 +263,9 @@ def main():
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "kernel": "fpop_dp_kernel", "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": st["dp_ms"],
+                "backtrack": {"kernel": "fpop_backtrack_kernel", "bytes_read": st["backtrack_bytes_read"], "kernel_ms": st["backtrack_ms"],
+                              "achieved": (st["backtrack_bytes_read"] / (st["backtrack_ms"] / 1e3) / 1e9) if st["backtrack_ms"] > 0 else 0.0,
+                              "unit": "GB/s", "note": "latency-bound pointer chase: one dependent record read per segment"},
                 "note": "DP is bound by fp64 issue/latency, not HBM (DESIGN.md); backtrack kernel ms=%.3f" % st["backtrack_ms"]}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",

@@ -566,7 +566,7 @@ int psd_plan_solve_impl(psd_plan* p, void* stream_v) {
     if (r.status == 0) {
       S.rows_solved += h.n_rows;
       S.store_bytes_algorithmic += h.n_rows * 24 + 20 * (int64_t)r.total_intervals;
-      S.backtrack_bytes_read += (int64_t)r.n_segments * 16;   // + 20 B per piece read, unknown here
+      S.backtrack_bytes_read += (int64_t)r.bt_bytes;
     }
   }
   p->n_seg_total = p->p_cursors[1];

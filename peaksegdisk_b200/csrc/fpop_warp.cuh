@@ -805,6 +805,7 @@ struct DpResult {
   int n_equality;
   int pad_;
   unsigned long long seg_offset;   // where the backtrack kernel put this problem's segments
+  unsigned long long bt_bytes;     // record + index bytes the backtrack read (8 + 16 + 20 per piece of the function used)
 };
 
 // optional per-row trace for tests (null in production): called by lane 0 after every row
@@ -1046,12 +1047,14 @@ PSD_DEV void backtrack_problem(const StorePool& sp, const unsigned long long* in
   int back_i = res->back_i;
   int use_down = 0;   // the last segment is "down"; the function read first is an "up" one
   int n_seg = 1, n_eq = 0, status = PSD_ST_OK;
+  unsigned long long bytes = 0;
   while (0 <= back_i) {
     if (n_seg > n_rows) { status = PSD_ST_BACKTRACK_LOST; break; }
     const unsigned char* rec = store_ptr(sp, index[back_i]);
     const unsigned* hdr = (const unsigned*)rec;
     const int n_up = (int)hdr[0], n_down = (int)hdr[1];
     const int n = use_down ? n_down : n_up;
+    bytes += 24ull + 20ull * (unsigned)n;
     const double* pairs = (const double*)(rec + 16) + (use_down ? 2 * n_up : 0);
     const int* bis = (const int*)((const double*)(rec + 16) + 2 * (n_up + n_down)) + (use_down ? n_up : 0);
     if (lane == 0) { seg_row[n_seg - 1] = back_i; seg_x[n_seg - 1] = best_x; }
@@ -1076,7 +1079,7 @@ PSD_DEV void backtrack_problem(const StorePool& sp, const unsigned long long* in
   }
   if (lane == 0) {
     seg_x[n_seg - 1] = best_x;
-    res->n_segments = n_seg; res->n_equality = n_eq;
+    res->n_segments = n_seg; res->n_equality = n_eq; res->bt_bytes = bytes;
     if (status != PSD_ST_OK) res->status = status;
   }
 }
