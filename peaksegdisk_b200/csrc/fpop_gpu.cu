@@ -515,21 +515,21 @@ int psd_plan_solve_impl(psd_plan* p, void* stream_v) {
       else if (r.status == PSD_ST_STORE_EXHAUSTED) exhausted.push_back(g);
       else { p->results[g] = r; if (r.pad_ > 0) S.n_overflow_tier++; }
     }
-    if (!exhausted.empty() && (int)exhausted.size() == n) {   // the pool held none of them
-      // first try a bigger pool (the automatic size is an estimate of ~1 KB per row)
+    if (!exhausted.empty()) {
+      // Some problems ran out of store.  In order of preference: a bigger HBM pool (the automatic
+      // size is only an estimate of ~1 KB per row), then overflow into mapped pinned host memory,
+      // and only then smaller waves that recycle the pool.
       size_t free_b = 0, total_b = 0;
       CK(cudaMemGetInfo(&free_b, &total_b));
       const unsigned long long lim = (((unsigned long long)((double)(free_b + p->pool_bytes) * 0.80)) / chunk) * chunk;
+      bool retry_bigger = false;
       if (p->opt.store_gb <= 0 && p->pool_bytes * 2 <= lim) {
         const unsigned long long want = std::min(lim, p->pool_bytes * 4);
         dfree(p->d_pool); p->pool_bytes = 0;
         CK(cudaMalloc(&p->d_pool, want));
         p->pool_bytes = want;
-        todo.swap(exhausted);
-        continue;
-      }
-      // HBM cannot grow any more: overflow into mapped pinned host memory
-      if (!p->d_spill && p->opt.host_spill_gb != 0) {
+        retry_bigger = true;
+      } else if (!p->d_spill && p->opt.host_spill_gb != 0) {
         double gb = p->opt.host_spill_gb;
         if (gb < 0) {   // automatic: a quarter of the host's available memory, at most 64 GB
           gb = 8;
@@ -539,22 +539,29 @@ int psd_plan_solve_impl(psd_plan* p, void* stream_v) {
             fclose(mf);
           }
           if (gb > 64) gb = 64;
+          // pinning is slow (~3 GB/s): do not pin more than the remaining problems can plausibly need
+          double need_rows = 0;
+          for (int g : exhausted) need_rows += (double)p->probs[p->gpu_ids[g]].n_rows;
+          const double est_gb = std::max(0.25, need_rows * 800.0 / (double)(1ull << 30));
+          if (gb > est_gb) gb = est_gb;
         }
         const unsigned long long want = ((unsigned long long)(gb * (double)(1ull << 30)) / chunk) * chunk;
         if (want >= chunk * 16 && cudaHostAlloc((void**)&p->h_spill, want, cudaHostAllocMapped | cudaHostAllocPortable) == cudaSuccess) {
           CK(cudaHostGetDevicePointer((void**)&p->d_spill, p->h_spill, 0));
           p->spill_bytes = want;
-          todo.swap(exhausted);
-          continue;
+          retry_bigger = true;
+        } else {
+          cudaGetLastError();   // no pinned memory to be had: smaller waves
+          p->h_spill = nullptr;
         }
-        cudaGetLastError();   // no pinned memory to be had: fall through to smaller waves
-        p->h_spill = nullptr;
       }
-      if (n == 1) { p->results[exhausted[0]] = p->p_results[exhausted[0]]; exhausted.clear(); }
-      else {
-        const int h = (n + 1) / 2;
-        deferred.insert(deferred.end(), exhausted.begin() + h, exhausted.end());
-        exhausted.resize(h);
+      if (!retry_bigger && (int)exhausted.size() == n) {   // same store, and it held none of them
+        if (n == 1) { p->results[exhausted[0]] = p->p_results[exhausted[0]]; exhausted.clear(); }
+        else {
+          const int h = (n + 1) / 2;
+          deferred.insert(deferred.end(), exhausted.begin() + h, exhausted.end());
+          exhausted.resize(h);
+        }
       }
     }
     todo.swap(exhausted);
