@@ -442,3 +442,14 @@ def test_reference_style_caller_runs_the_gpu_solver(psd, tmp_path):
     assert out.returncode == 0, out.stdout + out.stderr
     assert outputs(bg, "10.5") == (case["segments"], case["loss"])
     assert os.path.getsize(bg + ".db") > 0      # R reports its size as `megabytes` and deletes it
+
+
+def test_differential_fuzz_against_oracle():
+    """tools/fuzz_gpu_vs_oracle.py: 150 random problems of six shapes (bursty zeros, huge counts,
+    trends with hundreds of pieces, random weights, penalties 0 and 1e-3..1e7) in one launch; every
+    summary field and every segment bit-identical to the oracle."""
+    import subprocess, sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "fuzz_gpu_vs_oracle.py"), "150", "7"],
+                         capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert " 0 mismatches" in out.stdout
