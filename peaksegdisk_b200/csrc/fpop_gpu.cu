@@ -50,10 +50,11 @@ struct DpKernelParams {
 
 static inline unsigned long long psd_ws_bytes(int cap, int ccap) { return cap > 0 ? PSD_WS_BYTES(cap, ccap) : PSD_WS_HDR; }
 
-#ifndef PSD_MIN_BLOCKS_PER_SM
-#define PSD_MIN_BLOCKS_PER_SM 1
-#endif
-__global__ void __launch_bounds__(PSD_MAX_WARPS_PER_BLOCK * 32, PSD_MIN_BLOCKS_PER_SM)
+// Two builds of the same kernel: <16,1> one phase-locked block per SM at 128 registers (the default:
+// lowest per-row latency), <14,2> two blocks per SM at 72 registers (28 warps/SM: +18 % on batches of
+// many short problems, -25 % when a long problem sets the critical path; see choose_config()).
+template <int MAXW, int MINB>
+__global__ void __launch_bounds__(MAXW * 32, MINB)
 fpop_dp_kernel(const DpKernelParams P) {
   uint64_t* etab = (uint64_t*)psd_smem;     // psd_smem: the block's dynamic shared memory (fpop_warp.cuh)
   uint64_t* ltab = etab + 256;
@@ -120,7 +121,7 @@ fpop_backtrack_kernel(const BtKernelParams P) {
 namespace {
 thread_local std::string g_last_error;
 std::mutex g_opt_mutex;
-struct Options { int piece_cap = 48; int overflow_cap = 8192; double store_gb = 0; int chunk_kb = 64; int max_warps_per_sm = 0; int blocks_per_sm = 1; int spill_cap = 512; double host_spill_gb = -1; } g_opt;
+struct Options { int piece_cap = 48; int overflow_cap = 8192; double store_gb = 0; int chunk_kb = 64; int max_warps_per_sm = 0; int blocks_per_sm = 1; int spill_cap = 512; double host_spill_gb = -1; int occupancy_mode = 0; } g_opt;
 
 bool cuda_ok(cudaError_t e, const char* what) {
   if (e == cudaSuccess) return true;
@@ -146,6 +147,7 @@ int psd_set_option_impl(const char* name, double value) {
   else if (n == "blocks_per_sm") g_opt.blocks_per_sm = std::max(1, (int)value);
   else if (n == "spill_cap") g_opt.spill_cap = std::max(0, (int)value);
   else if (n == "host_spill_gb") g_opt.host_spill_gb = value;
+  else if (n == "occupancy_mode") g_opt.occupancy_mode = (int)value;   // 0 auto, 1 one block/SM, 2 two blocks/SM
   else return PSD_ERR_ARG;
   return 0;
 }
@@ -189,8 +191,9 @@ struct psd_plan {
   psd_stats stats;
   cudaEvent_t ev[8];
   bool ev_ok = false;
-  int warps_per_block = 0, cap = 0, ccap = 0;
-  size_t smem_bytes = 0;
+  struct LaunchCfg { bool ok = false; int blocks = 1, wpb = 0, cap = 0, ccap = 0; size_t smem = 0; } cfg[2];
+  bool configured = false;
+  double last_mean_intervals = 0;   // of the previous solve of this plan (0: unknown)
 
   ~psd_plan() { release(); }
   void release_device() {
@@ -225,6 +228,7 @@ psd_plan* psd_plan_create_impl(int device) {
   if (const char* e = getenv("PSD_BLOCKS_PER_SM")) p->opt.blocks_per_sm = std::max(1, atoi(e));
   if (const char* e = getenv("PSD_SPILL_CAP")) p->opt.spill_cap = std::max(0, atoi(e));
   if (const char* e = getenv("PSD_HOST_SPILL_GB")) p->opt.host_spill_gb = atof(e);
+  if (const char* e = getenv("PSD_OCCUPANCY_MODE")) p->opt.occupancy_mode = atoi(e);
   memset(&p->stats, 0, sizeof p->stats);
   return p;
 }
@@ -370,33 +374,58 @@ int psd_plan_upload_impl(psd_plan* p, void* stream_v) {
   return 0;
 }
 
-static int configure_kernel(psd_plan* p) {
-  if (p->warps_per_block) return 0;
-  int cap = p->opt.piece_cap;
+template <int MAXW, int MINB>
+static int configure_one(psd_plan* p, psd_plan::LaunchCfg& L, int cap0, int blocks) {
+  int cap = cap0;
   if (cap < 8) cap = 8;
   cap = (cap + 1) & ~1;
   for (;;) {
     const int ccap = 2 * cap;
     const size_t per_warp = psd_ws_bytes(cap, ccap);
-    const int nblk = p->opt.blocks_per_sm;   // independent phase-locked blocks per SM
     // each block also costs ~1 KB of reserved shared memory
-    int w = (int)((((size_t)p->prop.sharedMemPerMultiprocessor / nblk) - 1024 - PSD_TAB_BYTES) / per_warp);
+    int w = (int)((((size_t)p->prop.sharedMemPerMultiprocessor / blocks) - 1024 - PSD_TAB_BYTES) / per_warp);
     w = std::min(w, (int)(((size_t)p->prop.sharedMemPerBlockOptin - PSD_TAB_BYTES) / per_warp));
-    w = std::min(w, PSD_MAX_WARPS_PER_BLOCK);
-    if (p->opt.max_warps_per_sm > 0) w = std::min(w, std::max(1, p->opt.max_warps_per_sm / nblk));
+    w = std::min(w, MAXW);
+    if (p->opt.max_warps_per_sm > 0) w = std::min(w, std::max(1, p->opt.max_warps_per_sm / blocks));
     for (; w >= 1; w--) {   // registers may allow fewer warps than shared memory does
       const size_t smem = PSD_TAB_BYTES + (size_t)w * per_warp;
-      CK(cudaFuncSetAttribute(fpop_dp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      CK(cudaFuncSetAttribute(fpop_dp_kernel<MAXW, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       int nb = 0;
-      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fpop_dp_kernel, w * 32, smem));
-      if (nb >= nblk) {
-        p->warps_per_block = w; p->cap = cap; p->ccap = ccap; p->smem_bytes = smem;
-        return 0;
-      }
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fpop_dp_kernel<MAXW, MINB>, w * 32, smem));
+      if (nb >= blocks) { L.ok = true; L.blocks = blocks; L.wpb = w; L.cap = cap; L.ccap = ccap; L.smem = smem; return 0; }
     }
     cap /= 2;
-    if (cap < 8) { g_last_error = "cannot fit the DP kernel's shared memory"; return PSD_ERR_CUDA; }
+    if (cap < 8) { L.ok = false; return 0; }
   }
+}
+
+static int configure_kernel(psd_plan* p) {
+  if (p->configured) return 0;
+  int rc = configure_one<PSD_MAX_WARPS_PER_BLOCK, 1>(p, p->cfg[0], p->opt.piece_cap, p->opt.blocks_per_sm);
+  if (rc) return rc;
+  if (!p->cfg[0].ok) { g_last_error = "cannot fit the DP kernel's shared memory"; return PSD_ERR_CUDA; }
+  rc = configure_one<14, 2>(p, p->cfg[1], p->opt.piece_cap / 2, 2);
+  if (rc) return rc;
+  p->configured = true;
+  return 0;
+}
+
+// Picks the launch configuration for one wave.  cfg[0] (one block/SM) unless the batch is clearly
+// throughput-bound: its longest problem, run at the slower per-row latency of cfg[1], must still
+// finish well before the batch as a whole would, and the functions must be small enough for the
+// smaller shared-memory tier (known only from a previous solve of the same plan).
+static int choose_config(psd_plan* p, const std::vector<int>& todo) {
+  if (p->opt.occupancy_mode == 1 || !p->cfg[1].ok) return 0;
+  if (p->opt.occupancy_mode == 2) return 1;
+  double total = 0, longest = 0;
+  for (int g : todo) { const double n = (double)p->probs[p->gpu_ids[g]].n_rows; total += n; if (n > longest) longest = n; }
+  const double n_sm = (double)p->prop.multiProcessorCount;
+  const double lat0 = 44e-6, thr0 = 0.32e6;          // config 0: seconds per row of one warp under load; rows/s per SM
+  const double lat1 = 80e-6, thr1 = 0.38e6;          // config 1 (measured on B200, profiles/README.md)
+  const double t0 = std::max(longest * lat0, total / (n_sm * thr0));
+  const double t1 = std::max(longest * lat1, total / (n_sm * thr1));
+  if (p->last_mean_intervals > 9.0) return 0;        // functions too large for the 24-piece tier
+  return (t1 < 0.92 * t0 && (int)todo.size() >= 20 * (int)n_sm) ? 1 : 0;
 }
 
 // DP + backtrack for every uploaded problem.  Device-only: no host<->device row traffic.
@@ -413,7 +442,7 @@ int psd_plan_solve_impl(psd_plan* p, void* stream_v) {
   if (ng == 0) { p->solved = true; return 0; }
   int rc = configure_kernel(p);
   if (rc) return rc;
-  S.piece_cap = p->cap; S.warps_per_sm = p->warps_per_block * p->opt.blocks_per_sm; S.n_sm = p->prop.multiProcessorCount;
+  S.piece_cap = p->cfg[0].cap; S.warps_per_sm = p->cfg[0].wpb * p->cfg[0].blocks; S.n_sm = p->prop.multiProcessorCount;
   // penalties may have changed since upload (sequential search): refresh the descriptors' penalty
   {
     std::vector<DpProblem> hp(ng);
@@ -461,13 +490,16 @@ int psd_plan_solve_impl(psd_plan* p, void* stream_v) {
     K.problems = p->d_problems; K.order = p->d_order; K.n_order = n; K.queue = p->d_queue; K.results = p->d_results;
     K.pool.base = p->d_pool; K.pool.cursor = p->d_cursors; K.pool.n_chunks = p->pool_bytes / chunk; K.pool.chunk_bytes = chunk;
     K.pool.host_base = p->d_spill; K.pool.host_cursor = p->d_cursors + 2; K.pool.host_chunks = p->spill_bytes / chunk;
-    int grid; size_t smem; int wpb;
+    int grid; size_t smem; int wpb; int which = 0; int blocks = 1;
     if (!global_tier) {
       // shared-memory tier, with a per-warp global workspace the kernel moves to (and back from)
       // when a row's functions outgrow shared memory
-      K.cap_s = p->cap; K.ccap_s = p->ccap; K.ws_s_bytes = psd_ws_bytes(K.cap_s, K.ccap_s);
+      which = choose_config(p, todo);
+      const psd_plan::LaunchCfg& L = p->cfg[which];
+      K.cap_s = L.cap; K.ccap_s = L.ccap; K.ws_s_bytes = psd_ws_bytes(K.cap_s, K.ccap_s);
       K.cap_g = p->opt.spill_cap; K.ccap_g = 3 * K.cap_g; K.ws_g_bytes = psd_ws_bytes(K.cap_g, K.ccap_g);
-      smem = p->smem_bytes; wpb = p->warps_per_block;
+      smem = L.smem; wpb = L.wpb; blocks = L.blocks;
+      S.piece_cap = L.cap; S.warps_per_sm = L.wpb * L.blocks;
     } else {
       // host-level re-run of problems that outgrew even that: global lists only
       K.cap_s = 0; K.ccap_s = 0; K.ws_s_bytes = psd_ws_bytes(0, 0);
@@ -475,7 +507,7 @@ int psd_plan_solve_impl(psd_plan* p, void* stream_v) {
       wpb = std::min(8, PSD_MAX_WARPS_PER_BLOCK);
       smem = PSD_TAB_BYTES + (size_t)wpb * K.ws_s_bytes;
     }
-    grid = std::max(1, std::min(p->prop.multiProcessorCount * (global_tier ? 1 : p->opt.blocks_per_sm), n));   // a small batch spreads one warp per SM
+    grid = std::max(1, std::min(p->prop.multiProcessorCount * blocks, n));   // a small batch spreads one warp per SM
     K.gws = nullptr;
     if (K.cap_g > 0) {
       const unsigned long long need = (unsigned long long)grid * wpb * K.ws_g_bytes;
@@ -488,7 +520,8 @@ int psd_plan_solve_impl(psd_plan* p, void* stream_v) {
     CK(cudaMemsetAsync(p->d_cursors, 0, sizeof(unsigned long long), st));   // recycle the store pool
     CK(cudaMemsetAsync(p->d_cursors + 2, 0, sizeof(unsigned long long), st));
     CK(cudaEventRecord(p->ev[2], st));
-    fpop_dp_kernel<<<grid, wpb * 32, smem, st>>>(K);
+    if (which == 1) fpop_dp_kernel<14, 2><<<grid, wpb * 32, smem, st>>>(K);
+    else fpop_dp_kernel<PSD_MAX_WARPS_PER_BLOCK, 1><<<grid, wpb * 32, smem, st>>>(K);
     CK(cudaGetLastError());
     CK(cudaEventRecord(p->ev[3], st));
     BtKernelParams B;
@@ -567,6 +600,7 @@ int psd_plan_solve_impl(psd_plan* p, void* stream_v) {
     todo.swap(exhausted);
   }
   // algorithmic bytes: per problem N*24 + 20*total_intervals
+  double sum_iv = 0, sum_rows = 0;
   for (size_t g = 0; g < ng; g++) {
     const DpResult& r = p->results[g];
     const HostProblem& h = p->probs[p->gpu_ids[g]];
@@ -574,8 +608,10 @@ int psd_plan_solve_impl(psd_plan* p, void* stream_v) {
       S.rows_solved += h.n_rows;
       S.store_bytes_algorithmic += h.n_rows * 24 + 20 * (int64_t)r.total_intervals;
       S.backtrack_bytes_read += (int64_t)r.bt_bytes;
+      sum_iv += (double)r.total_intervals; sum_rows += (double)h.n_rows;
     }
   }
+  if (sum_rows > 0) p->last_mean_intervals = sum_iv / (2.0 * sum_rows);
   p->n_seg_total = p->p_cursors[1];
   p->solved = true;
   return 0;
