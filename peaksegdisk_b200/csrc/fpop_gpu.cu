@@ -16,6 +16,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -131,6 +132,18 @@ bool cuda_ok(cudaError_t e, const char* what) {
 #define CK(call) do { if (!cuda_ok((call), #call)) return PSD_ERR_CUDA; } while (0)
 
 template <class T> void dfree(T*& p) { if (p) cudaFree(p); p = nullptr; }
+
+// PSD_TRACE=1: wall-clock stage marks on stderr (where does a small solve's latency go?)
+struct Trace {
+  bool on; std::chrono::steady_clock::time_point t;
+  Trace() : on(getenv("PSD_TRACE") != nullptr), t(std::chrono::steady_clock::now()) {}
+  void mark(const char* what) {
+    if (!on) return;
+    const auto n = std::chrono::steady_clock::now();
+    fprintf(stderr, "[psd trace] %-34s %9.3f ms\n", what, std::chrono::duration<double, std::milli>(n - t).count());
+    t = n;
+  }
+};
 }  // namespace
 
 void psd_set_last_error(const std::string& s) { g_last_error = s; }
@@ -259,6 +272,7 @@ const psd_stats& psd_plan_stats_ref(const psd_plan* p) { return p->stats; }
 // H2D: pack the rows of the non-trivial problems, allocate index / result / segment buffers.
 int psd_plan_upload_impl(psd_plan* p, void* stream_v) {
   cudaStream_t st = (cudaStream_t)stream_v;
+  Trace tr;
   if (p->ev_ok) CK(cudaSetDevice(p->device));
   p->gpu_ids.clear();
   int64_t total = 0;
@@ -271,12 +285,14 @@ int psd_plan_upload_impl(psd_plan* p, void* stream_v) {
   const size_t ng = p->gpu_ids.size();
   if (ng == 0) { p->uploaded = true; p->solved = false; return 0; }
   { const int rc = ensure_device(p); if (rc) return rc; }
+  tr.mark("upload: ensure_device");
   if ((size_t)total > p->p_rows_cap) {
     if (p->p_weight) cudaFreeHost(p->p_weight); if (p->p_cov) cudaFreeHost(p->p_cov);
     CK(cudaMallocHost(&p->p_weight, sizeof(int32_t) * total));
     CK(cudaMallocHost(&p->p_cov, sizeof(int32_t) * total));
     p->p_rows_cap = total; p->packed = false;
   }
+  tr.mark("upload: pinned row staging");
   // rows are packed into the pinned staging buffers once per change of the problem set; a repeated
   // upload of the same plan is then a pure pinned-host -> device copy
   if (!p->packed) {
@@ -287,6 +303,7 @@ int psd_plan_upload_impl(psd_plan* p, void* stream_v) {
     }
     p->packed = true;
   }
+  tr.mark("upload: pack rows");
   // device buffers are grow-only: a plan that is re-uploaded with the same shapes allocates nothing
   if ((size_t)total > p->d_rows_cap) {
     dfree(p->d_weight); dfree(p->d_cov); dfree(p->d_index);
@@ -313,6 +330,7 @@ int psd_plan_upload_impl(psd_plan* p, void* stream_v) {
     CK(cudaMalloc(&p->d_seg_x, sizeof(double) * (total + ng)));
     p->d_seg_cap = total + ng;
   }
+  tr.mark("upload: device buffers");
   if (ng > p->p_res_cap) {
     if (p->p_results) cudaFreeHost(p->p_results);
     CK(cudaMallocHost(&p->p_results, sizeof(DpResult) * ng));
@@ -326,6 +344,7 @@ int psd_plan_upload_impl(psd_plan* p, void* stream_v) {
   }
   if (!p->p_cursors) CK(cudaMallocHost(&p->p_cursors, sizeof(unsigned long long) * 4));
   if (!p->p_queue_init) CK(cudaMallocHost(&p->p_queue_init, sizeof(int) * 4));
+  tr.mark("upload: pinned result staging");
   // store pool: sized from free memory unless the option pins it
   size_t free_b = 0, total_b = 0;
   CK(cudaMemGetInfo(&free_b, &total_b));
@@ -350,6 +369,7 @@ int psd_plan_upload_impl(psd_plan* p, void* stream_v) {
     CK(cudaMalloc(&p->d_pool, want));
     p->pool_bytes = want; p->pool_chunk = chunk;
   }
+  tr.mark("upload: store pool");
   // device problem descriptors
   std::vector<DpProblem> hp(ng);
   std::vector<unsigned long long> soff(ng);
@@ -367,6 +387,7 @@ int psd_plan_upload_impl(psd_plan* p, void* stream_v) {
   CK(cudaMemcpyAsync(p->d_seg_scratch_off, soff.data(), sizeof(unsigned long long) * ng, cudaMemcpyHostToDevice, st));
   CK(cudaEventRecord(p->ev[1], st));
   CK(cudaStreamSynchronize(st));   // hp/soff are pageable temporaries
+  tr.mark("upload: H2D + sync");
   float ms = 0; cudaEventElapsedTime(&ms, p->ev[0], p->ev[1]);
   p->stats.h2d_ms = ms;
   p->stats.h2d_bytes = (int64_t)(2 * sizeof(int) * total + (sizeof(DpProblem) + 8) * ng);
@@ -431,6 +452,7 @@ static int choose_config(psd_plan* p, const std::vector<int>& todo) {
 // DP + backtrack for every uploaded problem.  Device-only: no host<->device row traffic.
 int psd_plan_solve_impl(psd_plan* p, void* stream_v) {
   cudaStream_t st = (cudaStream_t)stream_v;
+  Trace tr;
   if (!p->uploaded) { g_last_error = "psd_plan_solve before psd_plan_upload"; return PSD_ERR_ARG; }
   const size_t ng = p->gpu_ids.size();
   if (ng) CK(cudaSetDevice(p->device));
@@ -442,6 +464,7 @@ int psd_plan_solve_impl(psd_plan* p, void* stream_v) {
   if (ng == 0) { p->solved = true; return 0; }
   int rc = configure_kernel(p);
   if (rc) return rc;
+  tr.mark("solve: configure_kernel");
   S.piece_cap = p->cfg[0].cap; S.warps_per_sm = p->cfg[0].wpb * p->cfg[0].blocks; S.n_sm = p->prop.multiProcessorCount;
   // penalties may have changed since upload (sequential search): refresh the descriptors' penalty
   {
@@ -514,6 +537,7 @@ int psd_plan_solve_impl(psd_plan* p, void* stream_v) {
       if (need > p->gws_bytes) { dfree(p->d_gws); p->gws_bytes = 0; CK(cudaMalloc(&p->d_gws, need)); p->gws_bytes = need; }
       K.gws = p->d_gws;
     }
+    tr.mark("solve: descriptors + workspace");
     CK(cudaMemcpyAsync(p->d_order, todo.data(), sizeof(int) * n, cudaMemcpyHostToDevice, st));
     p->p_queue_init[0] = grid * wpb;   // slots below this are assigned statically
     CK(cudaMemcpyAsync(p->d_queue, p->p_queue_init, sizeof(int), cudaMemcpyHostToDevice, st));
@@ -535,7 +559,9 @@ int psd_plan_solve_impl(psd_plan* p, void* stream_v) {
     // the wave's status words decide what (if anything) has to be re-run
     CK(cudaMemcpyAsync(p->p_results, p->d_results, sizeof(DpResult) * ng, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(p->p_cursors, p->d_cursors, sizeof(unsigned long long) * 4, cudaMemcpyDeviceToHost, st));
+    tr.mark("solve: launches enqueued");
     CK(cudaStreamSynchronize(st));
+    tr.mark("solve: kernels + status D2H");
     float ms = 0;
     cudaEventElapsedTime(&ms, p->ev[2], p->ev[3]); S.dp_ms += ms;
     cudaEventElapsedTime(&ms, p->ev[3], p->ev[4]); S.backtrack_ms += ms;
