@@ -92,6 +92,11 @@ typedef struct psd_stats {
   int32_t piece_cap;         /* shared-memory tier capacity (pieces per function) */
   int32_t warps_per_sm;
   int32_t n_sm;
+  /* count-vector problems (psd_plan_add_counts): the device run-length encoding done at upload */
+  int32_t n_rle_launches;
+  double rle_ms;                    /* device time of the four RLE kernels */
+  int64_t rle_positions;            /* count positions encoded */
+  int64_t rle_bytes_algorithmic;    /* 4 B per position read + 12 B per row written */
 } psd_stats;
 
 /* device < 0 selects the current CUDA device. */
@@ -101,6 +106,12 @@ void psd_plan_destroy(psd_plan *plan);
  * Returns the problem id (>= 0) or a negative PSD_ERR_*. */
 int psd_plan_add(psd_plan *plan, int64_t n_rows, const int32_t *chromStart, const int32_t *chromEnd,
                  const int32_t *coverage, double penalty, int penalty_is_inf);
+/* In-memory front end for a count vector (replaces R/PeakSegFPOP_vec.R:18-25 + PeakSegFPOP_df's
+ * bedGraph round trip): counts[i] >= 0 is the coverage of base [i, i+1).  The run-length encoding
+ * into bedGraph rows happens on the device at upload.  Results are the same as psd_plan_add() on the
+ * rows (chromStart 0-based, chromEnd = cumulative run lengths).  Returns the problem id or -PSD_ERR_*. */
+int psd_plan_add_counts(psd_plan *plan, int64_t n_positions, const int32_t *counts, double penalty,
+                        int penalty_is_inf);
 int psd_plan_size(const psd_plan *plan);
 /* stream: a cudaStream_t (0 = default stream).  upload/solve/download enqueue work on it;
  * download synchronizes the stream before returning. */

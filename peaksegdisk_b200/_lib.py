@@ -23,13 +23,15 @@ class PsdStats(C.Structure):
                 ("store_bytes_spilled_host", C.c_int64),
                 ("backtrack_bytes_read", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
                 ("n_launches", C.c_int32), ("n_waves", C.c_int32), ("n_overflow_tier", C.c_int32),
-                ("piece_cap", C.c_int32), ("warps_per_sm", C.c_int32), ("n_sm", C.c_int32)]
+                ("piece_cap", C.c_int32), ("warps_per_sm", C.c_int32), ("n_sm", C.c_int32),
+                ("n_rle_launches", C.c_int32), ("rle_ms", C.c_double), ("rle_positions", C.c_int64),
+                ("rle_bytes_algorithmic", C.c_int64)]
 
 
 # every symbol include/peaksegdisk_b200.h declares (tests check the library exports all of them)
 C_ABI_SYMBOLS = [
     "psd_fpop_disk", "psd_fpop_disk_batch", "psd_status_message", "psd_last_error", "psd_plan_create",
-    "psd_plan_destroy", "psd_plan_add", "psd_plan_size", "psd_plan_upload", "psd_plan_solve", "psd_plan_download",
+    "psd_plan_destroy", "psd_plan_add", "psd_plan_add_counts", "psd_plan_size", "psd_plan_upload", "psd_plan_solve", "psd_plan_download",
     "psd_plan_run", "psd_plan_result", "psd_plan_segments", "psd_plan_get_stats", "psd_plan_set_penalty",
     "psd_set_option", "psd_device_count",
     "_Z16PeakSegFPOP_diskPcS_S_",   # the reference's own C++-linkage entry (src/PeakSegFPOPLog.h:15)
@@ -57,6 +59,8 @@ def _load():
     lib.psd_plan_destroy.argtypes = [C.c_void_p]
     lib.psd_plan_add.restype = C.c_int
     lib.psd_plan_add.argtypes = [C.c_void_p, C.c_int64, i32p, i32p, i32p, C.c_double, C.c_int]
+    lib.psd_plan_add_counts.restype = C.c_int
+    lib.psd_plan_add_counts.argtypes = [C.c_void_p, C.c_int64, i32p, C.c_double, C.c_int]
     lib.psd_plan_size.restype = C.c_int
     lib.psd_plan_size.argtypes = [C.c_void_p]
     for name in ("psd_plan_upload", "psd_plan_solve", "psd_plan_download", "psd_plan_run"):

@@ -261,6 +261,26 @@ def PeakSegFPOP_vec(count_vec, pen_num):
     return PeakSegFPOP_df(df, pen_num)
 
 
+def PeakSegFPOP_vec_batch(count_vecs, pen_nums):
+    """Many PeakSegFPOP_vec calls as ONE in-memory batch: no bedGraph files, the count vectors go to
+    the device as they are and are run-length encoded there (rle_gpu.cuh).  Returns one dict per
+    problem with the `loss` row and `segments` table PeakSegFPOP_vec reports (chrom "chrUnknown")."""
+    from .plan import solve_counts_batch
+    pens = list(pen_nums)
+    for pen_num in pens:
+        if not (isinstance(pen_num, (int, float, np.integer, np.floating)) and not isinstance(pen_num, bool)
+                and not math.isnan(float(pen_num)) and 0 <= pen_num):
+            raise ValueError("pen.num must be non-negative numeric scalar")
+    plan, ids = solve_counts_batch(zip(count_vecs, [float(p) for p in pens]))
+    out = []
+    for pid in ids:
+        st, en, pk, mean = plan.segments(pid)
+        seg = pd.DataFrame({"chrom": "chrUnknown", "chromStart": st, "chromEnd": en,
+                            "status": np.where(pk == 1, "peak", "background"), "mean": mean})
+        out.append({"loss": pd.DataFrame([plan.loss_row(pid)]), "segments": seg})
+    return out
+
+
 def _solve_many(requests):
     """requests: list of (problem_dir, penalty_str).  Everything that is not already cached goes to
     the GPU in ONE batched launch; returns the PeakSegFPOP_dir result of every request."""

@@ -21,6 +21,7 @@
 #include <string>
 #include <vector>
 #include "fpop_warp.cuh"
+#include "rle_gpu.cuh"
 #include "plan_internal.h"
 
 #ifndef PSD_MAX_WARPS_PER_BLOCK
@@ -90,6 +91,8 @@ struct BtKernelParams {
   int* scratch_row; double* scratch_x;         // n_rows + 1 entries per problem
   int* seg_row; double* seg_x;                 // compacted output
   unsigned long long* seg_cursor;
+  const int* end_base;                         // count-vector problems: chromEnd rows made by rle_gpu.cuh
+  const long long* end_off;                    // per problem: offset into end_base, -1 = a row problem
 };
 
 __global__ void __launch_bounds__(PSD_BT_WARPS_PER_BLOCK * 32)
@@ -112,9 +115,12 @@ fpop_backtrack_kernel(const BtKernelParams P) {
   unsigned long long off = 0;
   if (lane == 0) { off = atomicAdd(P.seg_cursor, (unsigned long long)ns); res->seg_offset = off; }
   off = __shfl_sync(0xffffffffu, off, 0);
+  const long long eo = P.end_base ? P.end_off[id] : -1;
   for (int s = lane; s < ns; s += 32) {
     P.seg_x[off + s] = sx[s];
-    P.seg_row[off + s] = (s < ns - 1) ? srow[s] : -1;
+    int r = (s < ns - 1) ? srow[s] : -1;
+    if (eo >= 0 && r >= 0) r = P.end_base[eo + r];   // row number -> coordinate (the host has no rows)
+    P.seg_row[off + s] = r;
   }
 }
 
@@ -186,6 +192,14 @@ struct psd_plan {
   unsigned char* d_pool = nullptr; unsigned long long pool_bytes = 0, pool_chunk = 0;
   size_t d_rows_cap = 0, d_prob_cap = 0, d_seg_cap = 0;
   unsigned char* d_gws = nullptr; unsigned long long gws_bytes = 0;
+  // count-vector problems: raw counts, chromEnd rows, run-length-encoding descriptors
+  int *d_raw = nullptr, *d_end = nullptr; size_t d_raw_cap = 0, d_end_cap = 0;
+  long long* d_end_off = nullptr;
+  RleVec* d_rle_vecs = nullptr; int *d_tile_vec = nullptr, *d_tile_count = nullptr, *d_rle_nrows = nullptr;
+  size_t d_rle_vec_cap = 0, d_tile_cap = 0;
+  int32_t* p_raw = nullptr; size_t p_raw_cap = 0;
+  int* p_rle_nrows = nullptr; size_t p_rle_nrows_cap = 0;
+  int64_t rows_plain = 0, total_pos = 0; size_t n_count_problems = 0;
   unsigned char* h_spill = nullptr; unsigned char* d_spill = nullptr; unsigned long long spill_bytes = 0;   // mapped pinned host region
   // pinned staging
   int32_t *p_weight = nullptr, *p_cov = nullptr;
@@ -213,6 +227,8 @@ struct psd_plan {
     dfree(d_weight); dfree(d_cov); dfree(d_index); dfree(d_problems); dfree(d_results); dfree(d_order);
     dfree(d_queue); dfree(d_cursors); dfree(d_seg_scratch_off); dfree(d_scratch_row); dfree(d_seg_row);
     dfree(d_scratch_x); dfree(d_seg_x); dfree(d_pool); dfree(d_gws);
+    dfree(d_raw); dfree(d_end); dfree(d_end_off); dfree(d_rle_vecs); dfree(d_tile_vec); dfree(d_tile_count); dfree(d_rle_nrows);
+    d_raw_cap = d_end_cap = d_rle_vec_cap = d_tile_cap = 0;
     d_rows_cap = d_prob_cap = d_seg_cap = 0; pool_bytes = 0; gws_bytes = 0;
     uploaded = false;
   }
@@ -222,6 +238,8 @@ struct psd_plan {
     if (p_results) cudaFreeHost(p_results); if (p_seg_row) cudaFreeHost(p_seg_row);
     if (p_seg_x) cudaFreeHost(p_seg_x); if (p_cursors) cudaFreeHost(p_cursors); if (p_queue_init) cudaFreeHost(p_queue_init);
     if (h_spill) cudaFreeHost(h_spill);
+    if (p_raw) cudaFreeHost(p_raw); if (p_rle_nrows) cudaFreeHost(p_rle_nrows);
+    p_raw = nullptr; p_rle_nrows = nullptr; p_raw_cap = p_rle_nrows_cap = 0;
     h_spill = d_spill = nullptr; spill_bytes = 0;
     p_queue_init = nullptr;
     p_weight = p_cov = nullptr; p_results = nullptr; p_seg_row = nullptr; p_seg_x = nullptr; p_cursors = nullptr;
@@ -275,22 +293,42 @@ int psd_plan_upload_impl(psd_plan* p, void* stream_v) {
   Trace tr;
   if (p->ev_ok) CK(cudaSetDevice(p->device));
   p->gpu_ids.clear();
-  int64_t total = 0;
+  int64_t total = 0, total_pos = 0;
+  size_t n_counts = 0;
+  // row problems first: their (weight, coverage) rows are copied from the host; the rows of
+  // count-vector problems are produced on the device and only their raw counts are copied
+  for (int pass = 0; pass < 2; pass++)
+    for (size_t i = 0; i < p->probs.size(); i++) {
+      HostProblem& hp = p->probs[i];
+      if (hp.status != 0 || hp.trivial || (int)hp.from_counts != pass) continue;
+      hp.row_off = total; total += hp.n_rows;
+      if (pass == 1) { hp.raw_off = total_pos; total_pos += hp.n_pos; n_counts++; }
+    }
+  p->rows_plain = 0;
+  for (const HostProblem& hp : p->probs) if (hp.status == 0 && !hp.trivial && !hp.from_counts) p->rows_plain += hp.n_rows;
   for (size_t i = 0; i < p->probs.size(); i++) {
-    HostProblem& hp = p->probs[i];
-    if (hp.status == 0 && !hp.trivial) { hp.row_off = total; total += hp.n_rows; p->gpu_ids.push_back((int)i); }
+    const HostProblem& hp = p->probs[i];
+    if (hp.status == 0 && !hp.trivial) p->gpu_ids.push_back((int)i);
   }
-  p->total_rows = total;
+  p->total_rows = total; p->total_pos = total_pos; p->n_count_problems = n_counts;
   p->stats.h2d_bytes = 0; p->stats.h2d_ms = 0;
   const size_t ng = p->gpu_ids.size();
   if (ng == 0) { p->uploaded = true; p->solved = false; return 0; }
   { const int rc = ensure_device(p); if (rc) return rc; }
   tr.mark("upload: ensure_device");
-  if ((size_t)total > p->p_rows_cap) {
+  const int64_t plain = p->rows_plain;
+  if ((size_t)plain > p->p_rows_cap) {
     if (p->p_weight) cudaFreeHost(p->p_weight); if (p->p_cov) cudaFreeHost(p->p_cov);
-    CK(cudaMallocHost(&p->p_weight, sizeof(int32_t) * total));
-    CK(cudaMallocHost(&p->p_cov, sizeof(int32_t) * total));
-    p->p_rows_cap = total; p->packed = false;
+    p->p_weight = p->p_cov = nullptr; p->p_rows_cap = 0;
+    CK(cudaMallocHost(&p->p_weight, sizeof(int32_t) * plain));
+    CK(cudaMallocHost(&p->p_cov, sizeof(int32_t) * plain));
+    p->p_rows_cap = plain; p->packed = false;
+  }
+  if ((size_t)total_pos > p->p_raw_cap) {
+    if (p->p_raw) cudaFreeHost(p->p_raw);
+    p->p_raw = nullptr; p->p_raw_cap = 0;
+    CK(cudaMallocHost(&p->p_raw, sizeof(int32_t) * total_pos));
+    p->p_raw_cap = total_pos; p->packed = false;
   }
   tr.mark("upload: pinned row staging");
   // rows are packed into the pinned staging buffers once per change of the problem set; a repeated
@@ -298,6 +336,7 @@ int psd_plan_upload_impl(psd_plan* p, void* stream_v) {
   if (!p->packed) {
     for (int id : p->gpu_ids) {
       const HostProblem& hp = p->probs[id];
+      if (hp.from_counts) { memcpy(p->p_raw + hp.raw_off, hp.counts.data(), sizeof(int32_t) * hp.n_pos); continue; }
       memcpy(p->p_weight + hp.row_off, hp.weight.data(), sizeof(int32_t) * hp.n_rows);
       memcpy(p->p_cov + hp.row_off, hp.coverage.data(), sizeof(int32_t) * hp.n_rows);
     }
@@ -313,7 +352,8 @@ int psd_plan_upload_impl(psd_plan* p, void* stream_v) {
     p->d_rows_cap = total;
   }
   if (ng > p->d_prob_cap) {
-    dfree(p->d_problems); dfree(p->d_results); dfree(p->d_order); dfree(p->d_seg_scratch_off);
+    dfree(p->d_problems); dfree(p->d_results); dfree(p->d_order); dfree(p->d_seg_scratch_off); dfree(p->d_end_off);
+    CK(cudaMalloc(&p->d_end_off, sizeof(long long) * ng));
     CK(cudaMalloc(&p->d_problems, sizeof(DpProblem) * ng));
     CK(cudaMalloc(&p->d_results, sizeof(DpResult) * ng));
     CK(cudaMalloc(&p->d_order, sizeof(int) * ng));
@@ -329,6 +369,39 @@ int psd_plan_upload_impl(psd_plan* p, void* stream_v) {
     CK(cudaMalloc(&p->d_seg_row, sizeof(int) * (total + ng)));
     CK(cudaMalloc(&p->d_seg_x, sizeof(double) * (total + ng)));
     p->d_seg_cap = total + ng;
+  }
+  // count-vector problems: raw counts in, rows made on the device
+  std::vector<RleVec> rvecs; std::vector<int> tile_vec;
+  if (n_counts) {
+    if ((size_t)total_pos > p->d_raw_cap) { dfree(p->d_raw); p->d_raw_cap = 0; CK(cudaMalloc(&p->d_raw, sizeof(int) * total_pos)); p->d_raw_cap = total_pos; }
+    if ((size_t)total > p->d_end_cap) { dfree(p->d_end); p->d_end_cap = 0; CK(cudaMalloc(&p->d_end, sizeof(int) * total)); p->d_end_cap = total; }
+    rvecs.reserve(n_counts);
+    for (int id : p->gpu_ids) {
+      const HostProblem& h = p->probs[id];
+      if (!h.from_counts) continue;
+      RleVec v; v.raw_off = h.raw_off; v.row_off = h.row_off; v.n_pos = (int)h.n_pos; v.tile0 = (int)tile_vec.size();
+      const int nt = (int)((h.n_pos + PSD_RLE_TILE - 1) / PSD_RLE_TILE);
+      tile_vec.insert(tile_vec.end(), (size_t)nt, (int)rvecs.size());
+      rvecs.push_back(v);
+    }
+    if (rvecs.size() > p->d_rle_vec_cap) {
+      dfree(p->d_rle_vecs); dfree(p->d_rle_nrows); p->d_rle_vec_cap = 0;
+      CK(cudaMalloc(&p->d_rle_vecs, sizeof(RleVec) * rvecs.size()));
+      CK(cudaMalloc(&p->d_rle_nrows, sizeof(int) * rvecs.size()));
+      p->d_rle_vec_cap = rvecs.size();
+    }
+    if (tile_vec.size() > p->d_tile_cap) {
+      dfree(p->d_tile_vec); dfree(p->d_tile_count); p->d_tile_cap = 0;
+      CK(cudaMalloc(&p->d_tile_vec, sizeof(int) * tile_vec.size()));
+      CK(cudaMalloc(&p->d_tile_count, sizeof(int) * tile_vec.size()));
+      p->d_tile_cap = tile_vec.size();
+    }
+    if (rvecs.size() > p->p_rle_nrows_cap) {
+      if (p->p_rle_nrows) cudaFreeHost(p->p_rle_nrows);
+      p->p_rle_nrows = nullptr; p->p_rle_nrows_cap = 0;
+      CK(cudaMallocHost(&p->p_rle_nrows, sizeof(int) * rvecs.size()));
+      p->p_rle_nrows_cap = rvecs.size();
+    }
   }
   tr.mark("upload: device buffers");
   if (ng > p->p_res_cap) {
@@ -373,24 +446,63 @@ int psd_plan_upload_impl(psd_plan* p, void* stream_v) {
   // device problem descriptors
   std::vector<DpProblem> hp(ng);
   std::vector<unsigned long long> soff(ng);
+  std::vector<long long> eoff(ng);
   for (size_t g = 0; g < ng; g++) {
     const HostProblem& h = p->probs[p->gpu_ids[g]];
     hp[g].weight = p->d_weight + h.row_off; hp[g].coverage = p->d_cov + h.row_off;
     hp[g].n_rows = (int)h.n_rows; hp[g].penalty = h.penalty; hp[g].dmin = h.dmin; hp[g].dmax = h.dmax;
     hp[g].index = p->d_index + h.row_off;
     soff[g] = (unsigned long long)h.row_off + g;
+    eoff[g] = h.from_counts ? (long long)h.row_off : -1;
   }
   CK(cudaEventRecord(p->ev[0], st));
-  CK(cudaMemcpyAsync(p->d_weight, p->p_weight, sizeof(int) * total, cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(p->d_cov, p->p_cov, sizeof(int) * total, cudaMemcpyHostToDevice, st));
+  if (plain) {
+    CK(cudaMemcpyAsync(p->d_weight, p->p_weight, sizeof(int) * plain, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(p->d_cov, p->p_cov, sizeof(int) * plain, cudaMemcpyHostToDevice, st));
+  }
+  if (n_counts) {
+    CK(cudaMemcpyAsync(p->d_raw, p->p_raw, sizeof(int) * total_pos, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(p->d_rle_vecs, rvecs.data(), sizeof(RleVec) * rvecs.size(), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(p->d_tile_vec, tile_vec.data(), sizeof(int) * tile_vec.size(), cudaMemcpyHostToDevice, st));
+  }
   CK(cudaMemcpyAsync(p->d_problems, hp.data(), sizeof(DpProblem) * ng, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(p->d_seg_scratch_off, soff.data(), sizeof(unsigned long long) * ng, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(p->d_end_off, eoff.data(), sizeof(long long) * ng, cudaMemcpyHostToDevice, st));
   CK(cudaEventRecord(p->ev[1], st));
-  CK(cudaStreamSynchronize(st));   // hp/soff are pageable temporaries
-  tr.mark("upload: H2D + sync");
+  p->stats.rle_ms = 0; p->stats.rle_bytes_algorithmic = 0; p->stats.rle_positions = 0; p->stats.n_rle_launches = n_counts ? 4 : 0;
+  if (n_counts) {
+    // run-length encode on the device (rle_gpu.cuh): 4 launches, all on the plan's stream
+    RleParams R;
+    R.vecs = p->d_rle_vecs; R.tile_vec = p->d_tile_vec; R.n_tiles = (int)tile_vec.size(); R.n_vecs = (int)rvecs.size();
+    R.raw = p->d_raw; R.coverage = p->d_cov; R.chrom_end = p->d_end; R.weight = p->d_weight;
+    R.tile_count = p->d_tile_count; R.n_rows = p->d_rle_nrows;
+    CK(cudaEventRecord(p->ev[5], st));
+    rle_count_kernel<<<R.n_tiles, PSD_RLE_WARPS * 32, 0, st>>>(R);
+    rle_scan_kernel<<<(R.n_vecs + 7) / 8, 256, 0, st>>>(R);
+    rle_scatter_kernel<<<R.n_tiles, PSD_RLE_WARPS * 32, 0, st>>>(R);
+    rle_weight_kernel<<<R.n_tiles, PSD_RLE_WARPS * 32, 0, st>>>(R);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(p->ev[6], st));
+    CK(cudaMemcpyAsync(p->p_rle_nrows, p->d_rle_nrows, sizeof(int) * rvecs.size(), cudaMemcpyDeviceToHost, st));
+  }
+  CK(cudaStreamSynchronize(st));   // hp/soff/... are pageable temporaries
+  tr.mark("upload: H2D + RLE + sync");
   float ms = 0; cudaEventElapsedTime(&ms, p->ev[0], p->ev[1]);
   p->stats.h2d_ms = ms;
-  p->stats.h2d_bytes = (int64_t)(2 * sizeof(int) * total + (sizeof(DpProblem) + 8) * ng);
+  p->stats.h2d_bytes = (int64_t)(2 * sizeof(int) * plain + sizeof(int) * total_pos + (sizeof(DpProblem) + 16) * ng +
+                                 sizeof(RleVec) * rvecs.size() + sizeof(int) * tile_vec.size());
+  if (n_counts) {
+    cudaEventElapsedTime(&ms, p->ev[5], p->ev[6]);
+    p->stats.rle_ms = ms; p->stats.rle_positions = total_pos;
+    p->stats.rle_bytes_algorithmic = (int64_t)(4 * total_pos + 12 * (total - plain));
+    size_t k = 0;
+    for (int id : p->gpu_ids) {
+      const HostProblem& h = p->probs[id];
+      if (!h.from_counts) continue;
+      if (p->p_rle_nrows[k] != (int)h.n_rows) { g_last_error = "device run-length encoding disagrees with the host's run count"; return PSD_ERR_INTERNAL; }
+      k++;
+    }
+  }
   p->uploaded = true; p->solved = false;
   return 0;
 }
@@ -552,6 +664,7 @@ int psd_plan_solve_impl(psd_plan* p, void* stream_v) {
     B.problems = p->d_problems; B.order = p->d_order; B.n_order = n; B.results = p->d_results; B.pool = K.pool;
     B.seg_scratch_off = p->d_seg_scratch_off; B.scratch_row = p->d_scratch_row; B.scratch_x = p->d_scratch_x;
     B.seg_row = p->d_seg_row; B.seg_x = p->d_seg_x; B.seg_cursor = p->d_cursors + 1;
+    B.end_base = p->n_count_problems ? p->d_end : nullptr; B.end_off = p->d_end_off;
     fpop_backtrack_kernel<<<(n + PSD_BT_WARPS_PER_BLOCK - 1) / PSD_BT_WARPS_PER_BLOCK, PSD_BT_WARPS_PER_BLOCK * 32, 0, st>>>(B);
     CK(cudaGetLastError());
     CK(cudaEventRecord(p->ev[4], st));

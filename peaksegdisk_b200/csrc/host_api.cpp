@@ -157,7 +157,7 @@ void render(const HostProblem& h, const std::string& chrom, const char* penalty_
     const double SWZ = h.sum_wz, W = h.bases;
     const double bc = (SWZ != 0) ? SWZ * (1 - hlog(SWZ) + hlog(W)) : 0;
     seg_txt = chrom; seg_txt += "\t";
-    snprintf(ib, sizeof ib, "%d\t%d\tbackground\t", h.chrom_start[0], h.chrom_end[n - 1]); seg_txt += ib;
+    snprintf(ib, sizeof ib, "%d\t%d\tbackground\t", hp_first_start(h), hp_last_end(h)); seg_txt += ib;
     format_g(seg_txt, "%g", SWZ / W); seg_txt += "\n";
     loss_txt = penalty_str;
     snprintf(ib, sizeof ib, "\t1\t0\t%d\t%d\t", (int)W, (int)n); loss_txt += ib;
@@ -166,10 +166,10 @@ void render(const HostProblem& h, const std::string& chrom, const char* penalty_
     return;
   }
   const int ns = h.n_segments;
-  int prev_end = h.chrom_end[n - 1];
+  int prev_end = hp_last_end(h);
   seg_txt.clear();
   for (int s = 0; s < ns; s++) {
-    const int st = (s < ns - 1) ? h.chrom_end[h.seg_row[s]] : h.chrom_start[0];
+    const int st = (s < ns - 1) ? hp_seg_start(h, s) : hp_first_start(h);
     seg_txt += chrom;
     snprintf(ib, sizeof ib, "\t%d\t%d\t%s\t", st, prev_end, (s & 1) ? "peak" : "background"); seg_txt += ib;
     format_g(seg_txt, "%g", hexp(h.seg_x[s])); seg_txt += "\n";
@@ -380,6 +380,37 @@ int psd_plan_add(psd_plan* plan, int64_t n_rows, const int32_t* chromStart, cons
   return (int)v.size() - 1;
 }
 
+// In-memory front end for a count vector (R/PeakSegFPOP_vec.R:18-25 does rle() + cumsum on the host
+// and goes through a bedGraph file): position i of `counts` is the base [i, i+1).  One host pass
+// for the totals the loss line needs (bases, sum of counts, runs = bedGraph.lines, log range); the
+// run-length encoding itself happens on the device at upload (rle_gpu.cuh).
+int psd_plan_add_counts(psd_plan* plan, int64_t n, const int32_t* counts, double penalty, int penalty_is_inf) {
+  if (!plan || n <= 0 || n > 0x3fffffff || !counts) return -PSD_ERR_ARG;
+  if (!penalty_is_inf) {
+    if (!std::isfinite(penalty)) return -PSD_ERR_PENALTY_NOT_FINITE;
+    if (penalty < 0) return -PSD_ERR_PENALTY_NEGATIVE;
+  }
+  int32_t lo = counts[0], hi = counts[0];
+  int64_t runs = 1; double sum = (double)counts[0];
+  for (int64_t i = 1; i < n; i++) {
+    const int32_t z = counts[i];
+    runs += (z != counts[i - 1]);
+    sum += (double)z;            // exact: integers below 2^53, like the reference's running double total
+    lo = z < lo ? z : lo; hi = z > hi ? z : hi;
+  }
+  if (lo < 0) return -PSD_ERR_ARG;
+  std::vector<HostProblem>& v = psd_plan_problems(plan);
+  v.emplace_back();
+  HostProblem& h = v.back();
+  h.from_counts = true; h.n_pos = n; h.n_rows = runs;
+  h.penalty = penalty; h.penalty_is_inf = penalty_is_inf != 0;
+  h.counts.assign(counts, counts + n);
+  h.bases = (double)n; h.sum_wz = sum; h.dmin = hlog((double)lo); h.dmax = hlog((double)hi);
+  h.trivial = h.penalty_is_inf || lo == hi;
+  psd_plan_invalidate(plan);
+  return (int)v.size() - 1;
+}
+
 int psd_plan_size(const psd_plan* plan) { return plan ? (int)psd_plan_problems_c(plan).size() : 0; }
 
 int psd_plan_set_penalty(psd_plan* plan, int id, double penalty, int penalty_is_inf) {
@@ -440,16 +471,15 @@ int psd_plan_segments(const psd_plan* plan, int id, int32_t* chromStart, int32_t
   const std::vector<HostProblem>& v = psd_plan_problems_c(plan);
   if (id < 0 || id >= (int)v.size()) return PSD_ERR_ARG;
   const HostProblem& h = v[id];
-  const int64_t n = h.n_rows;
   if (h.status) return h.status;
   if (h.trivial) {
-    chromStart[0] = h.chrom_start[0]; chromEnd[0] = h.chrom_end[n - 1]; is_peak[0] = 0; mean[0] = h.sum_wz / h.bases;
+    chromStart[0] = hp_first_start(h); chromEnd[0] = hp_last_end(h); is_peak[0] = 0; mean[0] = h.sum_wz / h.bases;
     return 0;
   }
   if (h.result_status != 0) return h.result_status < 0 ? PSD_ERR_ARG : h.result_status;
-  int prev_end = h.chrom_end[n - 1];
+  int prev_end = hp_last_end(h);
   for (int s = 0; s < h.n_segments; s++) {
-    const int st = (s < h.n_segments - 1) ? h.chrom_end[h.seg_row[s]] : h.chrom_start[0];
+    const int st = (s < h.n_segments - 1) ? hp_seg_start(h, s) : hp_first_start(h);
     chromStart[s] = st; chromEnd[s] = prev_end; is_peak[s] = s & 1; mean[s] = hexp(h.seg_x[s]);
     prev_end = st;
   }

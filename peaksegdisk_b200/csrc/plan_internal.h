@@ -13,6 +13,12 @@ struct HostProblem {
   double penalty = 0;
   int64_t n_rows = 0;
   std::vector<int32_t> chrom_start, chrom_end, coverage, weight;
+  // count-vector problems (psd_plan_add_counts): no row arrays on the host, the device run-length
+  // encodes `counts`; positions are 0..n_pos and seg_row then holds coordinates, not row numbers
+  bool from_counts = false;
+  int64_t n_pos = 0;
+  std::vector<int32_t> counts;
+  int64_t raw_off = 0;            // offset into the packed device count buffer
   double bases = 0, sum_wz = 0;   // pass-1 totals (src/PeakSegFPOPLog.cpp:187-189)
   double dmin = 0, dmax = 0;      // log(min coverage), log(max coverage)
   int64_t row_off = 0;            // offset into the packed device row arrays
@@ -23,6 +29,11 @@ struct HostProblem {
   std::vector<int> seg_row;       // last row of the previous segment, last segment first (-1 for the first)
   std::vector<double> seg_x;      // log-mean per segment
 };
+
+inline int hp_first_start(const HostProblem& h) { return h.from_counts ? 0 : h.chrom_start[0]; }
+inline int hp_last_end(const HostProblem& h) { return h.from_counts ? (int)h.n_pos : h.chrom_end[h.n_rows - 1]; }
+// chromStart of segment s (segments are stored last first; s < n_segments - 1)
+inline int hp_seg_start(const HostProblem& h, int s) { return h.from_counts ? h.seg_row[s] : h.chrom_end[h.seg_row[s]]; }
 
 struct psd_plan;
 psd_plan* psd_plan_create_impl(int device);

@@ -45,6 +45,19 @@ class Plan:
             raise ValueError(_lib.status_text(-pid, penalty=str(penalty)))
         return pid
 
+    def add_counts(self, counts, penalty):
+        """One problem from a count vector (counts[i] = coverage of base [i, i+1)); the run-length
+        encoding into rows happens on the device at upload (R/PeakSegFPOP_vec.R:18-25 does it in R)."""
+        v = np.asarray(counts)
+        if not np.issubdtype(v.dtype, np.integer):
+            raise ValueError("count.vec must be integer")
+        c, cp = _i32(v)
+        is_inf = 1 if (isinstance(penalty, float) and math.isinf(penalty) and penalty > 0) else 0
+        pid = _lib.lib.psd_plan_add_counts(self._h, len(c), cp, 0.0 if is_inf else float(penalty), is_inf)
+        if pid < 0:
+            raise ValueError(_lib.status_text(-pid, penalty=str(penalty)))
+        return pid
+
     def set_penalty(self, pid, penalty):
         is_inf = 1 if (math.isinf(penalty) and penalty > 0) else 0
         rc = _lib.lib.psd_plan_set_penalty(self._h, pid, 0.0 if is_inf else float(penalty), is_inf)
@@ -108,5 +121,14 @@ def solve_batch(problems, device=-1, stream=0):
     """problems: iterable of (chromStart, chromEnd, coverage, penalty).  Returns (plan, ids)."""
     plan = Plan(device)
     ids = [plan.add(s, e, c, pen) for (s, e, c, pen) in problems]
+    plan.run(stream)
+    return plan, ids
+
+
+def solve_counts_batch(problems, device=-1, stream=0):
+    """problems: iterable of (count_vector, penalty): the in-memory form of PeakSegFPOP_vec for many
+    vectors at once; the vectors are run-length encoded on the device.  Returns (plan, ids)."""
+    plan = Plan(device)
+    ids = [plan.add_counts(v, pen) for (v, pen) in problems]
     plan.run(stream)
     return plan, ids

@@ -444,6 +444,86 @@ def test_reference_style_caller_runs_the_gpu_solver(psd, tmp_path):
     assert os.path.getsize(bg + ".db") > 0      # R reports its size as `megabytes` and deletes it
 
 
+def test_count_vectors_are_run_length_encoded_on_the_device(psd):
+    """psd_plan_add_counts() takes the raw count vector; the device RLE must give
+    exactly the rows R's rle()/cumsum give (R/PeakSegFPOP_vec.R:18-25), so every output equals the
+    row-array solve and the oracle.  Shapes: tile-boundary lengths (a tile is 8,192 positions),
+    runs that span tiles and warps, single positions, constant vectors, mixed with row problems."""
+    from peaksegdisk_b200 import synth
+    rng = np.random.default_rng(77)
+    vecs = []
+    for n in (1, 2, 31, 32, 33, 1023, 1024, 1025, 8191, 8192, 8193, 16384, 20000, 50000):
+        vecs.append(synth.poisson_counts(1000 + n, n))
+    long_runs = np.repeat(rng.integers(0, 4, size=40), rng.integers(1, 3000, size=40)).astype(np.int64)
+    vecs.append(long_runs)                                        # runs crossing several warps / tiles
+    vecs.append(np.concatenate([np.zeros(9000, np.int64), [7], np.zeros(9000, np.int64)]))
+    vecs.append(np.arange(300) % 2)                               # every position is its own run
+    vecs.append(np.full(12345, 3))                                # constant: one-segment model on the host
+    vecs.append(np.array([5]))
+    pens = [float(10 ** rng.uniform(-1, 5)) for _ in vecs]
+    pens[3] = float("inf")
+    plan = psd.Plan(0)
+    ids = []
+    for k, (v, pen) in enumerate(zip(vecs, pens)):
+        ids.append(plan.add_counts(v, pen))
+        if k % 4 == 0:                                            # interleave a row problem: both kinds share one launch
+            s, e, c = synth.poisson_problem(500 + k, 3000)
+            ids.append(("rows", plan.add(s, e, c, 50.0), s, e, c))
+    plan.run()
+    st = plan.stats()
+    assert st["n_rle_launches"] == 4 and st["rle_positions"] > 0
+    k = 0
+    for item in ids:
+        if isinstance(item, tuple):
+            _, pid, s, e, c = item
+            _check_vs_oracle(plan, pid, s, e, c, 50.0)
+            continue
+        v, pen = vecs[k], pens[k]; k += 1
+        s, e, c = synth.rle_rows(v)
+        r = plan.result(item)
+        assert r.status == 0 and r.n_rows == len(c) and r.bases == len(v)
+        if r.trivial:
+            seg = plan.segments(item)
+            assert (int(seg[0][0]), int(seg[1][0]), int(seg[2][0])) == (0, len(v), 0)
+            ref, _ = psd.solve_batch([(s, e, c, pen)])
+            assert plan.loss_row(item) == ref.loss_row(0) and seg[3][0] == ref.segments(0)[3][0]
+        else:
+            _check_vs_oracle(plan, item, s, e, c, pen)
+    # the R-named batched front end reports the same tables
+    out = psd.PeakSegFPOP_vec_batch([vecs[0], vecs[12]], [pens[0], pens[12]])
+    for o, kk in zip(out, (0, 12)):
+        s, e, c = synth.rle_rows(vecs[kk])
+        stt, summ, oseg = oracle_bind.solve_rows(s, e, c, pens[kk])
+        assert int(o["loss"]["peaks"][0]) == int(summ[2]) and float(o["loss"]["total.loss"][0]) == summ[6]
+        assert np.array_equal(o["segments"]["chromStart"].to_numpy(), oseg[0])
+        assert list(o["segments"]["status"]) == [("peak" if i % 2 else "background") for i in range(len(oseg[0]))]
+    with pytest.raises(ValueError):
+        plan.add_counts(np.array([1, -2, 3]), 1.0)
+    with pytest.raises(ValueError):
+        plan.add_counts(np.array([1.5, 2.0]), 1.0)
+
+
+def test_count_vector_batch_full_size_matches_row_batch(psd):
+    """Config-2-sized vectors (1e4..1e5 positions): device-RLE problems and host-RLE row problems
+    give bit-identical loss rows and segments; re-upload and penalty updates work on count problems."""
+    from peaksegdisk_b200 import synth
+    vecs = [synth.poisson_counts(seed) for seed in range(40, 56)]
+    a = psd.Plan(0); b = psd.Plan(0)
+    for v in vecs:
+        for pen in (1e2, 1e4):
+            a.add_counts(v, pen)
+            b.add(*synth.rle_rows(v), pen)
+    a.run(); b.run()
+    for pid in range(len(a)):
+        assert a.loss_row(pid) == b.loss_row(pid)
+        sa, sb = a.segments(pid), b.segments(pid)
+        assert all(np.array_equal(x, y) for x, y in zip(sa[:3], sb[:3])) and np.array_equal(sa[3].view(np.uint64), sb[3].view(np.uint64))
+    assert a.stats()["rle_positions"] == 2 * sum(len(v) for v in vecs)
+    a.set_penalty(0, 1e3); b.set_penalty(0, 1e3)
+    a.run(); b.run()
+    assert a.loss_row(0) == b.loss_row(0) and a.loss_row(1) == b.loss_row(1)
+
+
 def test_differential_fuzz_against_oracle():
     """tools/fuzz_gpu_vs_oracle.py: 150 random problems of six shapes (bursty zeros, huge counts,
     trends with hundreds of pieces, random weights, penalties 0 and 1e-3..1e7) in one launch; every
