@@ -247,19 +247,31 @@ struct psd_plan {
   }
 };
 
+static Options current_options() {
+  Options o;
+  { std::lock_guard<std::mutex> lk(g_opt_mutex); o = g_opt; }
+  // environment overrides (tuning experiments)
+  if (const char* e = getenv("PSD_PIECE_CAP")) o.piece_cap = atoi(e);
+  if (const char* e = getenv("PSD_STORE_GB")) o.store_gb = atof(e);
+  if (const char* e = getenv("PSD_MAX_WARPS")) o.max_warps_per_sm = atoi(e);
+  if (const char* e = getenv("PSD_BLOCKS_PER_SM")) o.blocks_per_sm = std::max(1, atoi(e));
+  if (const char* e = getenv("PSD_SPILL_CAP")) o.spill_cap = std::max(0, atoi(e));
+  if (const char* e = getenv("PSD_HOST_SPILL_GB")) o.host_spill_gb = atof(e);
+  if (const char* e = getenv("PSD_OCCUPANCY_MODE")) o.occupancy_mode = atoi(e);
+  return o;
+}
+
+static bool same_options(const Options& a, const Options& b) {
+  return a.piece_cap == b.piece_cap && a.overflow_cap == b.overflow_cap && a.store_gb == b.store_gb && a.chunk_kb == b.chunk_kb &&
+         a.max_warps_per_sm == b.max_warps_per_sm && a.blocks_per_sm == b.blocks_per_sm && a.spill_cap == b.spill_cap &&
+         a.host_spill_gb == b.host_spill_gb && a.occupancy_mode == b.occupancy_mode;
+}
+
 psd_plan* psd_plan_create_impl(int device) {
   // No CUDA call here: a plan holding only one-segment (trivial) problems never needs the device.
   psd_plan* p = new psd_plan();
   p->device = device;
-  { std::lock_guard<std::mutex> lk(g_opt_mutex); p->opt = g_opt; }
-  // environment overrides (tuning experiments): PSD_PIECE_CAP, PSD_STORE_GB
-  if (const char* e = getenv("PSD_PIECE_CAP")) p->opt.piece_cap = atoi(e);
-  if (const char* e = getenv("PSD_STORE_GB")) p->opt.store_gb = atof(e);
-  if (const char* e = getenv("PSD_MAX_WARPS")) p->opt.max_warps_per_sm = atoi(e);
-  if (const char* e = getenv("PSD_BLOCKS_PER_SM")) p->opt.blocks_per_sm = std::max(1, atoi(e));
-  if (const char* e = getenv("PSD_SPILL_CAP")) p->opt.spill_cap = std::max(0, atoi(e));
-  if (const char* e = getenv("PSD_HOST_SPILL_GB")) p->opt.host_spill_gb = atof(e);
-  if (const char* e = getenv("PSD_OCCUPANCY_MODE")) p->opt.occupancy_mode = atoi(e);
+  p->opt = current_options();
   memset(&p->stats, 0, sizeof p->stats);
   return p;
 }
@@ -277,6 +289,44 @@ static int ensure_device(psd_plan* p) {
   for (auto& e : p->ev) CK(cudaEventCreate(&e));
   p->ev_ok = true;
   return 0;
+}
+
+// ---- one recycled plan for the file entry points ------------------------------------------------------
+// PeakSegFPOP_disk is called once per (file, penalty) by the reference's R code; creating and
+// destroying the device buffers, the pinned staging and the store pool on every call costs 10-50 ms
+// (much more on a box with slow allocation) next to a ~100 ms solve.  The file entry points
+// therefore park their plan here when its footprint is small and take it back on the next call:
+// its buffers are grow-only.  The parked plan is never freed at process exit on purpose (static
+// destructors may run after the CUDA runtime is gone).
+namespace {
+std::mutex g_park_mutex;
+psd_plan* g_parked = nullptr;
+}
+
+psd_plan* psd_plan_acquire_parked() {
+  psd_plan* p = nullptr;
+  { std::lock_guard<std::mutex> lk(g_park_mutex); p = g_parked; g_parked = nullptr; }
+  if (p) {
+    int dev = -1;
+    const bool ok = cudaGetDevice(&dev) == cudaSuccess && dev == p->device && same_options(p->opt, current_options());
+    if (ok) return p;
+    psd_plan_destroy_impl(p);
+  }
+  return psd_plan_create_impl(-1);
+}
+
+void psd_plan_release_parked(psd_plan* p) {
+  if (!p) return;
+  const unsigned long long pinned = (unsigned long long)(p->p_rows_cap * 8 + p->p_raw_cap * 4 + p->p_seg_cap * 12 + p->p_res_cap * sizeof(DpResult));
+  const bool small = p->ev_ok && p->pool_bytes <= (1ull << 30) && pinned <= (256ull << 20) && p->spill_bytes == 0 &&
+                     p->gws_bytes <= (512ull << 20);
+  if (small) {
+    p->probs.clear(); p->gpu_ids.clear(); p->results.clear(); p->seg_row.clear(); p->seg_x.clear();
+    p->uploaded = p->solved = p->packed = false; p->last_mean_intervals = 0;
+    std::lock_guard<std::mutex> lk(g_park_mutex);
+    if (!g_parked) { g_parked = p; return; }
+  }
+  psd_plan_destroy_impl(p);
 }
 
 void psd_plan_destroy_impl(psd_plan* p) { if (p) { if (p->ev_ok) cudaSetDevice(p->device); delete p; } }

@@ -266,7 +266,7 @@ int run_file_batch(int n, const char* const* bedgraphs, const char* const* penal
     FileJob& j = jobs[i];
     if (j.status) continue;
     if (!plan) {
-      plan = psd_plan_create_impl(-1);
+      plan = psd_plan_acquire_parked();
       if (!plan) { fatal = PSD_ERR_CUDA; break; }
     }
     const Parsed& P = *j.parsed;
@@ -310,7 +310,7 @@ int run_file_batch(int n, const char* const* bedgraphs, const char* const* penal
     }
     status_out[i] = j.status;
   });
-  if (plan) psd_plan_destroy_impl(plan);
+  if (plan) { if (fatal) psd_plan_destroy_impl(plan); else psd_plan_release_parked(plan); }
   return fatal;
 }
 

@@ -444,6 +444,40 @@ def test_reference_style_caller_runs_the_gpu_solver(psd, tmp_path):
     assert os.path.getsize(bg + ".db") > 0      # R reports its size as `megabytes` and deletes it
 
 
+def test_concurrent_single_problem_calls_from_host_threads(psd, tmp_path):
+    """SURVEY 8b "Threading": the replacement must be callable concurrently from several host threads
+    (distinct files).  Eight threads call the single-problem entry point repeatedly; every result
+    equals the golden file, and the plan parked between calls is reused without cross-talk."""
+    import ctypes as C, threading
+    g = golden("golden_mono27ac.json")
+    pens = list(g["penalties"])
+    src = open(os.path.join(GOLD, "Mono27ac_coverage.bedGraph")).read()
+    small = [c for c in golden("golden_small.json")][:8]
+    errors = []
+
+    def worker(k):
+        try:
+            path = str(tmp_path / ("t%d.bedGraph" % k))
+            open(path, "w").write(src)
+            for rep in range(3):
+                pen = pens[(k + rep) % len(pens)]
+                st = psd._lib.lib.psd_fpop_disk(path.encode(), pen.encode(), (path + ".db").encode())
+                assert st == 0, st
+                seg, loss = outputs(path, pen)
+                assert loss == g["penalties"][pen]["loss"] and sha(seg) == g["penalties"][pen]["segments_sha256"]
+                case = small[(k + rep) % len(small)]
+                sp = str(tmp_path / ("s%d_%d.bedGraph" % (k, rep)))
+                open(sp, "w").write(case["input"])
+                st = psd._lib.lib.psd_fpop_disk(sp.encode(), case["penalty"].encode(), (sp + ".db").encode())
+                assert st == 0 and outputs(sp, case["penalty"]) == (case["segments"], case["loss"])
+        except Exception as e:   # surfaced in the main thread
+            errors.append((k, repr(e)))
+
+    threads = [threading.Thread(target=worker, args=(k,)) for k in range(8)]
+    [t.start() for t in threads]; [t.join() for t in threads]
+    assert not errors, errors
+
+
 def test_count_vectors_are_run_length_encoded_on_the_device(psd):
     """psd_plan_add_counts() takes the raw count vector; the device RLE must give
     exactly the rows R's rle()/cumsum give (R/PeakSegFPOP_vec.R:18-25), so every output equals the
