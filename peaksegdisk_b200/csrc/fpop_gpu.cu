@@ -195,7 +195,8 @@ struct psd_plan {
   // count-vector problems: raw counts, chromEnd rows, run-length-encoding descriptors
   int *d_raw = nullptr, *d_end = nullptr; size_t d_raw_cap = 0, d_end_cap = 0;
   long long* d_end_off = nullptr;
-  RleVec* d_rle_vecs = nullptr; int *d_tile_vec = nullptr, *d_tile_count = nullptr, *d_rle_nrows = nullptr;
+  RleVec* d_rle_vecs = nullptr; int *d_tile_vec = nullptr, *d_rle_nrows = nullptr;
+  unsigned long long* d_tile_state = nullptr;   // [n_tiles] look-back words, then ticket (4 B) and error flag (4 B)
   size_t d_rle_vec_cap = 0, d_tile_cap = 0;
   int32_t* p_raw = nullptr; size_t p_raw_cap = 0;
   int* p_rle_nrows = nullptr; size_t p_rle_nrows_cap = 0;
@@ -227,7 +228,7 @@ struct psd_plan {
     dfree(d_weight); dfree(d_cov); dfree(d_index); dfree(d_problems); dfree(d_results); dfree(d_order);
     dfree(d_queue); dfree(d_cursors); dfree(d_seg_scratch_off); dfree(d_scratch_row); dfree(d_seg_row);
     dfree(d_scratch_x); dfree(d_seg_x); dfree(d_pool); dfree(d_gws);
-    dfree(d_raw); dfree(d_end); dfree(d_end_off); dfree(d_rle_vecs); dfree(d_tile_vec); dfree(d_tile_count); dfree(d_rle_nrows);
+    dfree(d_raw); dfree(d_end); dfree(d_end_off); dfree(d_rle_vecs); dfree(d_tile_vec); dfree(d_tile_state); dfree(d_rle_nrows);
     d_raw_cap = d_end_cap = d_rle_vec_cap = d_tile_cap = 0;
     d_rows_cap = d_prob_cap = d_seg_cap = 0; pool_bytes = 0; gws_bytes = 0;
     uploaded = false;
@@ -441,16 +442,16 @@ int psd_plan_upload_impl(psd_plan* p, void* stream_v) {
       p->d_rle_vec_cap = rvecs.size();
     }
     if (tile_vec.size() > p->d_tile_cap) {
-      dfree(p->d_tile_vec); dfree(p->d_tile_count); p->d_tile_cap = 0;
+      dfree(p->d_tile_vec); dfree(p->d_tile_state); p->d_tile_cap = 0;
       CK(cudaMalloc(&p->d_tile_vec, sizeof(int) * tile_vec.size()));
-      CK(cudaMalloc(&p->d_tile_count, sizeof(int) * tile_vec.size()));
+      CK(cudaMalloc(&p->d_tile_state, sizeof(unsigned long long) * (tile_vec.size() + 1)));
       p->d_tile_cap = tile_vec.size();
     }
-    if (rvecs.size() > p->p_rle_nrows_cap) {
+    if (rvecs.size() + 1 > p->p_rle_nrows_cap) {   // + the kernel's error flag
       if (p->p_rle_nrows) cudaFreeHost(p->p_rle_nrows);
       p->p_rle_nrows = nullptr; p->p_rle_nrows_cap = 0;
-      CK(cudaMallocHost(&p->p_rle_nrows, sizeof(int) * rvecs.size()));
-      p->p_rle_nrows_cap = rvecs.size();
+      CK(cudaMallocHost(&p->p_rle_nrows, sizeof(int) * (rvecs.size() + 1)));
+      p->p_rle_nrows_cap = rvecs.size() + 1;
     }
   }
   tr.mark("upload: device buffers");
@@ -519,21 +520,21 @@ int psd_plan_upload_impl(psd_plan* p, void* stream_v) {
   CK(cudaMemcpyAsync(p->d_seg_scratch_off, soff.data(), sizeof(unsigned long long) * ng, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(p->d_end_off, eoff.data(), sizeof(long long) * ng, cudaMemcpyHostToDevice, st));
   CK(cudaEventRecord(p->ev[1], st));
-  p->stats.rle_ms = 0; p->stats.rle_bytes_algorithmic = 0; p->stats.rle_positions = 0; p->stats.n_rle_launches = n_counts ? 4 : 0;
+  p->stats.rle_ms = 0; p->stats.rle_bytes_algorithmic = 0; p->stats.rle_positions = 0; p->stats.n_rle_launches = n_counts ? 1 : 0;
   if (n_counts) {
-    // run-length encode on the device (rle_gpu.cuh): 4 launches, all on the plan's stream
+    // run-length encode on the device (rle_gpu.cuh): one single-pass kernel on the plan's stream
     RleParams R;
     R.vecs = p->d_rle_vecs; R.tile_vec = p->d_tile_vec; R.n_tiles = (int)tile_vec.size(); R.n_vecs = (int)rvecs.size();
     R.raw = p->d_raw; R.coverage = p->d_cov; R.chrom_end = p->d_end; R.weight = p->d_weight;
-    R.tile_count = p->d_tile_count; R.n_rows = p->d_rle_nrows;
+    R.tile_state = p->d_tile_state; R.n_rows = p->d_rle_nrows;
+    R.ticket = (unsigned int*)(p->d_tile_state + R.n_tiles); R.error = (int*)(R.ticket + 1);
+    CK(cudaMemsetAsync(p->d_tile_state, 0, sizeof(unsigned long long) * ((size_t)R.n_tiles + 1), st));
     CK(cudaEventRecord(p->ev[5], st));
-    rle_count_kernel<<<R.n_tiles, PSD_RLE_WARPS * 32, 0, st>>>(R);
-    rle_scan_kernel<<<(R.n_vecs + 7) / 8, 256, 0, st>>>(R);
-    rle_scatter_kernel<<<R.n_tiles, PSD_RLE_WARPS * 32, 0, st>>>(R);
-    rle_weight_kernel<<<R.n_tiles, PSD_RLE_WARPS * 32, 0, st>>>(R);
+    rle_encode_kernel<<<R.n_tiles, PSD_RLE_WARPS * 32, 0, st>>>(R);
     CK(cudaGetLastError());
     CK(cudaEventRecord(p->ev[6], st));
     CK(cudaMemcpyAsync(p->p_rle_nrows, p->d_rle_nrows, sizeof(int) * rvecs.size(), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(p->p_rle_nrows + rvecs.size(), R.error, sizeof(int), cudaMemcpyDeviceToHost, st));
   }
   CK(cudaStreamSynchronize(st));   // hp/soff/... are pageable temporaries
   tr.mark("upload: H2D + RLE + sync");
@@ -545,6 +546,7 @@ int psd_plan_upload_impl(psd_plan* p, void* stream_v) {
     cudaEventElapsedTime(&ms, p->ev[5], p->ev[6]);
     p->stats.rle_ms = ms; p->stats.rle_positions = total_pos;
     p->stats.rle_bytes_algorithmic = (int64_t)(4 * total_pos + 12 * (total - plain));
+    if (p->p_rle_nrows[rvecs.size()] != 0) { g_last_error = "device run-length encoding: look-back gave up"; return PSD_ERR_INTERNAL; }
     size_t k = 0;
     for (int id : p->gpu_ids) {
       const HostProblem& h = p->probs[id];

@@ -6,15 +6,18 @@
 // to HBM as they are (4 B per position) and become the DP kernel's (weight, coverage) rows plus a
 // chromEnd array for the backtrack, without the text or row-array detour.
 //
-// HBM-bound integer work, no tensor cores: a position is a "head" when it differs from its
-// predecessor; row index = number of heads before it.  Vectors are cut into tiles of 8,192
-// positions (8 warps x 32 stripes x 32 lanes); a tile never straddles two vectors.
-//   pass 1  rle_count_kernel    heads per tile                               reads 4 B/position
-//   pass 2  rle_scan_kernel     per vector: exclusive scan of its tile counts, n_rows, last chromEnd
-//   pass 3  rle_scatter_kernel  coverage[row], chromEnd[row-1]               reads 4 B/position (L2), writes 8 B/row
-//   pass 4  rle_weight_kernel   weight[row] = chromEnd[row] - chromEnd[row-1]    8 B/row
-// All loads of a warp are 128-byte coalesced stripes; ranks come from ballots, no shared-memory scan
-// beyond the 8 warp totals of a block.  Algorithmic bytes: 4 per position + 12 per row.
+// HBM-bound integer work, no tensor cores.  A position is a "head" when it differs from its
+// predecessor; its row is the number of heads before it; a head at position i closes the previous
+// row: chromEnd[row-1] = i, weight[row-1] = i - (position of the previous head).  ONE kernel, one
+// pass over the counts (single-pass scan with decoupled look-back, per vector):
+//   * vectors are cut into tiles of 8,192 positions (8 warps x 32 stripes x 32 lanes); a tile never
+//     straddles two vectors; blocks take tiles in ticket order (atomic counter), so every
+//     predecessor of a running tile is running or done and the look-back cannot deadlock;
+//   * a warp loads its 32 stripes as 128-byte coalesced requests (all 32 loads in flight), heads
+//     come from shuffles + ballots, ranks from popcounts; the only shared memory is 8 warp totals;
+//   * thread 0 publishes the tile's (head count, last head position) as one 64-bit word, looks back
+//     over the vector's earlier tiles for its exclusive prefix, then publishes the inclusive one.
+// Traffic = algorithmic bytes: 4 B per position read + 12 B per row written.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -24,7 +27,7 @@
 
 struct RleVec {
   long long raw_off;   // first position in the packed count buffer
-  long long row_off;   // first row in the packed row arrays (capacity n_pos rows)
+  long long row_off;   // first row in the packed row arrays
   int n_pos;
   int tile0;           // id of the vector's first tile
 };
@@ -35,20 +38,43 @@ struct RleParams {
   int n_tiles, n_vecs;
   const int* raw;
   int* coverage; int* chrom_end; int* weight;   // indexed by row_off + row
-  int* tile_count;       // heads per tile; exclusive prefix within the vector after pass 2
-  int* n_rows;           // per vector
+  unsigned long long* tile_state;   // zeroed before the launch; see rle_pack()
+  unsigned int* ticket;             // zeroed before the launch
+  int* n_rows;                      // per vector
+  int* error;                       // set to 1 if a look-back ever gave up (never expected)
 };
 
-// Head masks of the 32 stripes a warp owns: stripe s covers positions wbase + 32*s + lane.
-__device__ __forceinline__ int rle_warp_heads(const int* __restrict__ v, int n_pos, int wbase, int lane,
-                                              unsigned (&mask)[PSD_RLE_STRIPES], int (&val)[PSD_RLE_STRIPES]) {
+// tile state word: [63:62] flag (0 empty, 1 aggregate of this tile, 2 inclusive prefix),
+// [61:31] head count, [30:0] last head position + 1 (0 = no head so far)
+__device__ __forceinline__ unsigned long long rle_pack(unsigned flag, unsigned count, unsigned last1) {
+  return ((unsigned long long)flag << 62) | ((unsigned long long)count << 31) | (unsigned long long)last1;
+}
+
+__global__ void __launch_bounds__(PSD_RLE_WARPS * 32) rle_encode_kernel(const RleParams P) {
+  __shared__ int s_tile;
+  __shared__ int s_wtot[PSD_RLE_WARPS];
+  __shared__ int s_wlast[PSD_RLE_WARPS];   // last head position + 1 within the warp's range, 0 = none
+  __shared__ unsigned s_excl_count, s_excl_last1;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) s_tile = (int)atomicAdd(P.ticket, 1u);
+  __syncthreads();
+  const int tile = s_tile;
+  if (tile >= P.n_tiles) return;
+  const int vi = P.tile_vec[tile];
+  const RleVec V = P.vecs[vi];
+  const int* __restrict__ v = P.raw + V.raw_off;
+  const int n_pos = V.n_pos;
+  const int wbase = (tile - V.tile0) * PSD_RLE_TILE + warp * (32 * PSD_RLE_STRIPES);
+
+  // ---- heads of the warp's 32 stripes --------------------------------------------------------------
+  unsigned mask[PSD_RLE_STRIPES]; int val[PSD_RLE_STRIPES];
 #pragma unroll
   for (int s = 0; s < PSD_RLE_STRIPES; s++) {
     const int i = wbase + 32 * s + lane;
-    val[s] = (i < n_pos) ? __ldg(v + i) : 0;
+    val[s] = (i < n_pos) ? __ldcs(v + i) : 0;
   }
-  int carry = (wbase > 0 && wbase < n_pos) ? __ldg(v + wbase - 1) : 0;   // value just before the warp's range
-  int total = 0;
+  int carry = (wbase > 0 && wbase < n_pos) ? __ldg(v + wbase - 1) : 0;   // the value just before the warp's range
+  int total = 0, wlast1 = 0;
 #pragma unroll
   for (int s = 0; s < PSD_RLE_STRIPES; s++) {
     const int i = wbase + 32 * s + lane;
@@ -58,86 +84,67 @@ __device__ __forceinline__ int rle_warp_heads(const int* __restrict__ v, int n_p
     mask[s] = __ballot_sync(0xffffffffu, head);
     carry = __shfl_sync(0xffffffffu, val[s], 31);
     total += __popc(mask[s]);
+    if (mask[s]) wlast1 = wbase + 32 * s + (31 - __clz(mask[s])) + 1;
   }
-  return total;
-}
-
-__global__ void __launch_bounds__(PSD_RLE_WARPS * 32) rle_count_kernel(const RleParams P) {
-  __shared__ int wtot[PSD_RLE_WARPS];
-  const int tile = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int vi = P.tile_vec[tile];
-  const RleVec V = P.vecs[vi];
-  const int wbase = (tile - V.tile0) * PSD_RLE_TILE + warp * (32 * PSD_RLE_STRIPES);
-  unsigned mask[PSD_RLE_STRIPES]; int val[PSD_RLE_STRIPES];
-  const int total = rle_warp_heads(P.raw + V.raw_off, V.n_pos, wbase, lane, mask, val);
-  if (lane == 0) wtot[warp] = total;
+  if (lane == 0) { s_wtot[warp] = total; s_wlast[warp] = wlast1; }
   __syncthreads();
+
+  // ---- tile prefix by decoupled look-back (thread 0) -------------------------------------------------
   if (threadIdx.x == 0) {
-    int t = 0;
+    unsigned t_count = 0, t_last1 = 0;
 #pragma unroll
-    for (int w = 0; w < PSD_RLE_WARPS; w++) t += wtot[w];
-    P.tile_count[tile] = t;
+    for (int w = 0; w < PSD_RLE_WARPS; w++) { t_count += (unsigned)s_wtot[w]; if (s_wlast[w]) t_last1 = (unsigned)s_wlast[w]; }
+    unsigned e_count = 0, e_last1 = 0;
+    if (tile > V.tile0) {
+      atomicExch(P.tile_state + tile, rle_pack(1u, t_count, t_last1));
+      for (int t = tile - 1; t >= V.tile0; t--) {
+        unsigned long long w = 0;
+        long long spins = 0;
+        do {
+          w = atomicAdd(P.tile_state + t, 0ull);
+          if (++spins > (1ll << 22)) { *P.error = 1; break; }
+        } while ((w >> 62) == 0);
+        e_count += (unsigned)((w >> 31) & 0x7fffffffu);
+        if (e_last1 == 0) e_last1 = (unsigned)(w & 0x7fffffffu);
+        if ((w >> 62) != 1) break;   // an inclusive prefix ends the walk
+      }
+    }
+    atomicExch(P.tile_state + tile, rle_pack(2u, e_count + t_count, t_last1 ? t_last1 : e_last1));
+    s_excl_count = e_count; s_excl_last1 = e_last1;
+    const bool last_tile = (tile - V.tile0 + 1) * PSD_RLE_TILE >= n_pos;
+    if (last_tile) {   // the vector's final row ends at n_pos
+      const int n_rows = (int)(e_count + t_count);
+      const int last_head = (int)(t_last1 ? t_last1 : e_last1) - 1;
+      P.n_rows[vi] = n_rows;
+      P.chrom_end[V.row_off + n_rows - 1] = n_pos;
+      P.weight[V.row_off + n_rows - 1] = n_pos - last_head;
+    }
   }
-}
-
-// One warp per vector: exclusive scan of its tile counts (in place), row count, chromEnd of the last row.
-__global__ void rle_scan_kernel(const RleParams P) {
-  const int vi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (vi >= P.n_vecs) return;
-  const RleVec V = P.vecs[vi];
-  const int nt = (V.n_pos + PSD_RLE_TILE - 1) / PSD_RLE_TILE;
-  int running = 0;
-  for (int t0 = 0; t0 < nt; t0 += 32) {
-    const int t = t0 + lane;
-    const int c = (t < nt) ? P.tile_count[V.tile0 + t] : 0;
-    int incl = c;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += o; }
-    if (t < nt) P.tile_count[V.tile0 + t] = running + incl - c;
-    running += __shfl_sync(0xffffffffu, incl, 31);
-  }
-  if (lane == 0) {
-    P.n_rows[vi] = running;
-    if (running > 0) P.chrom_end[V.row_off + running - 1] = V.n_pos;
-  }
-}
-
-__global__ void __launch_bounds__(PSD_RLE_WARPS * 32) rle_scatter_kernel(const RleParams P) {
-  __shared__ int wtot[PSD_RLE_WARPS];
-  const int tile = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int vi = P.tile_vec[tile];
-  const RleVec V = P.vecs[vi];
-  const int wbase = (tile - V.tile0) * PSD_RLE_TILE + warp * (32 * PSD_RLE_STRIPES);
-  unsigned mask[PSD_RLE_STRIPES]; int val[PSD_RLE_STRIPES];
-  const int total = rle_warp_heads(P.raw + V.raw_off, V.n_pos, wbase, lane, mask, val);
-  if (lane == 0) wtot[warp] = total;
   __syncthreads();
-  int rank = P.tile_count[tile];
+
+  // ---- scatter: coverage of this row, chromEnd and weight of the row it closes ---------------------
+  int rank = (int)s_excl_count;
+  int prev1 = (int)s_excl_last1;            // last head position + 1 before the warp's range
 #pragma unroll
-  for (int w = 0; w < PSD_RLE_WARPS; w++) rank += (w < warp) ? wtot[w] : 0;
+  for (int w = 0; w < PSD_RLE_WARPS; w++) {
+    if (w < warp) { rank += s_wtot[w]; if (s_wlast[w]) prev1 = s_wlast[w]; }
+  }
   int* cov = P.coverage + V.row_off;
   int* end = P.chrom_end + V.row_off;
+  int* wgt = P.weight + V.row_off;
   const unsigned lt = (1u << lane) - 1u;
 #pragma unroll
   for (int s = 0; s < PSD_RLE_STRIPES; s++) {
-    if ((mask[s] >> lane) & 1u) {
-      const int row = rank + __popc(mask[s] & lt);
+    const unsigned m = mask[s];
+    if ((m >> lane) & 1u) {
+      const int i = wbase + 32 * s + lane;
+      const unsigned lower = m & lt;
+      const int row = rank + __popc(lower);
+      const int prev_head = lower ? wbase + 32 * s + (31 - __clz(lower)) : prev1 - 1;
       cov[row] = val[s];
-      if (row > 0) end[row - 1] = wbase + 32 * s + lane;   // this run starts where the previous one ends
+      if (row > 0) { end[row - 1] = i; wgt[row - 1] = i - prev_head; }
     }
-    rank += __popc(mask[s]);
+    rank += __popc(m);
+    if (m) prev1 = wbase + 32 * s + (31 - __clz(m)) + 1;
   }
-}
-
-__global__ void __launch_bounds__(PSD_RLE_WARPS * 32) rle_weight_kernel(const RleParams P) {
-  const int tile = blockIdx.x;
-  const int vi = P.tile_vec[tile];
-  const RleVec V = P.vecs[vi];
-  const int n_rows = P.n_rows[vi];
-  const int base = (tile - V.tile0) * PSD_RLE_TILE;
-  if (base >= n_rows) return;
-  const int* end = P.chrom_end + V.row_off;
-  int* w = P.weight + V.row_off;
-  for (int r = base + threadIdx.x; r < base + PSD_RLE_TILE && r < n_rows; r += blockDim.x)
-    w[r] = end[r] - (r ? end[r - 1] : 0);
 }
