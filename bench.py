@@ -267,6 +267,27 @@ def main():
                               "achieved": (st["backtrack_bytes_read"] / (st["backtrack_ms"] / 1e3) / 1e9) if st["backtrack_ms"] > 0 else 0.0,
                               "unit": "GB/s", "note": "latency-bound pointer chase: one dependent record read per segment"},
                 "note": "DP is bound by fp64 issue/latency, not HBM (DESIGN.md); backtrack kernel ms=%.3f" % st["backtrack_ms"]}
+    # secondary kernel, measured outside the timed region: the device run-length encoding of the
+    # count-vector front end (psd_plan_add_counts) on a sample of the same vectors
+    try:
+        from peaksegdisk_b200 import synth
+        plan_c = psd.Plan(local_rank)
+        for seed in list(shard.rank_seeds(rank, args.vectors))[:256]:
+            plan_c.add_counts(synth.poisson_counts(seed, 4000 if args.quick else None).astype("int32"), 1000.0)
+        best = None
+        for _ in range(4):
+            plan_c.upload(stream)
+            sc = plan_c.stats()
+            if best is None or sc["rle_ms"] < best["rle_ms"]:
+                best = sc
+        rle_gbs = best["rle_bytes_algorithmic"] / (best["rle_ms"] / 1e3) / 1e9 if best["rle_ms"] > 0 else 0.0
+        roofline["rle"] = {"kernel": "rle_encode_kernel", "bound": "hbm", "positions": best["rle_positions"],
+                           "algorithmic_bytes_per_launch": best["rle_bytes_algorithmic"], "kernel_ms": best["rle_ms"],
+                           "achieved": rle_gbs, "peak": peak, "unit": "GB/s", "frac": rle_gbs / peak,
+                           "note": "4 B/position read + 12 B/row written; 256 of the vectors, not part of the timed step"}
+        plan_c.close()
+    except Exception as exc:   # the headline numbers do not depend on it
+        roofline["rle"] = {"error": repr(exc)}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": dict(config, problems_per_gpu=len(probs), rows_x_penalties_per_gpu=rows_per_step,

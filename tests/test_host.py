@@ -64,6 +64,38 @@ def test_input_errors_and_trivial_branch_without_gpu(tmp_path, capfd):
     assert n > 25
 
 
+def test_count_vector_front_end_trivial_models_without_gpu():
+    """psd_plan_add_counts (R/PeakSegFPOP_vec.R:18-25): the one-segment models (penalty Inf, constant
+    vector) are closed-form on the host and equal the oracle on the rle() rows; argument errors."""
+    import numpy as np
+    import oracle_bind
+    import peaksegdisk_b200 as psd
+    from peaksegdisk_b200 import synth
+    rng = np.random.default_rng(5)
+    cases = [(rng.poisson(3.0, size=1000), float("inf")), (np.full(77, 4), 10.0), (np.zeros(5, int), 0.0),
+             (np.array([1, 3, 0, 4, 2]), float("inf")), (np.array([9]), 1.0)]
+    plan = psd.Plan()
+    ids = [plan.add_counts(v, pen) for v, pen in cases]
+    plan.run()                       # nothing to send to a device
+    for pid, (v, pen) in zip(ids, cases):
+        s, e, c = synth.rle_rows(v)
+        st, summ, oseg = oracle_bind.solve_rows(s, e, c, pen)
+        got = plan.loss_row(pid)
+        assert st == 0 and (got["segments"], got["peaks"], got["bases"], got["bedGraph.lines"]) == (1, 0, len(v), len(c))
+        assert got["total.loss"] == summ[6] and got["mean.pen.cost"] == summ[5]
+        seg = plan.segments(pid)
+        assert (int(seg[0][0]), int(seg[1][0]), int(seg[2][0])) == (0, len(v), 0) and seg[3][0] == oseg[3][0]
+    assert plan.stats()["n_rle_launches"] == 0
+    with pytest.raises(ValueError):
+        plan.add_counts(np.array([1, -1]), 1.0)
+    with pytest.raises(ValueError):
+        plan.add_counts(np.array([1, 2]), -1.0)
+    with pytest.raises(ValueError):
+        plan.add_counts(np.array([0.5, 2.0]), 1.0)
+    with pytest.raises(ValueError):
+        psd.PeakSegFPOP_vec_batch([np.array([1, 2])], [float("nan")])
+
+
 def test_not_enough_columns_message(tmp_path, capfd):
     from peaksegdisk_b200 import _lib
     path = str(tmp_path / "x.bedGraph")

@@ -13,7 +13,7 @@ nv = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 vecs = [synth.poisson_counts(s % 1024).astype(np.int32) for s in range(nv)]
 peak = 6554.9
 try:
-    peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbps"]
+    peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
 except Exception:
     pass
 plan = psd.Plan(0)
