@@ -133,7 +133,9 @@ int psd_plan_set_penalty(psd_plan *plan, int id, double penalty, int penalty_is_
  * "overflow_cap" (global tier, default 8192), "store_gb" (HBM pool, default 0 = auto),
  * "chunk_kb" (store chunk, default 64), "spill_cap" (per-warp global workspace, default 512),
  * "host_spill_gb" (pinned-host overflow of the store: -1 = automatic, 0 = off),
- * "occupancy_mode" (0 = choose per batch, 1 = one block of 14 warps per SM, 2 = two blocks). */
+ * "occupancy_mode" (0 = choose per batch, 1 = one block of 14 warps per SM, 2 = two blocks),
+ * "devices" (GPUs one psd_fpop_disk_batch call may use: 1 = the current device (default), k = the
+ * first k, <= 0 = all; problems are dealt longest-first, one plan and host thread per GPU). */
 int psd_set_option(const char *name, double value);
 
 int psd_device_count(void);

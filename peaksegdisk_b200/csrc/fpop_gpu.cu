@@ -128,7 +128,7 @@ fpop_backtrack_kernel(const BtKernelParams P) {
 namespace {
 thread_local std::string g_last_error;
 std::mutex g_opt_mutex;
-struct Options { int piece_cap = 48; int overflow_cap = 8192; double store_gb = 0; int chunk_kb = 64; int max_warps_per_sm = 0; int blocks_per_sm = 1; int spill_cap = 512; double host_spill_gb = -1; int occupancy_mode = 0; } g_opt;
+struct Options { int piece_cap = 48; int overflow_cap = 8192; double store_gb = 0; int chunk_kb = 64; int max_warps_per_sm = 0; int blocks_per_sm = 1; int spill_cap = 512; double host_spill_gb = -1; int occupancy_mode = 0; int devices = 1; } g_opt;
 
 bool cuda_ok(cudaError_t e, const char* what) {
   if (e == cudaSuccess) return true;
@@ -167,6 +167,7 @@ int psd_set_option_impl(const char* name, double value) {
   else if (n == "spill_cap") g_opt.spill_cap = std::max(0, (int)value);
   else if (n == "host_spill_gb") g_opt.host_spill_gb = value;
   else if (n == "occupancy_mode") g_opt.occupancy_mode = (int)value;   // 0 auto, 1 one block/SM, 2 two blocks/SM
+  else if (n == "devices") g_opt.devices = (int)value;                 // 1 current device only, k first k GPUs, <= 0 all
   else return PSD_ERR_ARG;
   return 0;
 }
@@ -247,6 +248,12 @@ struct psd_plan {
     if (ev_ok) { for (auto& e : ev) cudaEventDestroy(e); ev_ok = false; }
   }
 };
+
+int psd_option_devices() {
+  if (const char* e = getenv("PSD_DEVICES")) return atoi(e);
+  std::lock_guard<std::mutex> lk(g_opt_mutex);
+  return g_opt.devices;
+}
 
 static Options current_options() {
   Options o;

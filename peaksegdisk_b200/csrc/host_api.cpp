@@ -20,6 +20,7 @@
 #include <stdexcept>
 #include <string>
 #include <thread>
+#include <algorithm>
 #include <atomic>
 #include <vector>
 #include "psd_math.h"
@@ -200,6 +201,7 @@ struct FileJob {
   std::shared_ptr<Parsed> parsed;
   bool loss_created = false, seg_created = false;
   int plan_id = -1;
+  int dev_slot = 0;          // which of the batch's plans (one per GPU in use) owns this problem
 };
 
 // Runs fn(i) for i in [0,n) on up to hardware_concurrency host threads.
@@ -247,7 +249,6 @@ int run_file_batch(int n, const char* const* bedgraphs, const char* const* penal
     j.parsed = it->second;
   }
   parallel_for((int)to_parse.size(), [&](int k) { parse_bedgraph(to_parse_name[k].c_str(), *to_parse[k]); });
-  psd_plan* plan = nullptr;
   int fatal = 0;
   for (int i = 0; i < n; i++) {
     FileJob& j = jobs[i];
@@ -261,12 +262,34 @@ int run_file_batch(int n, const char* const* bedgraphs, const char* const* penal
     j.loss_created = touch(prefix + "_loss.tsv");
     j.seg_created = touch(prefix + "_segments.bed");
   }
-  // build the plan
+  // Multi-GPU inside one call (option "devices" > 1): the problems are independent, so
+  // they are dealt to the GPUs longest-first onto the least loaded one, each GPU gets its own plan
+  // and host thread, and there is no exchange between them.
+  int n_dev = psd_option_devices();
+  if (n_dev != 1) {
+    const int have = psd_device_count_impl();
+    n_dev = (n_dev <= 0 || n_dev > have) ? have : n_dev;
+    if (n_dev < 1) n_dev = 1;
+  }
+  if (n_dev > 1) {
+    std::vector<int> order;
+    for (int i = 0; i < n; i++) if (!jobs[i].status) order.push_back(i);
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return jobs[a].parsed->cov.size() > jobs[b].parsed->cov.size(); });
+    std::vector<double> load(n_dev, 0.0);
+    for (int i : order) {
+      int best = 0;
+      for (int d = 1; d < n_dev; d++) if (load[d] < load[best]) best = d;
+      jobs[i].dev_slot = best; load[best] += (double)jobs[i].parsed->cov.size();
+    }
+  }
+  std::vector<psd_plan*> plans(n_dev, nullptr);
+  // build the plans
   for (int i = 0; i < n; i++) {
     FileJob& j = jobs[i];
     if (j.status) continue;
+    psd_plan*& plan = plans[j.dev_slot];
     if (!plan) {
-      plan = psd_plan_acquire_parked();
+      plan = (n_dev == 1) ? psd_plan_acquire_parked() : psd_plan_create_impl(j.dev_slot);
       if (!plan) { fatal = PSD_ERR_CUDA; break; }
     }
     const Parsed& P = *j.parsed;
@@ -287,16 +310,25 @@ int run_file_batch(int n, const char* const* bedgraphs, const char* const* penal
       if (!ok) { j.status = PSD_ERR_WRITING_COST_FUNCTIONS; psd_plan_problems(plan)[j.plan_id].status = j.status; }
     }
   }
-  if (!fatal && plan) {
-    int rc = psd_plan_run(plan, nullptr);
-    if (rc) fatal = rc;
+  if (!fatal) {
+    if (n_dev == 1) {
+      if (plans[0]) fatal = psd_plan_run(plans[0], nullptr);
+    } else {
+      std::vector<int> rcs(n_dev, 0);
+      std::vector<std::string> errs(n_dev);
+      std::vector<std::thread> pool;
+      for (int d = 0; d < n_dev; d++)
+        if (plans[d]) pool.emplace_back([&, d]() { rcs[d] = psd_plan_run(plans[d], nullptr); if (rcs[d]) errs[d] = psd_get_last_error(); });
+      for (auto& th : pool) th.join();
+      for (int d = 0; d < n_dev; d++) if (rcs[d] && !fatal) { fatal = rcs[d]; psd_set_last_error(errs[d]); }
+    }
   }
   // render and write the result files on all host cores
   parallel_for(n, [&](int i) {
     FileJob& j = jobs[i];
     if (!j.status && fatal) j.status = fatal;
     if (!j.status) {
-      const HostProblem& h = psd_plan_problems(plan)[j.plan_id];
+      const HostProblem& h = psd_plan_problems(plans[j.dev_slot])[j.plan_id];
       if (!h.trivial && h.result_status != 0) j.status = (h.result_status < 0) ? PSD_ERR_INTERNAL : h.result_status;
       else {
         std::string seg_txt, loss_txt;
@@ -310,7 +342,8 @@ int run_file_batch(int n, const char* const* bedgraphs, const char* const* penal
     }
     status_out[i] = j.status;
   });
-  if (plan) { if (fatal) psd_plan_destroy_impl(plan); else psd_plan_release_parked(plan); }
+  for (psd_plan* plan : plans)
+    if (plan) { if (fatal || n_dev > 1) psd_plan_destroy_impl(plan); else psd_plan_release_parked(plan); }
   return fatal;
 }
 

@@ -50,5 +50,6 @@ int psd_plan_solve_impl(psd_plan* p, void* stream);
 int psd_plan_download_impl(psd_plan* p, void* stream);
 int psd_device_count_impl();
 int psd_set_option_impl(const char* name, double value);
+int psd_option_devices();                      // option "devices" / env PSD_DEVICES: GPUs one batched file call may use
 void psd_set_last_error(const std::string& s);
 const std::string& psd_get_last_error();

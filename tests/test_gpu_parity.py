@@ -478,6 +478,33 @@ def test_concurrent_single_problem_calls_from_host_threads(psd, tmp_path):
     assert not errors, errors
 
 
+def test_batched_file_call_spread_over_two_gpus(psd, tmp_path):
+    """SURVEY 8e inside one process: option "devices" deals the problems of one psd_fpop_disk_batch
+    call to several GPUs (one plan + host thread each, no exchange).  Same files as on one GPU."""
+    if psd._lib.lib.psd_device_count() < 2:
+        pytest.skip("needs two GPUs")
+    g = golden("golden_mono27ac.json")
+    pens = list(g["penalties"])
+    path = str(tmp_path / "coverage.bedGraph")
+    open(path, "w").write(open(os.path.join(GOLD, "Mono27ac_coverage.bedGraph")).read())
+    files, ps, want = [path] * len(pens), list(pens), []
+    for k, case in enumerate(c for c in golden("golden_small.json") if c["status"] == 0):
+        sp = str(tmp_path / ("s%d.bedGraph" % k))
+        open(sp, "w").write(case["input"])
+        files.append(sp); ps.append(case["penalty"]); want.append((sp, case))
+    try:
+        psd._lib.lib.psd_set_option(b"devices", 2.0)
+        st = psd.PeakSegFPOP_file_batch(files, ps)
+    finally:
+        psd._lib.lib.psd_set_option(b"devices", 1.0)
+    assert st == [0] * len(files)
+    for pen in pens:
+        seg, loss = outputs(path, pen)
+        assert loss == g["penalties"][pen]["loss"] and sha(seg) == g["penalties"][pen]["segments_sha256"], pen
+    for sp, case in want:
+        assert outputs(sp, case["penalty"]) == (case["segments"], case["loss"]), case["name"]
+
+
 def test_count_vectors_are_run_length_encoded_on_the_device(psd):
     """psd_plan_add_counts() takes the raw count vector; the device RLE must give
     exactly the rows R's rle()/cumsum give (R/PeakSegFPOP_vec.R:18-25), so every output equals the
