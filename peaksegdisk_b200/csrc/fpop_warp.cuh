@@ -405,7 +405,12 @@ PSD_DEVNI int min_mono_op(const WarpWs ws, const PList in, const PList out, doub
 // ---- push_min_pieces (:870-1259) for one overlap interval, one lane --------------------------------
 // Result: nc candidate pieces.  Candidate 0 comes from f if s0 == 0 else from g; candidates
 // alternate sources; split points x1 (and x2).   [s0] | x1 | [!s0] | x2 | [s0]
-struct PairOut { int nc; int s0; double x1, x2; };
+struct PairOut {
+  int nc; int s0; double x1, x2;
+#if defined(PSD_TIMING)
+  int two;   // statistics only: this interval ran the two Newton solves
+#endif
+};
 
 PSD_DEV PairOut pair_rule(const int cap, const PList f, const PList g, int i, int j, double dmin,
                           double* lo_out, double* hi_out) {
@@ -462,6 +467,9 @@ PSD_DEV PairOut pair_rule(const int cap, const PList f, const PList g, int i, in
   // below does not read (exact, the solvers are pure) was measured 10 % SLOWER: it splits the lanes
   // of a Newton round into two differently-predicated regions.
   double rs = PSD_INF, rl = PSD_INF;
+#if defined(PSD_TIMING)
+  o.two = two ? 1 : 0;
+#endif
   if (two) {
     PSD_T0(tn);
     rs = root_left(da, db, dc, lo, 0.0, xo, c1, dl);
@@ -573,6 +581,9 @@ PSD_DEVNI int min_env_op(const WarpWs ws, const PList f, const PList g, const PL
   if (K > 2 * cap) { K = 2 * cap; }
   // 2. crossing rule per interval -> candidate pieces
   int T = 0;
+#if defined(PSD_TIMING) && !defined(PSD_EMU)
+  int stat_jobs = 0, stat_rounds = 0;
+#endif
   for (int base = 0; base < K; base += PSD_G) {
     const int q = base + lane;
     const bool valid = q < K;
@@ -580,6 +591,7 @@ PSD_DEVNI int min_env_op(const WarpWs ws, const PList f, const PList g, const PL
     double lo = 0, hi = 0;
     int i = 0, j = 0;
 #if defined(PSD_TIMING) && !defined(PSD_EMU)
+    o.two = 0;
     if ((threadIdx.x & 15u) == 0) atomicAdd(&psd_dbg[20], 1ull);
     if (valid) atomicAdd(&psd_dbg[21], 1ull);
 #endif
@@ -588,6 +600,12 @@ PSD_DEVNI int min_env_op(const WarpWs ws, const PList f, const PList g, const PL
       i = code & 0xffff; j = code >> 16;
       o = pair_rule(cap, f, g, i, j, dmin, &lo, &hi);
     }
+#if defined(PSD_TIMING) && !defined(PSD_EMU)
+    {   // how many Newton rounds does this call run, and how many would a compacted job list need?
+      const unsigned tw = psd_g_ballot(valid && o.two);
+      stat_jobs += psd_popc(tw); stat_rounds += tw ? 1 : 0;
+    }
+#endif
     int incl = o.nc;
     for (int d = 1; d < PSD_G; d <<= 1) { const int t = psd_g_shfl_up_i(incl, d); if (lane >= d) incl += t; }
     const int off = T + incl - o.nc;
@@ -603,6 +621,16 @@ PSD_DEVNI int min_env_op(const WarpWs ws, const PList f, const PList g, const PL
     T += psd_g_shfl_i(incl, PSD_G - 1);
   }
   psd_g_sync();
+#if defined(PSD_TIMING) && !defined(PSD_EMU)
+  if ((threadIdx.x & 15u) == 0) {
+    atomicAdd(&psd_dbg[22], (unsigned long long)stat_jobs);
+    atomicAdd(&psd_dbg[23], (unsigned long long)stat_rounds);
+    atomicAdd(&psd_dbg[24], 1ull);
+    if (stat_rounds) atomicAdd(&psd_dbg[25], 1ull);
+    atomicAdd(&psd_dbg[26], (unsigned long long)((stat_jobs + PSD_G - 1) / PSD_G));   // rounds a compacted job list needs
+    if (K > PSD_G) atomicAdd(&psd_dbg[27], 1ull);
+  }
+#endif
   PSD_T1(t2, 9);
   PSD_T0(t3);
   if (T > ccap) T = ccap;
