@@ -617,6 +617,7 @@ static int choose_config(psd_plan* p, const std::vector<int>& todo) {
   const double t0 = std::max(longest * lat0, total / (n_sm * thr0));
   const double t1 = std::max(longest * lat1, total / (n_sm * thr1));
   if (p->last_mean_intervals > 9.0) return 0;        // functions too large for the 24-piece tier
+  if (p->last_mean_intervals == 0 && longest > 30000) return 0;   // unknown sizes: functions grow with the row count
   return (t1 < 0.92 * t0 && (int)todo.size() >= 20 * (int)n_sm) ? 1 : 0;
 }
 
