@@ -18,6 +18,7 @@
 #include <cstring>
 #include <chrono>
 #include <mutex>
+#include <queue>
 #include <string>
 #include <vector>
 #include "fpop_warp.cuh"
@@ -220,7 +221,7 @@ struct psd_plan {
   psd_stats stats;
   cudaEvent_t ev[8];
   bool ev_ok = false;
-  struct LaunchCfg { bool ok = false; int blocks = 1, wpb = 0, cap = 0, ccap = 0; size_t smem = 0; } cfg[2];
+  struct LaunchCfg { bool ok = false; int blocks = 1, wpb = 0, cap = 0, ccap = 0; size_t smem = 0; } cfg[3];
   bool configured = false;
   double last_mean_intervals = 0;   // of the previous solve of this plan (0: unknown)
 
@@ -598,27 +599,47 @@ static int configure_kernel(psd_plan* p) {
   if (!p->cfg[0].ok) { g_last_error = "cannot fit the DP kernel's shared memory"; return PSD_ERR_CUDA; }
   rc = configure_one<14, 2>(p, p->cfg[1], p->opt.piece_cap / 2, 2);
   if (rc) return rc;
+  rc = configure_one<20, 1>(p, p->cfg[2], (p->opt.piece_cap * 2) / 3, 1);   // experiment: 96 registers, 20 warps, 32-piece tier
+  if (rc) return rc;
   p->configured = true;
   return 0;
 }
 
-// Picks the launch configuration for one wave.  cfg[0] (one block/SM) unless the batch is clearly
-// throughput-bound: its longest problem, run at the slower per-row latency of cfg[1], must still
-// finish well before the batch as a whole would, and the functions must be small enough for the
-// smaller shared-memory tier (known only from a previous solve of the same plan).
+// Makespan, in rows, of the persistent-warp queue: problems (longest first) go to the slot that frees
+// up first.  This is what the kernel's static first assignment + atomic queue does when every slot
+// advances at the same rows per second.
+static double queue_makespan(const psd_plan* p, const std::vector<int>& todo, size_t slots) {
+  if (todo.size() <= slots) return todo.empty() ? 0.0 : (double)p->probs[p->gpu_ids[todo[0]]].n_rows;
+  std::priority_queue<double, std::vector<double>, std::greater<double>> free_at;
+  for (size_t k = 0; k < slots; k++) free_at.push((double)p->probs[p->gpu_ids[todo[k]]].n_rows);
+  double last = 0;
+  for (size_t k = slots; k < todo.size(); k++) {
+    const double t = free_at.top() + (double)p->probs[p->gpu_ids[todo[k]]].n_rows;
+    free_at.pop(); free_at.push(t);
+  }
+  while (!free_at.empty()) { last = free_at.top(); free_at.pop(); }
+  return last;
+}
+
+// Picks the launch configuration for one wave (todo is sorted longest first).  Measured on B200
+// (profiles/README.md): with twice the warps per SM, cfg[1] moves 1.2x the rows per second per SM,
+// so each of its warps advances at 1.2/2 of a cfg[0] warp's rate.  Both makespans are simulated;
+// cfg[1] must win by 5 %, and the functions must be small enough for its 24-piece shared-memory
+// tier (known from a previous solve of the same plan, else assumed for short problems only).
 static int choose_config(psd_plan* p, const std::vector<int>& todo) {
   if (p->opt.occupancy_mode == 1 || !p->cfg[1].ok) return 0;
   if (p->opt.occupancy_mode == 2) return 1;
-  double total = 0, longest = 0;
-  for (int g : todo) { const double n = (double)p->probs[p->gpu_ids[g]].n_rows; total += n; if (n > longest) longest = n; }
-  const double n_sm = (double)p->prop.multiProcessorCount;
-  const double lat0 = 44e-6, thr0 = 0.32e6;          // config 0: seconds per row of one warp under load; rows/s per SM
-  const double lat1 = 80e-6, thr1 = 0.38e6;          // config 1 (measured on B200, profiles/README.md)
-  const double t0 = std::max(longest * lat0, total / (n_sm * thr0));
-  const double t1 = std::max(longest * lat1, total / (n_sm * thr1));
-  if (p->last_mean_intervals > 9.0) return 0;        // functions too large for the 24-piece tier
+  if (p->opt.occupancy_mode == 3) return p->cfg[2].ok ? 2 : 0;
+  if (todo.empty()) return 0;
+  const double longest = (double)p->probs[p->gpu_ids[todo[0]]].n_rows;
+  if (p->last_mean_intervals > 9.0) return 0;
   if (p->last_mean_intervals == 0 && longest > 30000) return 0;   // unknown sizes: functions grow with the row count
-  return (t1 < 0.92 * t0 && (int)todo.size() >= 20 * (int)n_sm) ? 1 : 0;
+  const size_t n_sm = (size_t)p->prop.multiProcessorCount;
+  const size_t slots0 = n_sm * (size_t)(p->cfg[0].wpb * p->cfg[0].blocks), slots1 = n_sm * (size_t)(p->cfg[1].wpb * p->cfg[1].blocks);
+  if (todo.size() <= slots0) return 0;                            // every problem already has its own warp
+  const double t0 = queue_makespan(p, todo, slots0) * (double)slots0;            // rows / (rows per second per SM), up to a constant
+  const double t1 = queue_makespan(p, todo, slots1) * (double)slots1 / 1.2;
+  return t1 < 0.95 * t0 ? 1 : 0;
 }
 
 // DP + backtrack for every uploaded problem.  Device-only: no host<->device row traffic.
@@ -717,6 +738,7 @@ int psd_plan_solve_impl(psd_plan* p, void* stream_v) {
     CK(cudaMemsetAsync(p->d_cursors + 2, 0, sizeof(unsigned long long), st));
     CK(cudaEventRecord(p->ev[2], st));
     if (which == 1) fpop_dp_kernel<14, 2><<<grid, wpb * 32, smem, st>>>(K);
+    else if (which == 2) fpop_dp_kernel<20, 1><<<grid, wpb * 32, smem, st>>>(K);
     else fpop_dp_kernel<PSD_MAX_WARPS_PER_BLOCK, 1><<<grid, wpb * 32, smem, st>>>(K);
     CK(cudaGetLastError());
     CK(cudaEventRecord(p->ev[3], st));
