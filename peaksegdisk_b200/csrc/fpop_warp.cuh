@@ -113,6 +113,13 @@ __device__ unsigned long long psd_dbg[32];
 //         [3cap,4cap): hi (right end of the piece, log-mean)   [4cap,5cap): back_x (prev_log_mean)
 // ints at byte offset 40*cap: back_i (data_i).  The left end of piece k is hi[k-1] (domain min for k=0).
 struct PList { double* base; int n; };
+// Shared-memory tier: the operators are instantiated a second time with the promise that every list
+// and scratch pointer is a shared-memory address (32-bit LDS/STS instead of generic 64-bit LD/ST).
+#if defined(PSD_EMU) || defined(PSD_NO_SHARED_HINT)
+#define PSD_ASSUME_SHARED(p) do {} while (0)
+#else
+#define PSD_ASSUME_SHARED(p) __builtin_assume(__isShared((const void*)(p)))
+#endif
 #define PL_A(L, i) ((L).base[(i)])
 #define PL_B(L, i) ((L).base[cap + (i)])
 #define PL_C(L, i) ((L).base[2 * cap + (i)])
@@ -270,7 +277,9 @@ PSD_DEV void pl_emit(const WarpWs ws, const PList out, int k, double a, double b
 //     (:327-336); more only needs the cost to fall across the piece (:484-510)
 //   * less stamps back_i, adds the penalty to c and +0.0 to a and b (add(0,0,c), :618-625); more only stamps
 // Output pieces are produced in scan order and, for dir 1, reversed at the end.
+template <bool SH>
 PSD_DEVNI int min_mono_op(const WarpWs ws, const PList in, const PList out, double dmin, int stamp, double cshift, int dir) {
+  if (SH) { PSD_ASSUME_SHARED(in.base); PSD_ASSUME_SHARED(out.base); PSD_ASSUME_SHARED(ws.scratch); PSD_ASSUME_SHARED(ws.flags); }
   const int lane = psd_glane();   // lane within this 16-lane group
   const int cap = ws.cap;
   const int n = in.n;
@@ -534,7 +543,9 @@ PSD_DEV PairOut pair_rule(const int cap, const PList f, const PList g, int i, in
 
 // ---- set_to_min_env_of(f, g) followed by the row rescale -------------------------------------------
 // f is the freshly built min-less/min-more function, g the previous cost function.
+template <bool SH>
 PSD_DEVNI int min_env_op(const WarpWs ws, const PList f, const PList g, const PList out, double dmin, const Rescale rs) {
+  if (SH) { PSD_ASSUME_SHARED(f.base); PSD_ASSUME_SHARED(g.base); PSD_ASSUME_SHARED(out.base); PSD_ASSUME_SHARED(ws.scratch); PSD_ASSUME_SHARED(ws.flags); }
   const int lane = psd_glane();   // lane within this 16-lane group
   const int cap = ws.cap, ccap = ws.ccap;
   int* const ivl = ws_ivl(ws);
@@ -709,7 +720,9 @@ PSD_DEVNI int min_env_op(const WarpWs ws, const PList f, const PList g, const PL
 }
 
 // copy with rescale (rows 0/1 of the DP, src/PeakSegFPOPLog.cpp:297-299, 324-328)
+template <bool SH>
 PSD_DEVNI int copy_rescale_op(const WarpWs ws, const PList in, const PList out, const Rescale rs) {
+  if (SH) { PSD_ASSUME_SHARED(in.base); PSD_ASSUME_SHARED(out.base); }
   const int lane = psd_glane();   // lane within this 16-lane group
   const int cap = ws.cap;
   for (int k = lane; k < in.n; k += PSD_G) {
@@ -804,7 +817,9 @@ PSD_DEV unsigned char* store_ptr(const StorePool& sp, unsigned long long off) {
   return off < hbm ? sp.base + off : sp.host_base + (off - hbm);
 }
 
+template <bool SH>
 PSD_DEV void store_write(const WarpWs ws, unsigned char* rec, int row, const PList up, const PList down) {
+  if (SH) { PSD_ASSUME_SHARED(up.base); PSD_ASSUME_SHARED(down.base); }
   // lanes 0-15 write the up function, lanes 16-31 the down function: one loop, one 128-bit store
   // {hi, back_x} and one 32-bit store {back_i} per piece
   const int lane = psd_lane();
@@ -972,7 +987,8 @@ PSD_DEV void dp_run_queue(const WarpWs& ws_s, const WarpWs& ws_g, const DpQueue&
       } else if (grp == 0 || t >= 2) {
         // min_less(down_{t-1}) on group 0 and min_more(up_{t-1}) on group 1: one converged call
         PSD_T0(ta);
-        tmp.n = min_mono_op(wg, grp ? upP : downP, tmp, dmin, t - 1, penalty / cw_done, grp);
+        tmp.n = in_g ? min_mono_op<false>(wg, grp ? upP : downP, tmp, dmin, t - 1, penalty / cw_done, grp)
+                     : min_mono_op<true>(wg, grp ? upP : downP, tmp, dmin, t - 1, penalty / cw_done, grp);
         PSD_T1(ta, grp);
       }
     }
@@ -984,8 +1000,8 @@ PSD_DEV void dp_run_queue(const WarpWs& ws_s, const WarpWs& ws_g, const DpQueue&
     if (have && t >= 1) {
       const PList prev = grp ? downP : upP;     // previous cost function of my chain
       const PList dst = grp ? downN : upN;
-      if (t == 1) n_out = copy_rescale_op(wg, grp ? downP : tmp, dst, rs);   // :297-299, :324-328
-      else { PSD_T0(tb); n_out = min_env_op(wg, tmp, prev, dst, dmin, rs); PSD_T1(tb, 2 + grp); }
+      if (t == 1) n_out = in_g ? copy_rescale_op<false>(wg, grp ? downP : tmp, dst, rs) : copy_rescale_op<true>(wg, grp ? downP : tmp, dst, rs);   // :297-299, :324-328
+      else { PSD_T0(tb); n_out = in_g ? min_env_op<false>(wg, tmp, prev, dst, dmin, rs) : min_env_op<true>(wg, tmp, prev, dst, dmin, rs); PSD_T1(tb, 2 + grp); }
       psd_syncwarp();   // both chains done; their lists are visible to the whole warp
     }
     psd_block_sync();   // block barrier 2 of 2
@@ -1027,7 +1043,8 @@ PSD_DEV void dp_run_queue(const WarpWs& ws_s, const WarpWs& ws_g, const DpQueue&
           const unsigned long long off = store_alloc(sp, sw, store_record_bytes(upP.n, downP.n));
           if (off == ~0ull) status = PSD_ST_STORE_EXHAUSTED;
           else {
-            store_write(ws, store_ptr(sp, off), t, upP, downP);
+            if (in_g) store_write<false>(ws, store_ptr(sp, off), t, upP, downP);
+            else store_write<true>(ws, store_ptr(sp, off), t, upP, downP);
             if (lane == (t & 31)) my_off = off;
             if ((t & 31) == 31 || t == N - 1) {
               const int r = (t & ~31) + lane;
