@@ -827,6 +827,7 @@ PSD_DEV void store_write(const WarpWs ws, unsigned char* rec, int row, const PLi
   const int grp = lane >> 4, gl = lane & 15;
   if (lane == 0) psd_st_cs_u4((unsigned*)rec, (unsigned)up.n, (unsigned)down.n, (unsigned)row, 0u);
   const PList L = grp ? down : up;
+  if (SH) PSD_ASSUME_SHARED(L.base);
   double* pairs = (double*)(rec + 16) + (grp ? 2 * up.n : 0);
   int* bis = (int*)((double*)(rec + 16) + 2 * (up.n + down.n)) + (grp ? up.n : 0);
   for (int k = gl; k < L.n; k += PSD_G) {
