@@ -6,6 +6,8 @@ the BASELINE.json configurations that are NOT the bench line (config 2 is bench.
   c3  one long problem (default 1e6 rows), a few penalties of a search chain (per-solve latency)
   c5  increasing counts (default N=1e4: cost functions of thousands of pieces, global tier)
   c1x Mono27ac x 1,000 penalties in one batched call (what the plan API is for)
+  c2f 128 config-2 vectors as bedGraph FILES x 5 penalties, one batched file call (text parse and
+      result files included on both sides)
 
 Prints one JSON object; both sides produce the same files and the outputs are compared byte for byte.
 usage: python tools/bench_configs.py [--c3-rows N] [--c5-rows N] [--skip c3,c5]"""
@@ -75,6 +77,15 @@ def main():
             out["c1_mono27ac_one_problem"] = both("c1", [mono], ["10.5"], tmp, 1, 6921)
             pens = [r_paste(p) for p in np.exp(np.linspace(np.log(1.0), np.log(1e6), 1000))]
             out["c1x_mono27ac_1000_penalties"] = both("c1x", [mono] * 1000, pens, tmp, threads, 6921 * 1000)
+        if "c2f" not in skip:
+            # config 2 through FILES: 128 of the count vectors as bedGraph text, 5 penalties each, one batched call
+            files, pens, rows = [], [], 0
+            for seed in range(128):
+                s_, e_, c_ = synth.poisson_problem(seed)
+                f = os.path.join(tmp, "v%d.bedGraph" % seed); synth.write_bedgraph(f, s_, e_, c_)
+                for pen in synth.C2_PENALTIES:
+                    files.append(f); pens.append(r_paste(pen)); rows += len(c_)
+            out["c2_files_128_vectors_x_5_penalties"] = both("c2f", files, pens, tmp, threads, rows)
         if "c3" not in skip:
             n_raw = int(args.c3_rows / 0.75)
             s, e, c = synth.poisson_problem(12345, n_raw)
