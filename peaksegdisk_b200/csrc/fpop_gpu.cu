@@ -140,17 +140,6 @@ bool cuda_ok(cudaError_t e, const char* what) {
 
 template <class T> void dfree(T*& p) { if (p) cudaFree(p); p = nullptr; }
 
-// PSD_TRACE=1: wall-clock stage marks on stderr (where does a small solve's latency go?)
-struct Trace {
-  bool on; std::chrono::steady_clock::time_point t;
-  Trace() : on(getenv("PSD_TRACE") != nullptr), t(std::chrono::steady_clock::now()) {}
-  void mark(const char* what) {
-    if (!on) return;
-    const auto n = std::chrono::steady_clock::now();
-    fprintf(stderr, "[psd trace] %-34s %9.3f ms\n", what, std::chrono::duration<double, std::milli>(n - t).count());
-    t = n;
-  }
-};
 }  // namespace
 
 void psd_set_last_error(const std::string& s) { g_last_error = s; }
@@ -327,8 +316,10 @@ psd_plan* psd_plan_acquire_parked() {
 void psd_plan_release_parked(psd_plan* p) {
   if (!p) return;
   const unsigned long long pinned = (unsigned long long)(p->p_rows_cap * 8 + p->p_raw_cap * 4 + p->p_seg_cap * 12 + p->p_res_cap * sizeof(DpResult));
-  const bool small = p->ev_ok && p->pool_bytes <= (1ull << 30) && pinned <= (256ull << 20) && p->spill_bytes == 0 &&
-                     p->gws_bytes <= (512ull << 20);
+  // freeing a multi-GB store pool and unpinning the staging costs 0.5-0.9 s per call (measured), far
+  // more than keeping them for the next call of the same process; only very large plans are let go
+  const bool small = p->ev_ok && p->pool_bytes <= (32ull << 30) && pinned <= (2ull << 30) && p->spill_bytes == 0 &&
+                     p->gws_bytes <= (2ull << 30);
   if (small) {
     p->probs.clear(); p->gpu_ids.clear(); p->results.clear(); p->seg_row.clear(); p->seg_x.clear();
     p->uploaded = p->solved = p->packed = false; p->last_mean_intervals = 0;
@@ -468,12 +459,8 @@ int psd_plan_upload_impl(psd_plan* p, void* stream_v) {
     CK(cudaMallocHost(&p->p_results, sizeof(DpResult) * ng));
     p->p_res_cap = ng;
   }
-  if ((size_t)(total + ng) > p->p_seg_cap) {
-    if (p->p_seg_row) cudaFreeHost(p->p_seg_row); if (p->p_seg_x) cudaFreeHost(p->p_seg_x);
-    CK(cudaMallocHost(&p->p_seg_row, sizeof(int) * (total + ng)));
-    CK(cudaMallocHost(&p->p_seg_x, sizeof(double) * (total + ng)));
-    p->p_seg_cap = total + ng;
-  }
+  // (the pinned staging of the segments is sized at download, from the number of segments found:
+  // pinning the worst case of one segment per row cost more than the whole D2H copy)
   if (!p->p_cursors) CK(cudaMallocHost(&p->p_cursors, sizeof(unsigned long long) * 4));
   if (!p->p_queue_init) CK(cudaMallocHost(&p->p_queue_init, sizeof(int) * 4));
   tr.mark("upload: pinned result staging");
@@ -846,6 +833,14 @@ int psd_plan_download_impl(psd_plan* p, void* stream_v) {
   p->stats.d2h_bytes = 0; p->stats.d2h_ms = 0;
   if (ng) {
     const unsigned long long ns = p->n_seg_total;
+    if (ns > p->p_seg_cap) {
+      if (p->p_seg_row) cudaFreeHost(p->p_seg_row); if (p->p_seg_x) cudaFreeHost(p->p_seg_x);
+      p->p_seg_row = nullptr; p->p_seg_x = nullptr; p->p_seg_cap = 0;
+      const size_t want = (size_t)(ns + ns / 4 + 1024);
+      CK(cudaMallocHost(&p->p_seg_row, sizeof(int) * want));
+      CK(cudaMallocHost(&p->p_seg_x, sizeof(double) * want));
+      p->p_seg_cap = want;
+    }
     CK(cudaEventRecord(p->ev[5], st));
     if (ns) {
       CK(cudaMemcpyAsync(p->p_seg_row, p->d_seg_row, sizeof(int) * ns, cudaMemcpyDeviceToHost, st));

@@ -232,6 +232,7 @@ bool write_file(const std::string& path, const std::string& text) {
 
 int run_file_batch(int n, const char* const* bedgraphs, const char* const* penalties, const char* const* dbs, int* status_out) {
   std::vector<FileJob> jobs(n);
+  Trace tr;
   // several penalties on one bedGraph parse it once; distinct files are parsed on all host cores
   std::map<std::string, std::shared_ptr<Parsed>> cache;
   std::vector<std::shared_ptr<Parsed>> to_parse;
@@ -249,6 +250,7 @@ int run_file_batch(int n, const char* const* bedgraphs, const char* const* penal
     j.parsed = it->second;
   }
   parallel_for((int)to_parse.size(), [&](int k) { parse_bedgraph(to_parse_name[k].c_str(), *to_parse[k]); });
+  tr.mark("files: parse");
   int fatal = 0;
   for (int i = 0; i < n; i++) {
     FileJob& j = jobs[i];
@@ -282,8 +284,9 @@ int run_file_batch(int n, const char* const* bedgraphs, const char* const* penal
       jobs[i].dev_slot = best; load[best] += (double)jobs[i].parsed->cov.size();
     }
   }
+  tr.mark("files: create outputs");
   std::vector<psd_plan*> plans(n_dev, nullptr);
-  // build the plans
+  // build the plans: slots first (serial, cheap), then rows / pass-1 totals / scratch db on all host cores
   for (int i = 0; i < n; i++) {
     FileJob& j = jobs[i];
     if (j.status) continue;
@@ -293,23 +296,37 @@ int run_file_batch(int n, const char* const* bedgraphs, const char* const* penal
       if (!plan) { fatal = PSD_ERR_CUDA; break; }
     }
     const Parsed& P = *j.parsed;
-    j.plan_id = psd_plan_add(plan, (int64_t)P.cov.size(), P.start.data(), P.end.data(), P.cov.data(), j.penalty, j.is_inf ? 1 : 0);
-    if (j.plan_id < 0) { j.status = -j.plan_id; continue; }
-    const HostProblem& h = psd_plan_problems(plan)[j.plan_id];
-    if (!h.trivial) {
-      // the reference creates its scratch db here; keep that contract (error 7 when unwritable)
-      FILE* d = fopen(j.db.c_str(), "wb");
-      bool ok = d != nullptr;
-      if (ok) {
-        char hdr[64];
-        memset(hdr, 0, sizeof hdr);
-        snprintf(hdr, sizeof hdr, "PSD-B200 cost functions live in HBM; rows=%lld", (long long)h.n_rows);
-        ok = fwrite(hdr, 1, sizeof hdr, d) == sizeof hdr;
-        if (fclose(d) != 0) ok = false;
-      }
-      if (!ok) { j.status = PSD_ERR_WRITING_COST_FUNCTIONS; psd_plan_problems(plan)[j.plan_id].status = j.status; }
-    }
+    if (P.cov.empty() || P.cov.size() > 0x3fffffff) { j.status = PSD_ERR_ARG; continue; }
+    std::vector<HostProblem>& v = psd_plan_problems(plan);
+    j.plan_id = (int)v.size();
+    v.emplace_back();
   }
+  if (!fatal) {
+    parallel_for(n, [&](int i) {
+      FileJob& j = jobs[i];
+      if (j.status || j.plan_id < 0) return;
+      const Parsed& P = *j.parsed;
+      HostProblem& h = psd_plan_problems(plans[j.dev_slot])[j.plan_id];
+      h.n_rows = (int64_t)P.cov.size(); h.penalty = j.penalty; h.penalty_is_inf = j.is_inf;
+      h.chrom_start = P.start; h.chrom_end = P.end; h.coverage = P.cov;
+      finish_problem(h);
+      if (!h.trivial) {
+        // the reference creates its scratch db here; keep that contract (error 7 when unwritable)
+        FILE* d = fopen(j.db.c_str(), "wb");
+        bool ok = d != nullptr;
+        if (ok) {
+          char hdr[64];
+          memset(hdr, 0, sizeof hdr);
+          snprintf(hdr, sizeof hdr, "PSD-B200 cost functions live in HBM; rows=%lld", (long long)h.n_rows);
+          ok = fwrite(hdr, 1, sizeof hdr, d) == sizeof hdr;
+          if (fclose(d) != 0) ok = false;
+        }
+        if (!ok) { j.status = PSD_ERR_WRITING_COST_FUNCTIONS; h.status = j.status; }
+      }
+    });
+    for (psd_plan* plan : plans) if (plan) psd_plan_invalidate(plan);
+  }
+  tr.mark("files: build plan");
   if (!fatal) {
     if (n_dev == 1) {
       if (plans[0]) fatal = psd_plan_run(plans[0], nullptr);
@@ -323,6 +340,7 @@ int run_file_batch(int n, const char* const* bedgraphs, const char* const* penal
       for (int d = 0; d < n_dev; d++) if (rcs[d] && !fatal) { fatal = rcs[d]; psd_set_last_error(errs[d]); }
     }
   }
+  tr.mark("files: upload + solve + download");
   // render and write the result files on all host cores
   parallel_for(n, [&](int i) {
     FileJob& j = jobs[i];
@@ -342,8 +360,10 @@ int run_file_batch(int n, const char* const* bedgraphs, const char* const* penal
     }
     status_out[i] = j.status;
   });
+  tr.mark("files: render + write");
   for (psd_plan* plan : plans)
     if (plan) { if (fatal || n_dev > 1) psd_plan_destroy_impl(plan); else psd_plan_release_parked(plan); }
+  tr.mark("files: park / release the plan");
   return fatal;
 }
 

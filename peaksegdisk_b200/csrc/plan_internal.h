@@ -1,7 +1,10 @@
 // plan_internal.h -- host-side types shared by fpop_gpu.cu (device plan) and host_api.cpp (C ABI,
 // bedGraph text I/O).  Not installed; the public surface is include/peaksegdisk_b200.h.
 #pragma once
+#include <chrono>
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <string>
 #include <vector>
 #include "../../include/peaksegdisk_b200.h"
@@ -34,6 +37,18 @@ inline int hp_first_start(const HostProblem& h) { return h.from_counts ? 0 : h.c
 inline int hp_last_end(const HostProblem& h) { return h.from_counts ? (int)h.n_pos : h.chrom_end[h.n_rows - 1]; }
 // chromStart of segment s (segments are stored last first; s < n_segments - 1)
 inline int hp_seg_start(const HostProblem& h, int s) { return h.from_counts ? h.seg_row[s] : h.chrom_end[h.seg_row[s]]; }
+
+// PSD_TRACE=1: wall-clock stage marks on stderr (where does a small solve's latency go?)
+struct Trace {
+  bool on; std::chrono::steady_clock::time_point t;
+  Trace() : on(getenv("PSD_TRACE") != nullptr), t(std::chrono::steady_clock::now()) {}
+  void mark(const char* what) {
+    if (!on) return;
+    const auto n = std::chrono::steady_clock::now();
+    fprintf(stderr, "[psd trace] %-34s %9.3f ms\n", what, std::chrono::duration<double, std::milli>(n - t).count());
+    t = n;
+  }
+};
 
 struct psd_plan;
 psd_plan* psd_plan_create_impl(int device);
