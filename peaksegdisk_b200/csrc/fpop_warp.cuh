@@ -133,8 +133,7 @@ struct PList { double* base; int n; };
 //   6 piece lists of `cap` pieces: up_{t-1}, down_{t-1}, up_t, down_t, min-less result, min-more result
 //   2 x scratch (one per half-warp group): candidate right ends (ccap doubles), interval codes
 //   (2*cap ints: i_f | i_g << 16), candidate sources (ccap ints: bit 30 = from g | piece index).
-// The handle is passed BY VALUE (`scratch` already points at the calling group's scratch) so the operators can be real (non-inlined)
-// functions: the DP's code footprint has to stay close to the instruction cache (profiles/).
+// The handle is passed BY VALUE (`scratch` already points at the calling group's scratch).
 struct WarpWs { unsigned char* base; unsigned char* scratch; int* flags; int cap; int ccap; };
 #define PSD_WS_HDR 16
 #define PSD_WS_LISTS 6
@@ -165,8 +164,16 @@ extern __shared__ __align__(16) unsigned char psd_smem[];
 PSD_DEV double w_exp(double x) { return psd_exp(x, PSD_ETAB); }
 PSD_DEV double w_log(double x) { return psd_log(x, PSD_LTAB); }
 #else
+#if defined(PSD_INLINE_EXP)
+PSD_DEV double w_exp(double x) { return psd_exp(x, PSD_ETAB); }
+#else
 PSD_DEVNI double w_exp(double x) { return psd_exp(x, PSD_ETAB); }
+#endif
+#if defined(PSD_INLINE_LOG)
+PSD_DEV double w_log(double x) { return psd_log(x, PSD_LTAB); }
+#else
 PSD_DEVNI double w_log(double x) { return psd_log(x, PSD_LTAB); }
+#endif
 #endif
 
 // rescale applied while writing an operator's output:  ((v * mul) + add) * inv  per coefficient,
@@ -193,6 +200,16 @@ PSD_DEV double pc_cost_m(double a, double b, double c, double m, double logm) {
 }
 PSD_DEV double pc_abs(double v) { return v < 0 ? -v : v; }
 
+// The two big operators are inlined into the kernel body, each at its single call site per tier
+// (the executed footprint per phase is unchanged, argument passing through local memory and 320 B of
+// spills go away: +1-2 %).  Real functions mattered only before the phase lock, when the warps of
+// an SM were at unrelated program counters.  -DPSD_NOINLINE_OPS restores them; exp/log stay real
+// functions (inlining those loses 3-4 %: they have ~20 call sites).
+#if defined(PSD_NOINLINE_OPS)
+#define PSD_OP PSD_DEVNI
+#else
+#define PSD_OP PSD_DEV
+#endif
 // The two Newton solvers are inlined into their three call sites (the code per phase stays the same
 // size, the 8-double argument shuffle of a call disappears: +4 % on config 2, +6 % on short
 // problems, profiles/README.md).  -DPSD_NOINLINE_ROOTS keeps them as real functions.
@@ -286,7 +303,7 @@ PSD_DEV void pl_emit(const WarpWs ws, const PList out, int k, double a, double b
 //   * less stamps back_i, adds the penalty to c and +0.0 to a and b (add(0,0,c), :618-625); more only stamps
 // Output pieces are produced in scan order and, for dir 1, reversed at the end.
 template <bool SH>
-PSD_DEVNI int min_mono_op(const WarpWs ws, const PList in, const PList out, double dmin, int stamp, double cshift, int dir) {
+PSD_OP int min_mono_op(const WarpWs ws, const PList in, const PList out, double dmin, int stamp, double cshift, int dir) {
   if (SH) { PSD_ASSUME_SHARED(in.base); PSD_ASSUME_SHARED(out.base); PSD_ASSUME_SHARED(ws.scratch); PSD_ASSUME_SHARED(ws.flags); }
   const int lane = psd_glane();   // lane within this 16-lane group
   const int cap = ws.cap;
@@ -552,7 +569,7 @@ PSD_DEV PairOut pair_rule(const int cap, const PList f, const PList g, int i, in
 // ---- set_to_min_env_of(f, g) followed by the row rescale -------------------------------------------
 // f is the freshly built min-less/min-more function, g the previous cost function.
 template <bool SH>
-PSD_DEVNI int min_env_op(const WarpWs ws, const PList f, const PList g, const PList out, double dmin, const Rescale rs) {
+PSD_OP int min_env_op(const WarpWs ws, const PList f, const PList g, const PList out, double dmin, const Rescale rs) {
   if (SH) { PSD_ASSUME_SHARED(f.base); PSD_ASSUME_SHARED(g.base); PSD_ASSUME_SHARED(out.base); PSD_ASSUME_SHARED(ws.scratch); PSD_ASSUME_SHARED(ws.flags); }
   const int lane = psd_glane();   // lane within this 16-lane group
   const int cap = ws.cap, ccap = ws.ccap;
