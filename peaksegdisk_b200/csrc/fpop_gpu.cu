@@ -210,7 +210,7 @@ struct psd_plan {
   psd_stats stats;
   cudaEvent_t ev[8];
   bool ev_ok = false;
-  struct LaunchCfg { bool ok = false; int blocks = 1, wpb = 0, cap = 0, ccap = 0; size_t smem = 0; } cfg[3];
+  struct LaunchCfg { bool ok = false; int blocks = 1, wpb = 0, cap = 0, ccap = 0; size_t smem = 0; } cfg[2];
   bool configured = false;
   double last_mean_intervals = 0;   // of the previous solve of this plan (0: unknown)
 
@@ -586,8 +586,6 @@ static int configure_kernel(psd_plan* p) {
   if (!p->cfg[0].ok) { g_last_error = "cannot fit the DP kernel's shared memory"; return PSD_ERR_CUDA; }
   rc = configure_one<14, 2>(p, p->cfg[1], p->opt.piece_cap / 2, 2);
   if (rc) return rc;
-  rc = configure_one<20, 1>(p, p->cfg[2], (p->opt.piece_cap * 2) / 3, 1);   // experiment: 96 registers, 20 warps, 32-piece tier
-  if (rc) return rc;
   p->configured = true;
   return 0;
 }
@@ -616,7 +614,6 @@ static double queue_makespan(const psd_plan* p, const std::vector<int>& todo, si
 static int choose_config(psd_plan* p, const std::vector<int>& todo) {
   if (p->opt.occupancy_mode == 1 || !p->cfg[1].ok) return 0;
   if (p->opt.occupancy_mode == 2) return 1;
-  if (p->opt.occupancy_mode == 3) return p->cfg[2].ok ? 2 : 0;
   if (todo.empty()) return 0;
   const double longest = (double)p->probs[p->gpu_ids[todo[0]]].n_rows;
   if (p->last_mean_intervals > 9.0) return 0;
@@ -725,7 +722,6 @@ int psd_plan_solve_impl(psd_plan* p, void* stream_v) {
     CK(cudaMemsetAsync(p->d_cursors + 2, 0, sizeof(unsigned long long), st));
     CK(cudaEventRecord(p->ev[2], st));
     if (which == 1) fpop_dp_kernel<14, 2><<<grid, wpb * 32, smem, st>>>(K);
-    else if (which == 2) fpop_dp_kernel<20, 1><<<grid, wpb * 32, smem, st>>>(K);
     else fpop_dp_kernel<PSD_MAX_WARPS_PER_BLOCK, 1><<<grid, wpb * 32, smem, st>>>(K);
     CK(cudaGetLastError());
     CK(cudaEventRecord(p->ev[3], st));
