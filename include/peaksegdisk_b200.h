@@ -140,6 +140,11 @@ int psd_set_option(const char *name, double value);
 
 int psd_device_count(void);
 
+/* psd_fpop_disk / psd_fpop_disk_batch keep the plan of their last call parked (device buffers, store
+ * pool and pinned staging, up to 32 GB of HBM) so that the next call does not allocate again; this
+ * frees it.  Safe to call at any time from any thread. */
+void psd_release_cache(void);
+
 #ifdef __cplusplus
 }
 #endif

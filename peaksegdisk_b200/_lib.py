@@ -33,7 +33,7 @@ C_ABI_SYMBOLS = [
     "psd_fpop_disk", "psd_fpop_disk_batch", "psd_status_message", "psd_last_error", "psd_plan_create",
     "psd_plan_destroy", "psd_plan_add", "psd_plan_add_counts", "psd_plan_size", "psd_plan_upload", "psd_plan_solve", "psd_plan_download",
     "psd_plan_run", "psd_plan_result", "psd_plan_segments", "psd_plan_get_stats", "psd_plan_set_penalty",
-    "psd_set_option", "psd_device_count",
+    "psd_set_option", "psd_device_count", "psd_release_cache",
     "_Z16PeakSegFPOP_diskPcS_S_",   # the reference's own C++-linkage entry (src/PeakSegFPOPLog.h:15)
 ]
 
@@ -61,6 +61,8 @@ def _load():
     lib.psd_plan_add.argtypes = [C.c_void_p, C.c_int64, i32p, i32p, i32p, C.c_double, C.c_int]
     lib.psd_plan_add_counts.restype = C.c_int
     lib.psd_plan_add_counts.argtypes = [C.c_void_p, C.c_int64, i32p, C.c_double, C.c_int]
+    lib.psd_release_cache.restype = None
+    lib.psd_release_cache.argtypes = []
     lib.psd_plan_size.restype = C.c_int
     lib.psd_plan_size.argtypes = [C.c_void_p]
     for name in ("psd_plan_upload", "psd_plan_solve", "psd_plan_download", "psd_plan_run"):

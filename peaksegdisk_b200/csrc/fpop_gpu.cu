@@ -313,6 +313,13 @@ psd_plan* psd_plan_acquire_parked() {
   return psd_plan_create_impl(-1);
 }
 
+// frees the parked plan (device buffers, store pool, pinned staging), if any
+void psd_plan_drop_parked() {
+  psd_plan* p = nullptr;
+  { std::lock_guard<std::mutex> lk(g_park_mutex); p = g_parked; g_parked = nullptr; }
+  if (p) psd_plan_destroy_impl(p);
+}
+
 void psd_plan_release_parked(psd_plan* p) {
   if (!p) return;
   const unsigned long long pinned = (unsigned long long)(p->p_rows_cap * 8 + p->p_raw_cap * 4 + p->p_seg_cap * 12 + p->p_res_cap * sizeof(DpResult));

@@ -547,6 +547,7 @@ int psd_plan_get_stats(const psd_plan* plan, psd_stats* out) {
 
 int psd_set_option(const char* name, double value) { return name ? psd_set_option_impl(name, value) : PSD_ERR_ARG; }
 int psd_device_count(void) { return psd_device_count_impl(); }
+void psd_release_cache(void) { psd_plan_drop_parked(); }
 
 }  // extern "C"
 

@@ -55,6 +55,7 @@ psd_plan* psd_plan_create_impl(int device);
 void psd_plan_destroy_impl(psd_plan* p);
 psd_plan* psd_plan_acquire_parked();          // file entry points: reuse the previous call's buffers
 void psd_plan_release_parked(psd_plan* p);
+void psd_plan_drop_parked();
 std::vector<HostProblem>& psd_plan_problems(psd_plan* p);
 const std::vector<HostProblem>& psd_plan_problems_c(const psd_plan* p);
 void psd_plan_invalidate(psd_plan* p);

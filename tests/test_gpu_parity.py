@@ -476,6 +476,9 @@ def test_concurrent_single_problem_calls_from_host_threads(psd, tmp_path):
     threads = [threading.Thread(target=worker, args=(k,)) for k in range(8)]
     [t.start() for t in threads]; [t.join() for t in threads]
     assert not errors, errors
+    psd._lib.lib.psd_release_cache()      # drops the parked plan; the next call simply builds a new one
+    worker(99)
+    assert not errors, errors
 
 
 def test_batched_file_call_spread_over_two_gpus(psd, tmp_path):
