@@ -41,7 +41,9 @@ struct DpKernelParams {
   const DpProblem* problems;
   const int* order;           // problem ids, longest first
   int n_order;
-  int* queue;                 // atomic cursor into order
+  int* queue;                 // atomic cursor into order (one per block when bins != null)
+  const int* bins;            // null: one global queue.  Else {begin, end} into order per block: each block works
+                              // through its own share, longest first, and stops refilling when the share is empty
   DpResult* results;
   StorePool pool;
   int cap_s, ccap_s;          // shared-memory tier (cap_s = 0: disabled, warps start in the global tier)
@@ -73,6 +75,11 @@ fpop_dp_kernel(const DpKernelParams P) {
   DpQueue Q;
   Q.problems = P.problems; Q.order = P.order; Q.n_order = P.n_order; Q.cursor = P.queue; Q.results = P.results;
   Q.first_slot = warp * (int)gridDim.x + (int)blockIdx.x;
+  if (P.bins) {
+    Q.first_slot = P.bins[2 * blockIdx.x] + warp;
+    Q.n_order = P.bins[2 * blockIdx.x + 1];
+    Q.cursor = P.queue + blockIdx.x;
+  }
   dp_run_queue(ws_s, ws_g, Q, P.pool);
 #if defined(PSD_TIMING)
   if (threadIdx.x == 0 && blockIdx.x < 160) {   // when did this block run out of work? (ns since kernel start is derived on the host)
@@ -129,7 +136,7 @@ fpop_backtrack_kernel(const BtKernelParams P) {
 namespace {
 thread_local std::string g_last_error;
 std::mutex g_opt_mutex;
-struct Options { int piece_cap = 48; int overflow_cap = 8192; double store_gb = 0; int chunk_kb = 64; int max_warps_per_sm = 0; int blocks_per_sm = 1; int spill_cap = 512; double host_spill_gb = -1; int occupancy_mode = 0; int devices = 1; } g_opt;
+struct Options { int piece_cap = 48; int overflow_cap = 8192; double store_gb = 0; int chunk_kb = 64; int max_warps_per_sm = 0; int blocks_per_sm = 1; int spill_cap = 512; double host_spill_gb = -1; int occupancy_mode = 0; int devices = 1; int queue_mode = 0; } g_opt;
 
 bool cuda_ok(cudaError_t e, const char* what) {
   if (e == cudaSuccess) return true;
@@ -157,6 +164,7 @@ int psd_set_option_impl(const char* name, double value) {
   else if (n == "spill_cap") g_opt.spill_cap = std::max(0, (int)value);
   else if (n == "host_spill_gb") g_opt.host_spill_gb = value;
   else if (n == "occupancy_mode") g_opt.occupancy_mode = (int)value;   // 0 auto, 1 one block/SM, 2 two blocks/SM
+  else if (n == "queue_mode") g_opt.queue_mode = (int)value;           // experiment: 0 one global queue, 1 one share of the batch per block
   else if (n == "devices") g_opt.devices = (int)value;                 // 1 current device only, k first k GPUs, <= 0 all
   else return PSD_ERR_ARG;
   return 0;
@@ -175,7 +183,7 @@ struct psd_plan {
   DpProblem* d_problems = nullptr;
   DpResult* d_results = nullptr;
   int* d_order = nullptr;
-  int* d_queue = nullptr;
+  int* d_queue = nullptr; int* d_bins = nullptr; size_t d_queue_cap = 0;
   unsigned long long* d_cursors = nullptr;     // [0] store chunk cursor, [1] segment cursor
   unsigned long long* d_seg_scratch_off = nullptr;
   int *d_scratch_row = nullptr, *d_seg_row = nullptr;
@@ -217,7 +225,7 @@ struct psd_plan {
   ~psd_plan() { release(); }
   void release_device() {
     dfree(d_weight); dfree(d_cov); dfree(d_index); dfree(d_problems); dfree(d_results); dfree(d_order);
-    dfree(d_queue); dfree(d_cursors); dfree(d_seg_scratch_off); dfree(d_scratch_row); dfree(d_seg_row);
+    dfree(d_queue); dfree(d_bins); d_queue_cap = 0; dfree(d_cursors); dfree(d_seg_scratch_off); dfree(d_scratch_row); dfree(d_seg_row);
     dfree(d_scratch_x); dfree(d_seg_x); dfree(d_pool); dfree(d_gws);
     dfree(d_raw); dfree(d_end); dfree(d_end_off); dfree(d_rle_vecs); dfree(d_tile_vec); dfree(d_tile_state); dfree(d_rle_nrows);
     d_raw_cap = d_end_cap = d_rle_vec_cap = d_tile_cap = 0;
@@ -256,13 +264,14 @@ static Options current_options() {
   if (const char* e = getenv("PSD_SPILL_CAP")) o.spill_cap = std::max(0, atoi(e));
   if (const char* e = getenv("PSD_HOST_SPILL_GB")) o.host_spill_gb = atof(e);
   if (const char* e = getenv("PSD_OCCUPANCY_MODE")) o.occupancy_mode = atoi(e);
+  if (const char* e = getenv("PSD_QUEUE_MODE")) o.queue_mode = atoi(e);
   return o;
 }
 
 static bool same_options(const Options& a, const Options& b) {
   return a.piece_cap == b.piece_cap && a.overflow_cap == b.overflow_cap && a.store_gb == b.store_gb && a.chunk_kb == b.chunk_kb &&
          a.max_warps_per_sm == b.max_warps_per_sm && a.blocks_per_sm == b.blocks_per_sm && a.spill_cap == b.spill_cap &&
-         a.host_spill_gb == b.host_spill_gb && a.occupancy_mode == b.occupancy_mode;
+         a.host_spill_gb == b.host_spill_gb && a.occupancy_mode == b.occupancy_mode && a.queue_mode == b.queue_mode;
 }
 
 psd_plan* psd_plan_create_impl(int device) {
@@ -417,7 +426,6 @@ int psd_plan_upload_impl(psd_plan* p, void* stream_v) {
     CK(cudaMalloc(&p->d_seg_scratch_off, sizeof(unsigned long long) * ng));
     p->d_prob_cap = ng;
   }
-  if (!p->d_queue) CK(cudaMalloc(&p->d_queue, sizeof(int) * 4));
   if (!p->d_cursors) CK(cudaMalloc(&p->d_cursors, sizeof(unsigned long long) * 4));
   if ((size_t)(total + ng) > p->d_seg_cap) {
     dfree(p->d_scratch_row); dfree(p->d_scratch_x); dfree(p->d_seg_row); dfree(p->d_seg_x);
@@ -469,7 +477,7 @@ int psd_plan_upload_impl(psd_plan* p, void* stream_v) {
   // (the pinned staging of the segments is sized at download, from the number of segments found:
   // pinning the worst case of one segment per row cost more than the whole D2H copy)
   if (!p->p_cursors) CK(cudaMallocHost(&p->p_cursors, sizeof(unsigned long long) * 4));
-  if (!p->p_queue_init) CK(cudaMallocHost(&p->p_queue_init, sizeof(int) * 4));
+  if (!p->p_queue_init) CK(cudaMallocHost(&p->p_queue_init, sizeof(int) * 3 * 1024));   // cursors + bins of up to 1024 blocks
   tr.mark("upload: pinned result staging");
   // store pool: sized from free memory unless the option pins it
   size_t free_b = 0, total_b = 0;
@@ -616,15 +624,18 @@ static double queue_makespan(const psd_plan* p, const std::vector<int>& todo, si
 // Picks the launch configuration for one wave (todo is sorted longest first).  Measured on B200
 // (profiles/README.md): with twice the warps per SM, cfg[1] moves 1.2x the rows per second per SM,
 // so each of its warps advances at 1.2/2 of a cfg[0] warp's rate.  Both makespans are simulated;
-// cfg[1] must win by 5 %, and the functions must be small enough for its 24-piece shared-memory
-// tier (known from a previous solve of the same plan, else assumed for short problems only).
+// cfg[1] must win by 5 %, the functions must be small enough for its 24-piece shared-memory tier
+// (when known from a previous solve of the same plan) and the problems must be short.
 static int choose_config(psd_plan* p, const std::vector<int>& todo) {
   if (p->opt.occupancy_mode == 1 || !p->cfg[1].ok) return 0;
   if (p->opt.occupancy_mode == 2) return 1;
   if (todo.empty()) return 0;
   const double longest = (double)p->probs[p->gpu_ids[todo[0]]].n_rows;
   if (p->last_mean_intervals > 9.0) return 0;
-  if (p->last_mean_intervals == 0 && longest > 30000) return 0;   // unknown sizes: functions grow with the row count
+  // Measured (profiles/README.md): the two-block build wins on batches of problems up to ~15 k rows
+  // (+16...+25 %) and loses on 7.5 k-75 k-row problems even when their functions are small and the
+  // long problems get the SM to themselves (-17 %): only short problems qualify.
+  if (longest > 20000) return 0;
   const size_t n_sm = (size_t)p->prop.multiProcessorCount;
   const size_t slots0 = n_sm * (size_t)(p->cfg[0].wpb * p->cfg[0].blocks), slots1 = n_sm * (size_t)(p->cfg[1].wpb * p->cfg[1].blocks);
   if (todo.size() <= slots0) return 0;                            // every problem already has its own warp
@@ -722,9 +733,44 @@ int psd_plan_solve_impl(psd_plan* p, void* stream_v) {
       K.gws = p->d_gws;
     }
     tr.mark("solve: descriptors + workspace");
-    CK(cudaMemcpyAsync(p->d_order, todo.data(), sizeof(int) * n, cudaMemcpyHostToDevice, st));
-    p->p_queue_init[0] = grid * wpb;   // slots below this are assigned statically
-    CK(cudaMemcpyAsync(p->d_queue, p->p_queue_init, sizeof(int), cudaMemcpyHostToDevice, st));
+    if ((size_t)grid > p->d_queue_cap || !p->d_queue) {
+      dfree(p->d_queue); dfree(p->d_bins); p->d_queue_cap = 0;
+      const size_t qn = std::max(4, grid);
+      CK(cudaMalloc(&p->d_queue, sizeof(int) * qn));
+      CK(cudaMalloc(&p->d_bins, sizeof(int) * 2 * qn));
+      p->d_queue_cap = qn;
+    }
+    K.bins = nullptr;
+    std::vector<int> binned;
+    if (!global_tier && p->opt.queue_mode == 1 && grid <= 1024 && n > grid * wpb) {
+      // EXPERIMENT (profiles/README.md): one share of the wave per block, longest-first onto the
+      // least loaded block by rows.  A block that has emptied its share does not refill, so the warps
+      // still working on long problems get the SM to themselves.
+      std::vector<std::vector<int>> bin(grid);
+      std::priority_queue<std::pair<double, int>, std::vector<std::pair<double, int>>, std::greater<std::pair<double, int>>> load;
+      for (int b = 0; b < grid; b++) load.push({0.0, b});
+      for (int g : todo) {
+        auto top = load.top(); load.pop();
+        bin[top.second].push_back(g);
+        load.push({top.first + (double)p->probs[p->gpu_ids[g]].n_rows, top.second});
+      }
+      binned.reserve(n);
+      for (int b = 0; b < grid; b++) {
+        p->p_queue_init[1024 + 2 * b] = (int)binned.size();
+        binned.insert(binned.end(), bin[b].begin(), bin[b].end());
+        p->p_queue_init[1024 + 2 * b + 1] = (int)binned.size();
+        p->p_queue_init[b] = p->p_queue_init[1024 + 2 * b] + wpb;   // the first wpb of a share are taken statically
+      }
+      CK(cudaMemcpyAsync(p->d_order, binned.data(), sizeof(int) * n, cudaMemcpyHostToDevice, st));
+      CK(cudaMemcpyAsync(p->d_queue, p->p_queue_init, sizeof(int) * grid, cudaMemcpyHostToDevice, st));
+      CK(cudaMemcpyAsync(p->d_bins, p->p_queue_init + 1024, sizeof(int) * 2 * grid, cudaMemcpyHostToDevice, st));
+      K.bins = p->d_bins;
+    } else {
+      CK(cudaMemcpyAsync(p->d_order, todo.data(), sizeof(int) * n, cudaMemcpyHostToDevice, st));
+      p->p_queue_init[0] = grid * wpb;   // slots below this are assigned statically
+      CK(cudaMemcpyAsync(p->d_queue, p->p_queue_init, sizeof(int), cudaMemcpyHostToDevice, st));
+    }
+    K.queue = p->d_queue;
     CK(cudaMemsetAsync(p->d_cursors, 0, sizeof(unsigned long long), st));   // recycle the store pool
     CK(cudaMemsetAsync(p->d_cursors + 2, 0, sizeof(unsigned long long), st));
     CK(cudaEventRecord(p->ev[2], st));
