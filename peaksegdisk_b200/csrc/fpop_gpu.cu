@@ -1,15 +1,21 @@
 // fpop_gpu.cu -- sm_100a kernels and the batched plan behind the C ABI (include/peaksegdisk_b200.h).
 //
 // Launch structure (one CUDA stream, no host sync between kernels):
-//   fpop_dp_kernel         persistent warps; each warp pops problems (longest first) from an atomic
-//                          queue and runs dp_problem() (fpop_warp.cuh): the whole DP of one
-//                          (bedGraph x penalty), piece lists in shared memory, cost-function
-//                          records streamed to the HBM chunk pool.
+//   rle_encode_kernel      (upload, count-vector problems only) run-length encodes raw count vectors
+//                          into the DP's rows (rle_gpu.cuh).
+//   fpop_dp_kernel<W,B>    persistent warps; each warp takes problems (longest first) from an atomic
+//                          queue and runs dp_run_queue() (fpop_warp.cuh): the whole DP of one
+//                          (bedGraph x penalty), piece lists in shared memory (moving to a per-warp
+//                          global workspace and back when a row's functions outgrow it), cost-function
+//                          records streamed to the HBM chunk pool.  Two builds: <16,1> one block of
+//                          14 warps per SM (default), <14,2> two blocks (waves of short problems,
+//                          choose_config()).
 //   fpop_backtrack_kernel  one warp per problem: backtrack_problem() walks the stored records,
 //                          then compacts the segments into one array for a single D2H copy.
-// Problems whose functions outgrow the shared-memory tier (status 101) are re-run by the same
-// kernel with per-warp piece lists in global memory; problems that do not fit the store pool
-// (status 102) are re-run in a later wave after the pool is recycled.
+// Problems whose functions outgrow even the per-warp workspace (status 101) are re-run by the same
+// kernel with larger piece lists in global memory; when the store pool is exhausted (status 102)
+// it is grown, then overflows into mapped pinned host memory, and only then are the remaining
+// problems re-run in a later wave after the pool is recycled.
 #include <cuda_runtime.h>
 #include <algorithm>
 #include <cmath>

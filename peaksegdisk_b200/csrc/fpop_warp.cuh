@@ -36,7 +36,8 @@
 // This header is compiled by nvcc for the product and, unmodified, by g++ against
 // tests/emu/warp_emu.h (PSD_EMU) where 32 fibers stand in for the lanes -- a test tool only.
 // Experiment switches (never set in the product build): PSD_TIMING (cycle counters), PSD_SPEC,
-// PSD_RETURN_NUM/DEN, PSD_INLINE_MATH; what they showed is in profiles/README.md.
+// PSD_RETURN_NUM/DEN, PSD_INLINE_MATH / PSD_INLINE_EXP / PSD_INLINE_LOG, PSD_NOINLINE_ROOTS,
+// PSD_NOINLINE_OPS, PSD_NO_SHARED_HINT; what they showed is in profiles/README.md.
 #pragma once
 #include "psd_math.h"
 
