@@ -568,10 +568,16 @@ PSD_DEV PairOut pair_rule(const int cap, const PList f, const PList g, int i, in
 #define PSD_SRC_G 0x40000000
 
 // ---- set_to_min_env_of(f, g) followed by the row rescale -------------------------------------------
-// f is the freshly built min-less/min-more function, g the previous cost function.
+// f is the freshly built min-less/min-more function, g the previous cost function; of / og are the
+// same two lists of the OTHER chain (the call is converged over both half-warps and stage 2 pools
+// the intervals of both chains over all 32 lanes).
 template <bool SH>
-PSD_OP int min_env_op(const WarpWs ws, const PList f, const PList g, const PList out, double dmin, const Rescale rs) {
-  if (SH) { PSD_ASSUME_SHARED(f.base); PSD_ASSUME_SHARED(g.base); PSD_ASSUME_SHARED(out.base); PSD_ASSUME_SHARED(ws.scratch); PSD_ASSUME_SHARED(ws.flags); }
+PSD_OP int min_env_op(const WarpWs ws, const PList f, const PList g, const PList of, const PList og, const PList out,
+                      double dmin, const Rescale rs) {
+  if (SH) {
+    PSD_ASSUME_SHARED(f.base); PSD_ASSUME_SHARED(g.base); PSD_ASSUME_SHARED(of.base); PSD_ASSUME_SHARED(og.base);
+    PSD_ASSUME_SHARED(out.base); PSD_ASSUME_SHARED(ws.scratch); PSD_ASSUME_SHARED(ws.flags);
+  }
   const int lane = psd_glane();   // lane within this 16-lane group
   const int cap = ws.cap, ccap = ws.ccap;
   int* const ivl = ws_ivl(ws);
@@ -612,62 +618,97 @@ PSD_OP int min_env_op(const WarpWs ws, const PList f, const PList g, const PList
       carry_next = psd_g_shfl_i(e + tie, (ng - base < PSD_G) ? ng - base - 1 : PSD_G - 1);
     }
   }
-  psd_g_sync();
+  if (K > 2 * cap) { K = 2 * cap; }
+  psd_syncwarp();   // both chains' interval lists are visible to the whole warp
   PSD_T1(t1, 8);
   PSD_T0(t2);
-  if (K > 2 * cap) { K = 2 * cap; }
-  // 2. crossing rule per interval -> candidate pieces
+  // 2. crossing rule per interval -> candidate pieces.  The intervals of BOTH chains (this call is
+  // converged: lanes 0-15 hold the up chain's arguments, lanes 16-31 the down chain's) are pooled
+  // over the 32 lanes: a chain with 20 intervals next to one with 10 takes one pass, not two, and
+  // the other warps of the block wait at the phase barrier for one pass less (profiles/README.md).
   int T = 0;
+  {
+    const int wl = psd_lane();
+    const int grp = wl >> 4;
+    // the other chain's scratch: same layout, the neighbouring scratch block
+    double* const of_base = of.base;
+    double* const og_base = og.base;
+    const int onf = of.n, ong = og.n, oK = psd_shfl_i(K, wl ^ 16);
+    WarpWs ows = ws;
+    ows.scratch = grp ? ws.scratch - PSD_WS_SCRATCH_BYTES(cap, ccap) : ws.scratch + PSD_WS_SCRATCH_BYTES(cap, ccap);
+    int* const oivl = ws_ivl(ows);
+    double* const ocand_x = ws_cand_x(ows);
+    int* const ocand_s = ws_cand_s(ows);
+    // NOTE: no PSD_ASSUME_SHARED(ows.scratch) here.  With that assumption on the derived pointer nvcc
+    // 12.9 generated code that read the wrong scratch block (every min_env came out with one piece;
+    // the emulator build was fine, bisected on the GPU).  The few cross-chain accesses stay generic.
+    const int K0 = grp ? oK : K, K1 = grp ? K : oK;     // intervals of the up / of the down chain
+    const int total = K0 + K1;
+    int T0 = 0, T1 = 0;
 #if defined(PSD_TIMING) && !defined(PSD_EMU)
-  int stat_jobs = 0, stat_rounds = 0;
+    int stat_jobs = 0, stat_rounds = 0;
 #endif
-  for (int base = 0; base < K; base += PSD_G) {
-    const int q = base + lane;
-    const bool valid = q < K;
-    PairOut o; o.nc = 0; o.s0 = 0; o.x1 = 0; o.x2 = 0;
-    double lo = 0, hi = 0;
-    int i = 0, j = 0;
+    for (int base = 0; base < total; base += 32) {
+      const int q = base + wl;
+      const bool valid = q < total;
+      const int c = (valid && q >= K0) ? 1 : 0;           // which chain this lane works for in this pass
+      const int qi = c ? q - K0 : q;
+      const bool mine = (c == grp);
+      PList F, G;
+      F.base = mine ? f.base : of_base; F.n = mine ? nf : onf;
+      G.base = mine ? g.base : og_base; G.n = mine ? ng : ong;
+      if (SH) { PSD_ASSUME_SHARED(F.base); PSD_ASSUME_SHARED(G.base); }
+      PairOut o; o.nc = 0; o.s0 = 0; o.x1 = 0; o.x2 = 0;
+      double lo = 0, hi = 0;
+      int i = 0, j = 0;
 #if defined(PSD_TIMING) && !defined(PSD_EMU)
-    o.two = 0;
-    if ((threadIdx.x & 15u) == 0) atomicAdd(&psd_dbg[20], 1ull);
-    if (valid) atomicAdd(&psd_dbg[21], 1ull);
+      o.two = 0;
+      if (wl == 0) atomicAdd(&psd_dbg[20], 1ull);
+      if (valid) atomicAdd(&psd_dbg[21], 1ull);
 #endif
-    if (valid) {
-      const int code = ivl[q];
-      i = code & 0xffff; j = code >> 16;
-      o = pair_rule(cap, f, g, i, j, dmin, &lo, &hi);
-    }
+      if (valid) {
+        const int code = (mine ? ivl : oivl)[qi];
+        i = code & 0xffff; j = code >> 16;
+        o = pair_rule(cap, F, G, i, j, dmin, &lo, &hi);
+      }
 #if defined(PSD_TIMING) && !defined(PSD_EMU)
-    {   // how many Newton rounds does this call run, and how many would a compacted job list need?
-      const unsigned tw = psd_g_ballot(valid && o.two);
-      stat_jobs += psd_popc(tw); stat_rounds += tw ? 1 : 0;
+      {
+        const unsigned tw = psd_ballot(valid && o.two);
+        stat_jobs += psd_popc(tw); stat_rounds += tw ? 1 : 0;
+      }
+#endif
+      // exclusive scan of the candidate counts, per chain: both counts ride in one int (<= 96 each)
+      const int mine_nc = valid ? o.nc : 0;
+      int incl = c ? (mine_nc << 16) : mine_nc;
+      for (int d = 1; d < 32; d <<= 1) { const int t = psd_shfl_up_i(incl, d); if (wl >= d) incl += t; }
+      const int tot = psd_shfl_i(incl, 31);
+      const int off = c ? T1 + (incl >> 16) - mine_nc : T0 + (incl & 0xffff) - mine_nc;
+      if (o.nc > 0) {
+        double* const CX = mine ? cand_x : ocand_x;
+        int* const CS = mine ? cand_s : ocand_s;
+        const int sf = i, sg = j | PSD_SRC_G;
+        const int c0 = o.s0 ? sg : sf, c1 = o.s0 ? sf : sg;
+        if (off + o.nc <= ccap) {
+          CS[off] = c0; CX[off] = (o.nc > 1) ? o.x1 : hi;
+          if (o.nc > 1) { CS[off + 1] = c1; CX[off + 1] = (o.nc > 2) ? o.x2 : hi; }
+          if (o.nc > 2) { CS[off + 2] = c0; CX[off + 2] = hi; }
+        } else ws_raise(ws, PSD_FLAG_OVERFLOW);
+      }
+      T0 += tot & 0xffff; T1 += tot >> 16;
+    }
+    T = grp ? T1 : T0;
+#if defined(PSD_TIMING) && !defined(PSD_EMU)
+    if (wl == 0) {
+      atomicAdd(&psd_dbg[22], (unsigned long long)stat_jobs);
+      atomicAdd(&psd_dbg[23], (unsigned long long)stat_rounds);
+      atomicAdd(&psd_dbg[24], 1ull);
+      if (stat_rounds) atomicAdd(&psd_dbg[25], 1ull);
+      atomicAdd(&psd_dbg[26], (unsigned long long)((stat_jobs + 31) / 32));   // rounds a compacted job list needs
+      if (total > 32) atomicAdd(&psd_dbg[27], 1ull);
     }
 #endif
-    int incl = o.nc;
-    for (int d = 1; d < PSD_G; d <<= 1) { const int t = psd_g_shfl_up_i(incl, d); if (lane >= d) incl += t; }
-    const int off = T + incl - o.nc;
-    if (o.nc > 0) {
-      const int sf = i, sg = j | PSD_SRC_G;
-      const int c0 = o.s0 ? sg : sf, c1 = o.s0 ? sf : sg;
-      if (off + o.nc <= ccap) {
-        cand_s[off] = c0; cand_x[off] = (o.nc > 1) ? o.x1 : hi;
-        if (o.nc > 1) { cand_s[off + 1] = c1; cand_x[off + 1] = (o.nc > 2) ? o.x2 : hi; }
-        if (o.nc > 2) { cand_s[off + 2] = c0; cand_x[off + 2] = hi; }
-      } else ws_raise(ws, PSD_FLAG_OVERFLOW);
-    }
-    T += psd_g_shfl_i(incl, PSD_G - 1);
   }
-  psd_g_sync();
-#if defined(PSD_TIMING) && !defined(PSD_EMU)
-  if ((threadIdx.x & 15u) == 0) {
-    atomicAdd(&psd_dbg[22], (unsigned long long)stat_jobs);
-    atomicAdd(&psd_dbg[23], (unsigned long long)stat_rounds);
-    atomicAdd(&psd_dbg[24], 1ull);
-    if (stat_rounds) atomicAdd(&psd_dbg[25], 1ull);
-    atomicAdd(&psd_dbg[26], (unsigned long long)((stat_jobs + PSD_G - 1) / PSD_G));   // rounds a compacted job list needs
-    if (K > PSD_G) atomicAdd(&psd_dbg[27], 1ull);
-  }
-#endif
+  psd_syncwarp();   // every candidate of my chain is in place, whichever half-warp wrote it
   PSD_T1(t2, 9);
   PSD_T0(t3);
   if (T > ccap) T = ccap;
@@ -1028,7 +1069,13 @@ PSD_DEV void dp_run_queue(const WarpWs& ws_s, const WarpWs& ws_g, const DpQueue&
       const PList prev = grp ? downP : upP;     // previous cost function of my chain
       const PList dst = grp ? downN : upN;
       if (t == 1) n_out = in_g ? copy_rescale_op<false>(wg, grp ? downP : tmp, dst, rs) : copy_rescale_op<true>(wg, grp ? downP : tmp, dst, rs);   // :297-299, :324-328
-      else { PSD_T0(tb); n_out = in_g ? min_env_op<false>(wg, tmp, prev, dst, dmin, rs) : min_env_op<true>(wg, tmp, prev, dst, dmin, rs); PSD_T1(tb, 2 + grp); }
+      else {
+        PSD_T0(tb);
+        PList otmp; otmp.base = ws_list(ws, 4 + (grp ^ 1)); otmp.n = psd_shfl_i(tmp.n, lane ^ 16);   // the other chain's lists
+        const PList oprev = grp ? upP : downP;
+        n_out = in_g ? min_env_op<false>(wg, tmp, prev, otmp, oprev, dst, dmin, rs) : min_env_op<true>(wg, tmp, prev, otmp, oprev, dst, dmin, rs);
+        PSD_T1(tb, 2 + grp);
+      }
       psd_syncwarp();   // both chains done; their lists are visible to the whole warp
     }
     psd_block_sync();   // block barrier 2 of 2

@@ -101,6 +101,7 @@ static inline double psd_dbl_(uint64_t u) { double v; memcpy(&v, &u, 8); return 
 #define psd_shfl_u64(v, src) (psd_emu::exchange((uint64_t)(v), (src), PSD_SITE))
 #define psd_shfl_xor_d(v, m) psd_dbl_(psd_emu::exchange(psd_bits_(v), psd_lane() ^ (m), PSD_SITE))
 #define psd_shfl_xor_i(v, m) ((int)(int64_t)psd_emu::exchange((uint64_t)(int64_t)(v), psd_lane() ^ (m), PSD_SITE))
+#define psd_shfl_up_i(v, d) ((int)(int64_t)psd_emu::exchange((uint64_t)(int64_t)(v), (psd_lane() - (d) < 0 ? psd_lane() : psd_lane() - (d)), PSD_SITE))
 #define psd_ballot(p) psd_emu::ballot((p), PSD_SITE)
 #define psd_syncwarp() psd_emu::block(psd_emu::WAIT_FULL, PSD_SITE)
 // 16-lane group collectives; up/down: lanes whose source falls outside the group keep their value
