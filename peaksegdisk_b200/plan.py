@@ -10,6 +10,10 @@ SEGMENT_COLUMNS = ["chrom", "chromStart", "chromEnd", "status", "mean"]     # R/
 
 
 def _i32(a):
+    a = np.asarray(a)
+    if a.dtype != np.int32 and a.size and np.issubdtype(a.dtype, np.integer):
+        if int(a.max()) > 2147483647 or int(a.min()) < -2147483648:   # R integers are 32-bit; do not wrap silently
+            raise ValueError("values do not fit a 32-bit integer")
     a = np.ascontiguousarray(a, dtype=np.int32)
     return a, a.ctypes.data_as(C.POINTER(C.c_int32))
 

@@ -94,6 +94,10 @@ def test_count_vector_front_end_trivial_models_without_gpu():
         plan.add_counts(np.array([0.5, 2.0]), 1.0)
     with pytest.raises(ValueError):
         psd.PeakSegFPOP_vec_batch([np.array([1, 2])], [float("nan")])
+    with pytest.raises(ValueError):
+        plan.add_counts(np.array([1, 2 ** 40]), 1.0)                 # would wrap in int32
+    with pytest.raises(ValueError):
+        plan.add(np.array([0, 1]), np.array([1, 2 ** 33]), np.array([1, 2]), 1.0)
 
 
 def test_not_enough_columns_message(tmp_path, capfd):
