@@ -132,7 +132,13 @@ PSD_HD double psd_log(double x, const uint64_t* __restrict__ T) {
   if (top - 0x0010u > 0x7fdfu) {  // x < 2^-1022, inf or nan
     if (ix * 2 == 0) return -PSD_INF;
     if (ix == 0x7ff0000000000000ULL) return x;
-    if ((top & 0x8000u) || (top & 0x7ff0u) == 0x7ff0u) return PSD_NAN;
+    if ((top & 0x8000u) || (top & 0x7ff0u) == 0x7ff0u) {
+      // glibc: __math_invalid(x) = (x - x) / (x - x).  On x86-64 that is the "real indefinite" NaN
+      // (sign bit set, printed as -nan by the reference's iostream) for negative arguments and the
+      // quieted argument for a NaN argument.
+      if ((ix << 1) > 0xffe0000000000000ULL) return PSD_U2D(ix | 0x0008000000000000ULL);
+      return PSD_U2D(0xfff8000000000000ULL);
+    }
     ix = PSD_D2U(x * PSD_U2D(0x4330000000000000ULL));  // subnormal: scale by 2^52
     ix -= 52ULL << 52;
   }

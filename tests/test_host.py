@@ -100,6 +100,20 @@ def test_count_vector_front_end_trivial_models_without_gpu():
         plan.add(np.array([0, 1]), np.array([1, 2 ** 33]), np.array([1, 2]), 1.0)
 
 
+def test_input_handling_fuzz_against_the_compiled_reference():
+    """Random well- and ill-formed bedGraph text / penalty strings: same status codes and, on every
+    branch that ends before the DP, byte-identical files (including the sign of NaN in degenerate
+    loss lines) as the unmodified reference binary.  tools/fuzz_parse_vs_reference.py, 300 cases."""
+    import subprocess, sys
+    import oracle_bind
+    if not oracle_bind.ref_available():
+        pytest.skip("oracle/_ref/ref_fpop not built")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "fuzz_parse_vs_reference.py"), "300", "11"],
+                         capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout[-2000:]
+    assert " 0 mismatches" in out.stdout
+
+
 def test_not_enough_columns_message(tmp_path, capfd):
     from peaksegdisk_b200 import _lib
     path = str(tmp_path / "x.bedGraph")
