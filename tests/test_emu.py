@@ -77,3 +77,29 @@ def test_spill_tier_overflow_is_reported(ec):
     orc, emu = ec.load()
     st, _, _, _ = ec.run_emu(emu, s, e, c, 1e4, cap=16, spill_cap=64)
     assert st == 101
+
+
+@pytest.mark.timeout(600)
+def test_degenerate_rows_terminate(ec):
+    """The C entry accepts what the reference accepts, including rows R's writeBedGraph would refuse
+    (chromEnd <= chromStart, negative counts: costs become inf / NaN).  The reference's output is
+    then garbage; the device code must still TERMINATE (a hung kernel takes the GPU with it) and
+    report ok / backtrack-lost / internal, never loop.  Same generator as a 54-case sweep that was
+    also run with a per-case watchdog."""
+    import random
+    orc, emu = ec.load()
+    rng = random.Random(3)
+    seen = set()
+    for k in range(24):
+        S, E, Cc, pos = [], [], [], rng.choice([0, 7])
+        for _ in range(rng.choice([2, 3, 5, 9, 20, 60])):
+            w = rng.choice([1, 2, 10, 0, -1, -5]) if rng.random() < 0.3 else rng.choice([1, 2, 10, 300])
+            z = rng.choice([0, 1, 5, 40, -3, -100]) if rng.random() < 0.25 else rng.choice([0, 1, 2, 5, 40])
+            S.append(pos); E.append(pos + w); Cc.append(z); pos += w
+        if len(set(Cc)) < 2:
+            continue
+        st, summ, seg, _ = ec.run_emu(emu, np.array(S, np.int32), np.array(E, np.int32), np.array(Cc, np.int32),
+                                      float(rng.choice([0, 1, 10.5, 1000, 1e6])), cap=48, spill_cap=512)
+        assert st in (0, 101, 103, 104), st
+        seen.add(st)
+    assert 0 in seen
