@@ -639,9 +639,9 @@ static int choose_config(psd_plan* p, const std::vector<int>& todo) {
   const double longest = (double)p->probs[p->gpu_ids[todo[0]]].n_rows;
   if (p->last_mean_intervals > 9.0) return 0;
   // Measured (profiles/README.md): the two-block build wins on batches of problems up to ~15 k rows
-  // (+16...+25 %) and loses on 7.5 k-75 k-row problems even when their functions are small and the
-  // long problems get the SM to themselves (-17 %): only short problems qualify.
-  if (longest > 20000) return 0;
+  // (+16...+25 %), loses 32 % on 30 k-row problems and 17 % on 7.5 k-75 k-row problems even when their
+  // functions are small and the long problems get the SM to themselves: only short problems qualify.
+  if (longest > 16000) return 0;
   const size_t n_sm = (size_t)p->prop.multiProcessorCount;
   const size_t slots0 = n_sm * (size_t)(p->cfg[0].wpb * p->cfg[0].blocks), slots1 = n_sm * (size_t)(p->cfg[1].wpb * p->cfg[1].blocks);
   if (todo.size() <= slots0) return 0;                            // every problem already has its own warp
