@@ -88,6 +88,14 @@ __device__ unsigned long long psd_dbg[32];
 #define PSD_T0(v) do {} while (0)
 #define PSD_T1(v, slot) do {} while (0)
 #endif
+// PSD_EMU_STATS (emulator only, tools/emu_stats.py): histograms of the sizes that decide how many
+// 16- or 32-lane passes an operator takes -- the source of the waiting at the phase barriers
+#if defined(PSD_EMU) && defined(PSD_EMU_STATS)
+extern unsigned long long psd_emu_stats[8][65];
+#define PSD_STAT(slot, leader, v) do { if (leader) { const int v_ = (v); psd_emu_stats[slot][v_ < 0 ? 0 : (v_ > 64 ? 64 : v_)]++; } } while (0)
+#else
+#define PSD_STAT(slot, leader, v) do {} while (0)
+#endif
 // While a flat stretch is open the pieces ahead are tested speculatively, PSD_SPEC lanes per round
 #ifndef PSD_SPEC
 #define PSD_SPEC 16
@@ -313,6 +321,8 @@ PSD_OP int min_mono_op(const WarpWs ws, const PList in, const PList out, double 
   double edge = dir ? PL_X(in, n - 1) : dmin;         // where the next output piece starts (scan order)
   double arg_at = PSD_INF;                            // where the flat piece's minimum is attained
   int out_n = 0;
+  int stat_windows = 0;
+  PSD_STAT(0, lane == 0, n);
   for (int base = 0; base < n; base += PSD_G) {
     const int u = base + lane;                        // scan position
     const bool valid = u < n;
@@ -388,6 +398,7 @@ PSD_OP int min_mono_op(const WarpWs ws, const PList in, const PList out, double 
         }
         pos = first + 1;
       } else {
+        stat_windows++;
         int flag = 0;
         double r = PSD_INF;   // no root: fails the interval test below
         if (valid && u >= pos && u < pos + PSD_SPEC) {
@@ -420,6 +431,7 @@ PSD_OP int min_mono_op(const WarpWs ws, const PList in, const PList out, double 
     if (lane == 0) pl_emit(ws, out, out_n, dir ? 0.0 : 0.0 + 0.0, dir ? 0.0 : 0.0 + 0.0, dir ? level : level + cshift, dir ? edge : PL_X(in, n - 1), arg_at, stamp);
     out_n++;
   }
+  PSD_STAT(1, lane == 0, stat_windows);
   psd_g_sync();
   if (dir && out_n <= cap) {   // pieces were produced right to left
     for (int k = lane; k < (out_n >> 1); k += PSD_G) {
@@ -442,8 +454,9 @@ PSD_OP int min_mono_op(const WarpWs ws, const PList in, const PList out, double 
 // alternate sources; split points x1 (and x2).   [s0] | x1 | [!s0] | x2 | [s0]
 struct PairOut {
   int nc; int s0; double x1, x2;
-#if defined(PSD_TIMING)
+#if defined(PSD_TIMING) || defined(PSD_EMU_STATS)
   int two;   // statistics only: this interval ran the two Newton solves
+  int heavy; // statistics only: this interval needed more than loads and comparisons
 #endif
 };
 
@@ -451,6 +464,9 @@ PSD_DEV PairOut pair_rule(const int cap, const PList f, const PList g, int i, in
                           double* lo_out, double* hi_out) {
   PSD_T0(q0);
   PairOut o; o.nc = 1; o.s0 = 0; o.x1 = 0; o.x2 = 0;
+#if defined(PSD_TIMING) || defined(PSD_EMU_STATS)
+  o.two = 0; o.heavy = 0;
+#endif
   const double pa = PL_A(f, i), pb = PL_B(f, i), pcst = PL_C(f, i);
   const double qa = PL_A(g, j), qb = PL_B(g, j), qcst = PL_C(g, j);
   const double plo = (i == 0) ? dmin : PL_X(f, i - 1), phi = PL_X(f, i);
@@ -476,6 +492,9 @@ PSD_DEV PairOut pair_rule(const int cap, const PList f, const PList g, int i, in
   PSD_T0(q1);
   if (lo == hi) { o.nc = 0; return o; }
   if (same_coefs(pa, pb, pcst, qa, qb, qcst)) { o.s0 = 0; return o; }
+#if defined(PSD_TIMING) || defined(PSD_EMU_STATS)
+  o.heavy = 1;
+#endif
   const double da = pa - qa, db = pb - qb, dc = pcst - qcst;
   const double ehi = w_exp(hi), elo = w_exp(lo);
   const double mid_m = (ehi + elo) / 2;
@@ -502,7 +521,7 @@ PSD_DEV PairOut pair_rule(const int cap, const PList f, const PList g, int i, in
   // below does not read (exact, the solvers are pure) was measured 10 % SLOWER: it splits the lanes
   // of a Newton round into two differently-predicated regions.
   double rs = PSD_INF, rl = PSD_INF;
-#if defined(PSD_TIMING)
+#if defined(PSD_TIMING) || defined(PSD_EMU_STATS)
   o.two = two ? 1 : 0;
 #endif
   if (two) {
@@ -619,6 +638,8 @@ PSD_OP int min_env_op(const WarpWs ws, const PList f, const PList g, const PList
     }
   }
   if (K > 2 * cap) { K = 2 * cap; }
+  PSD_STAT(2, lane == 0, ng);
+  PSD_STAT(3, lane == 0, K);
   psd_syncwarp();   // both chains' interval lists are visible to the whole warp
   PSD_T1(t1, 8);
   PSD_T0(t2);
@@ -644,9 +665,13 @@ PSD_OP int min_env_op(const WarpWs ws, const PList f, const PList g, const PList
     // the emulator build was fine, bisected on the GPU).  The few cross-chain accesses stay generic.
     const int K0 = grp ? oK : K, K1 = grp ? K : oK;     // intervals of the up / of the down chain
     const int total = K0 + K1;
+    PSD_STAT(4, wl == 0, total);
     int T0 = 0, T1 = 0;
 #if defined(PSD_TIMING) && !defined(PSD_EMU)
     int stat_jobs = 0, stat_rounds = 0;
+#endif
+#if defined(PSD_EMU_STATS)
+    int stat_heavy = 0, stat_two = 0;
 #endif
     for (int base = 0; base < total; base += 32) {
       const int q = base + wl;
@@ -661,6 +686,9 @@ PSD_OP int min_env_op(const WarpWs ws, const PList f, const PList g, const PList
       PairOut o; o.nc = 0; o.s0 = 0; o.x1 = 0; o.x2 = 0;
       double lo = 0, hi = 0;
       int i = 0, j = 0;
+#if defined(PSD_EMU_STATS)
+      o.two = 0; o.heavy = 0;
+#endif
 #if defined(PSD_TIMING) && !defined(PSD_EMU)
       o.two = 0;
       if (wl == 0) atomicAdd(&psd_dbg[20], 1ull);
@@ -676,6 +704,9 @@ PSD_OP int min_env_op(const WarpWs ws, const PList f, const PList g, const PList
         const unsigned tw = psd_ballot(valid && o.two);
         stat_jobs += psd_popc(tw); stat_rounds += tw ? 1 : 0;
       }
+#endif
+#if defined(PSD_EMU_STATS)
+      stat_heavy += psd_popc(psd_ballot(valid && o.heavy)); stat_two += psd_popc(psd_ballot(valid && o.two));
 #endif
       // exclusive scan of the candidate counts, per chain: both counts ride in one int (<= 96 each)
       const int mine_nc = valid ? o.nc : 0;
@@ -697,6 +728,10 @@ PSD_OP int min_env_op(const WarpWs ws, const PList f, const PList g, const PList
       T0 += tot & 0xffff; T1 += tot >> 16;
     }
     T = grp ? T1 : T0;
+#if defined(PSD_EMU_STATS)
+    PSD_STAT(6, wl == 0, stat_heavy);
+    PSD_STAT(7, wl == 0, stat_two);
+#endif
 #if defined(PSD_TIMING) && !defined(PSD_EMU)
     if (wl == 0) {
       atomicAdd(&psd_dbg[22], (unsigned long long)stat_jobs);
@@ -712,6 +747,7 @@ PSD_OP int min_env_op(const WarpWs ws, const PList f, const PList g, const PList
   PSD_T1(t2, 9);
   PSD_T0(t3);
   if (T > ccap) T = ccap;
+  PSD_STAT(5, lane == 0, T);
   // 3. push_piece: merge each candidate into the current run when it equals the run's head
   int out_n = 0;
   bool carry_ok = false;

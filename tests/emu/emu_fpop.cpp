@@ -24,7 +24,17 @@ void lane_main(void* arg) {
 }
 }  // namespace
 
+#if defined(PSD_EMU_STATS)
+unsigned long long psd_emu_stats[8][65];
+#endif
+
 extern "C" {
+#if defined(PSD_EMU_STATS)
+void emu_stats_read(int slot, unsigned long long* out65, int reset) {
+  for (int i = 0; i < 65; i++) { out65[i] = psd_emu_stats[slot][i]; if (reset) psd_emu_stats[slot][i] = 0; }
+}
+#endif
+
 
 // Same outputs as oracle_fpop_rows (non-trivial problems only).  cap = list capacity to emulate.
 // Returns the DpResult status (0 ok, 101 piece overflow, ...).
