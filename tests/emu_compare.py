@@ -10,7 +10,7 @@ EMU_TRACE = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.
 
 def load():
     orc = C.CDLL(os.path.join(ROOT, "oracle/_build/liboracle_fpop.so"))
-    emu = C.CDLL(os.path.join(ROOT, "tests/_build/libpsd_emu.so"))
+    emu = C.CDLL(os.environ.get("PSD_EMU_LIB") or os.path.join(ROOT, "tests/_build/libpsd_emu.so"))
     orc.oracle_fpop_rows.restype = C.c_int
     emu.emu_fpop_rows.restype = C.c_int
     return orc, emu
