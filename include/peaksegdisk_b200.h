@@ -103,6 +103,8 @@ typedef struct psd_stats {
 psd_plan *psd_plan_create(int device);
 void psd_plan_destroy(psd_plan *plan);
 /* Adds one problem; rows are copied.  penalty_is_inf != 0 selects the no-peaks model.
+ * Rows must be contiguous (chromStart[i] == chromEnd[i-1], else -6 like the file path,
+ * src/PeakSegFPOPLog.cpp:180-186), of positive width and non-negative coverage (else -PSD_ERR_ARG).
  * Returns the problem id (>= 0) or a negative PSD_ERR_*. */
 int psd_plan_add(psd_plan *plan, int64_t n_rows, const int32_t *chromStart, const int32_t *chromEnd,
                  const int32_t *coverage, double penalty, int penalty_is_inf);

@@ -157,8 +157,21 @@ def PeakSegFPOP_file_batch(bedGraph_files, pen_strs, db_files=None):
 
 
 def _read_loss(path):
-    df = pd.read_csv(path, sep="\t", header=None, names=col_name_list["loss"])
-    return df
+    """One _loss.tsv line.  The %.20g doubles are parsed with Python's float() (correctly rounded;
+    pandas' default parser is not): the sequential search derives its next 15-digit penalty string
+    from total.loss differences, where one ulp can change the string."""
+    with open(path) as f:
+        lines = [ln for ln in f.read().split("\n") if ln != ""]
+    names = col_name_list["loss"]
+    int_cols = {"segments", "peaks", "bases", "bedGraph.lines", "equality.constraints"}
+    cols = {n: [] for n in names}
+    for ln in lines:
+        fields = ln.split("\t")
+        if len(fields) != len(names):
+            raise ValueError("%s: expected %d tab-separated fields, found %d" % (path, len(names), len(fields)))
+        for n, v in zip(names, fields):
+            cols[n].append(int(v) if n in int_cols else _as_numeric(v))
+    return pd.DataFrame(cols, columns=names)
 
 
 def _read_segments(path):
@@ -180,7 +193,8 @@ def _first_last_line(path):
 def _already_computed(cov, seg_bed, loss_tsv, timing_tsv):
     """The cache test of R/PeakSegFPOP_dir.R:70-93."""
     try:
-        timing = pd.read_csv(timing_tsv, sep="\t", header=None, names=["penalty", "megabytes", "seconds"])
+        timing = pd.read_csv(timing_tsv, sep="\t", header=None, names=["penalty", "megabytes", "seconds"],
+                             float_precision="round_trip")
         loss = _read_loss(loss_tsv)
         fs, ls = _first_last_line(seg_bed)
         fc, lc = _first_last_line(cov)

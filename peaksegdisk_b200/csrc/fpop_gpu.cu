@@ -477,6 +477,7 @@ int psd_plan_upload_impl(psd_plan* p, void* stream_v) {
   tr.mark("upload: device buffers");
   if (ng > p->p_res_cap) {
     if (p->p_results) cudaFreeHost(p->p_results);
+    p->p_results = nullptr; p->p_res_cap = 0;
     CK(cudaMallocHost(&p->p_results, sizeof(DpResult) * ng));
     p->p_res_cap = ng;
   }
@@ -514,12 +515,15 @@ int psd_plan_upload_impl(psd_plan* p, void* stream_v) {
   std::vector<DpProblem> hp(ng);
   std::vector<unsigned long long> soff(ng);
   std::vector<long long> eoff(ng);
+  // backtrack scratch: n_rows + 1 entries per problem, handed out in gpu_ids order (independent of
+  // the row_off order, which puts count-vector problems after row problems)
+  unsigned long long scratch_cursor = 0;
   for (size_t g = 0; g < ng; g++) {
     const HostProblem& h = p->probs[p->gpu_ids[g]];
     hp[g].weight = p->d_weight + h.row_off; hp[g].coverage = p->d_cov + h.row_off;
     hp[g].n_rows = (int)h.n_rows; hp[g].penalty = h.penalty; hp[g].dmin = h.dmin; hp[g].dmax = h.dmax;
     hp[g].index = p->d_index + h.row_off;
-    soff[g] = (unsigned long long)h.row_off + g;
+    soff[g] = scratch_cursor; scratch_cursor += (unsigned long long)h.n_rows + 1ull;
     eoff[g] = h.from_counts ? (long long)h.row_off : -1;
   }
   CK(cudaEventRecord(p->ev[0], st));

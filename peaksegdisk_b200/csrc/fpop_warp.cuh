@@ -37,7 +37,7 @@
 // tests/emu/warp_emu.h (PSD_EMU) where 32 fibers stand in for the lanes -- a test tool only.
 // Experiment switches (never set in the product build): PSD_TIMING (cycle counters), PSD_SPEC,
 // PSD_RETURN_NUM/DEN, PSD_INLINE_MATH / PSD_INLINE_EXP / PSD_INLINE_LOG, PSD_NOINLINE_ROOTS,
-// PSD_NOINLINE_OPS, PSD_NO_SHARED_HINT, PSD_DEFER_NEWTON (emulator-verified, not yet run on a GPU);
+// PSD_NOINLINE_OPS, PSD_NO_SHARED_HINT;
 // what they showed is in profiles/README.md.
 #pragma once
 #include "psd_math.h"
@@ -587,157 +587,14 @@ PSD_DEV PairOut pair_rule(const int cap, const PList f, const PList g, int i, in
 
 #define PSD_SRC_G 0x40000000
 
-#if defined(PSD_DEFER_NEWTON)
-// ---- EXPERIMENT (off in the product build; emulator-verified only, see profiles/README.md) ----------
-// pair_rule split at the has_two_roots decision.  pair_pre() finishes every interval that does not
-// need the two Newton solves and otherwise returns the state the solves and the rule's tail need (a
-// "job"); pair_post() runs the solves and the tail.  min_env_op then runs ONE compacted Newton round
-// per call instead of one per 32-interval pass.
-#define PSD_JOB_DOUBLES 14
-#define PSD_CAND_VOID (-1)
-struct PairJob { double da, db, dc, lo, hi, xo, m, c1, c2, dl, dr, elo, dmid; int flags; };   // flags: eq_left | eq_right << 1 | by_mid << 2
-
-PSD_DEV bool pair_pre(const int cap, const PList f, const PList g, int i, int j, double dmin, double* hi_out, PairOut* op, PairJob* job) {
-  PairOut o; o.nc = 1; o.s0 = 0; o.x1 = 0; o.x2 = 0;
-#if defined(PSD_TIMING) || defined(PSD_EMU_STATS)
-  o.two = 0; o.heavy = 0;
-#endif
-  const double pa = PL_A(f, i), pb = PL_B(f, i), pcst = PL_C(f, i);
-  const double qa = PL_A(g, j), qb = PL_B(g, j), qcst = PL_C(g, j);
-  const double plo = (i == 0) ? dmin : PL_X(f, i - 1), phi = PL_X(f, i);
-  const double qlo = (j == 0) ? dmin : PL_X(g, j - 1), qhi = PL_X(g, j);
-  bool eq_left, eq_right;
-  double lo, hi;
-  if (plo < qlo) { eq_left = same_coefs(PL_A(g, j - 1), PL_B(g, j - 1), PL_C(g, j - 1), pa, pb, pcst); lo = qlo; }
-  else {
-    lo = plo;
-    if (qlo < plo) eq_left = same_coefs(PL_A(f, i - 1), PL_B(f, i - 1), PL_C(f, i - 1), qa, qb, qcst);
-    else eq_left = (i == 0 || j == 0) ? false
-                   : same_coefs(PL_A(f, i - 1), PL_B(f, i - 1), PL_C(f, i - 1), PL_A(g, j - 1), PL_B(g, j - 1), PL_C(g, j - 1));
-  }
-  if (phi < qhi) { eq_right = same_coefs(PL_A(f, i + 1), PL_B(f, i + 1), PL_C(f, i + 1), qa, qb, qcst); hi = phi; }
-  else {
-    hi = qhi;
-    if (qhi < phi) eq_right = same_coefs(pa, pb, pcst, PL_A(g, j + 1), PL_B(g, j + 1), PL_C(g, j + 1));
-    else eq_right = (i + 1 == f.n || j + 1 == g.n) ? false
-                    : same_coefs(PL_A(f, i + 1), PL_B(f, i + 1), PL_C(f, i + 1), PL_A(g, j + 1), PL_B(g, j + 1), PL_C(g, j + 1));
-  }
-  *hi_out = hi;
-  if (lo == hi) { o.nc = 0; *op = o; return false; }
-  if (same_coefs(pa, pb, pcst, qa, qb, qcst)) { o.s0 = 0; *op = o; return false; }
-  const double da = pa - qa, db = pb - qb, dc = pcst - qcst;
-  const double ehi = w_exp(hi), elo = w_exp(lo);
-  const double mid_m = (ehi + elo) / 2;
-  const double dmid = pc_cost(da, db, dc, w_log(mid_m));
-  const int by_mid = (dmid < 0) ? 0 : 1;
-  if (eq_left && eq_right) { o.s0 = by_mid; *op = o; return false; }
-  if (db == 0) {
-    if (da == 0) { o.s0 = (dc < 0) ? 0 : 1; *op = o; return false; }
-    if (dc == 0) { o.s0 = (da < 0) ? 0 : 1; *op = o; return false; }
-    const double x = w_log(-dc / da);
-    if (lo < x && x < hi) { o.nc = 2; o.x1 = x; o.s0 = (0 < da) ? 0 : 1; *op = o; return false; }
-    o.s0 = by_mid; *op = o; return false;
-  }
-  const double dl = pc_cost_e(da, db, dc, lo, elo), dr = pc_cost_e(da, db, dc, hi, ehi);
-  const double m = -db / da;
-  const double xo = w_log(m);
-  const double c1 = pc_cost(da, db, dc, xo);
-  const double c2 = pc_cost_m(da, db, dc, m, xo);
-  const bool two = two_roots(da, c1, c2, 0.0);
-  if (!two) {   // the rule's tail without roots (:536-582 of pair_rule with two == false)
-    if (eq_right || eq_left) o.s0 = by_mid;
-    else { const double v = (pc_abs(dmid) < PSD_EPS) ? dr : dmid; o.s0 = (v < 0) ? 0 : 1; }
-    *op = o; return false;
-  }
-  job->da = da; job->db = db; job->dc = dc; job->lo = lo; job->hi = hi; job->xo = xo; job->m = m; job->c1 = c1; job->c2 = c2;
-  job->dl = dl; job->dr = dr; job->elo = elo; job->dmid = dmid;
-  job->flags = (eq_left ? 1 : 0) | (eq_right ? 2 : 0) | (by_mid ? 4 : 0);
-  *op = o;
-  return true;
-}
-
-// the two Newton solves and the rule's tail for an interval whose difference has two roots
-PSD_DEV PairOut pair_post(const PairJob jb) {
-  PairOut o; o.nc = 1; o.s0 = 0; o.x1 = 0; o.x2 = 0;
-#if defined(PSD_TIMING) || defined(PSD_EMU_STATS)
-  o.two = 1; o.heavy = 1;
-#endif
-  const double da = jb.da, db = jb.db, dc = jb.dc, lo = jb.lo, hi = jb.hi, xo = jb.xo, m = jb.m, dl = jb.dl, dr = jb.dr, elo = jb.elo;
-  const bool eq_left = (jb.flags & 1) != 0, eq_right = (jb.flags & 2) != 0;
-  const double rs = root_left(da, db, dc, lo, 0.0, xo, jb.c1, dl);
-  const double rl = root_right(da, db, dc, hi, 0.0, m, jb.c2, dr);
-  if (eq_right) {
-    if (lo < rs && rs < xo && xo < hi) { o.nc = 2; o.x1 = rs; o.s0 = (dl < 0) ? 0 : 1; return o; }
-    const bool f_low_at_zero = 0 < db;
-    if (rs < lo) o.s0 = f_low_at_zero ? 1 : 0;
-    else o.s0 = f_low_at_zero ? 0 : 1;
-    return o;
-  }
-  if (eq_left) {
-    if (lo < xo && xo < rl && rl < hi) { o.nc = 2; o.x1 = rl; o.s0 = (dr < 0) ? 1 : 0; return o; }
-    o.s0 = (jb.flags & 4) ? 1 : 0; return o;
-  }
-  double x1 = PSD_INF, x2 = PSD_INF;
-  {
-    const bool l_in = lo < rl && rl < hi;
-    const bool s_in = lo < rs && 0 < w_exp(rs) && rs < hi;
-    if (l_in) { if (s_in && rs < rl) { x1 = rs; x2 = rl; } else x1 = rl; }
-    else if (s_in) x1 = rs;
-  }
-  if (x2 != PSD_INF) {
-    bool f_first;
-    if (x2 - x1 < x1 - lo) {
-      const double bm = (elo + w_exp(x1)) / 2;
-      f_first = pc_cost(da, db, dc, w_log(bm)) < 0;
-    } else {
-      f_first = !(pc_cost(da, db, dc, (x1 + x2) / 2) < 0);
-    }
-    o.nc = 3; o.x1 = x1; o.x2 = x2; o.s0 = f_first ? 0 : 1;
-  } else if (x1 != PSD_INF) {
-    const double bm = (elo + w_exp(x1)) / 2;
-    const double before = pc_cost(da, db, dc, w_log(bm));
-    const double after = pc_cost(da, db, dc, (hi + x1) / 2);
-    if (before < 0) {
-      if (after < 0) o.s0 = 0;
-      else { o.nc = 2; o.x1 = x1; o.s0 = 0; }
-    } else {
-      if (after < 0) { o.nc = 2; o.x1 = x1; o.s0 = 1; }
-      else o.s0 = 1;
-    }
-  } else {
-    const double v = (pc_abs(jb.dmid) < PSD_EPS) ? dr : jb.dmid;
-    o.s0 = (v < 0) ? 0 : 1;
-  }
-  return o;
-}
-
-// the three candidate slots of interval qi (unused ones are void); compacted after the Newton round
-PSD_DEV void pair_write_slots(int* CS, double* CX, int qi, const PairOut o, int i, int j, double hi) {
-  const int sf = i, sg = j | PSD_SRC_G;
-  const int c0 = o.s0 ? sg : sf, c1 = o.s0 ? sf : sg;
-  CS[3 * qi] = (o.nc > 0) ? c0 : PSD_CAND_VOID;     CX[3 * qi] = (o.nc > 1) ? o.x1 : hi;
-  CS[3 * qi + 1] = (o.nc > 1) ? c1 : PSD_CAND_VOID; CX[3 * qi + 1] = (o.nc > 2) ? o.x2 : hi;
-  CS[3 * qi + 2] = (o.nc > 2) ? c0 : PSD_CAND_VOID; CX[3 * qi + 2] = hi;
-}
-#endif
 
 // ---- set_to_min_env_of(f, g) followed by the row rescale -------------------------------------------
 // f is the freshly built min-less/min-more function, g the previous cost function; of / og are the
 // same two lists of the OTHER chain (the call is converged over both half-warps and stage 2 pools
 // the intervals of both chains over all 32 lanes).
-#if defined(PSD_DEFER_NEWTON)
-#define PSD_DEFER_PARAM , const PList oout   /* the other chain's output list: job records live in both output lists */
-#define PSD_DEFER_ARG(x) , x
-#else
-#define PSD_DEFER_PARAM
-#define PSD_DEFER_ARG(x)
-#endif
 template <bool SH>
-PSD_OP int min_env_op(const WarpWs ws, const PList f, const PList g, const PList of, const PList og, const PList out PSD_DEFER_PARAM,
+PSD_OP int min_env_op(const WarpWs ws, const PList f, const PList g, const PList of, const PList og, const PList out,
                       double dmin, const Rescale rs) {
-#if defined(PSD_DEFER_NEWTON)
-  if (SH) PSD_ASSUME_SHARED(oout.base);
-#endif
   if (SH) {
     PSD_ASSUME_SHARED(f.base); PSD_ASSUME_SHARED(g.base); PSD_ASSUME_SHARED(of.base); PSD_ASSUME_SHARED(og.base);
     PSD_ASSUME_SHARED(out.base); PSD_ASSUME_SHARED(ws.scratch); PSD_ASSUME_SHARED(ws.flags);
@@ -812,101 +669,13 @@ PSD_OP int min_env_op(const WarpWs ws, const PList f, const PList g, const PList
     const int total = K0 + K1;
     PSD_STAT(4, wl == 0, total);
     int T0 = 0, T1 = 0;
-#if defined(PSD_DEFER_NEWTON)
-    // job records: PSD_JOB_DOUBLES doubles each, in the two output lists (not written before stage 3)
-    const int per_buf = (44 * cap) / (8 * PSD_JOB_DOUBLES);
-    const bool defer = 3 * K0 <= ccap && 3 * K1 <= ccap && per_buf >= 16;
-    if (defer) {
-      double* const jbuf0 = grp ? oout.base : out.base;   // chain 0's output list, chain 1's
-      double* const jbuf1 = grp ? out.base : oout.base;
-      if (SH) { PSD_ASSUME_SHARED(jbuf0); PSD_ASSUME_SHARED(jbuf1); }
-      const int job_cap = 2 * per_buf;
-      const unsigned ltm = (wl == 0) ? 0u : (0xffffffffu >> (32 - wl));
-      int n_jobs = 0;
-      for (int base = 0;; base += 32) {
-        const bool more = base < total;
-        const int q = base + wl;
-        const bool valid = more && q < total;
-        const int c = (valid && q >= K0) ? 1 : 0;
-        const int qi = c ? q - K0 : q;
-        const bool mine = (c == grp);
-        PList F, G;
-        F.base = mine ? f.base : of_base; F.n = mine ? nf : onf;
-        G.base = mine ? g.base : og_base; G.n = mine ? ng : ong;
-        if (SH) { PSD_ASSUME_SHARED(F.base); PSD_ASSUME_SHARED(G.base); }
-        PairOut o; o.nc = 0; o.s0 = 0; o.x1 = 0; o.x2 = 0;
-        PairJob jb; jb.da = jb.db = jb.dc = jb.lo = jb.hi = jb.xo = jb.m = jb.c1 = jb.c2 = jb.dl = jb.dr = jb.elo = jb.dmid = 0; jb.flags = 0;
-        double hi = 0;
-        int i = 0, j = 0;
-        bool need = false;
-        if (valid) {
-          const int code = (mine ? ivl : oivl)[qi];
-          i = code & 0xffff; j = code >> 16;
-          need = pair_pre(cap, F, G, i, j, dmin, &hi, &o, &jb);
-          if (!need) pair_write_slots(mine ? cand_s : ocand_s, mine ? cand_x : ocand_x, qi, o, i, j, hi);
-        }
-        const unsigned jm = psd_ballot(need);
-        const int nj = psd_popc(jm);
-        if ((!more && n_jobs > 0) || (more && n_jobs + nj > job_cap)) {
-          // the Newton round: one lane per queued job, whichever chain and pass it came from
-          psd_syncwarp();
-          for (int kb = 0; kb < n_jobs; kb += 32) {
-            const int k = kb + wl;
-            if (k < n_jobs) {
-              const double* rec = ((k < per_buf) ? jbuf0 : jbuf1) + (k % per_buf) * PSD_JOB_DOUBLES;
-              PairJob r;
-              r.da = rec[0]; r.db = rec[1]; r.dc = rec[2]; r.lo = rec[3]; r.hi = rec[4]; r.xo = rec[5]; r.m = rec[6];
-              r.c1 = rec[7]; r.c2 = rec[8]; r.dl = rec[9]; r.dr = rec[10]; r.elo = rec[11]; r.dmid = rec[12];
-              const unsigned long long meta = PSD_D2U(rec[13]);
-              r.flags = (int)(meta >> 52) & 7;
-              const int ji = (int)(meta & 0xffff), jj = (int)((meta >> 16) & 0xffff), jq = (int)((meta >> 32) & 0xffff), jc = (int)((meta >> 48) & 1);
-              const PairOut po = pair_post(r);
-              const bool jmine = (jc == grp);
-              pair_write_slots(jmine ? cand_s : ocand_s, jmine ? cand_x : ocand_x, jq, po, ji, jj, r.hi);
-            }
-          }
-          n_jobs = 0;
-          psd_syncwarp();
-        }
-        if (!more) break;
-        if (need) {
-          const int k = n_jobs + psd_popc(jm & ltm);
-          double* rec = ((k < per_buf) ? jbuf0 : jbuf1) + (k % per_buf) * PSD_JOB_DOUBLES;
-          rec[0] = jb.da; rec[1] = jb.db; rec[2] = jb.dc; rec[3] = jb.lo; rec[4] = jb.hi; rec[5] = jb.xo; rec[6] = jb.m;
-          rec[7] = jb.c1; rec[8] = jb.c2; rec[9] = jb.dl; rec[10] = jb.dr; rec[11] = jb.elo; rec[12] = jb.dmid;
-          rec[13] = PSD_U2D((unsigned long long)i | ((unsigned long long)j << 16) | ((unsigned long long)qi << 32) |
-                            ((unsigned long long)c << 48) | ((unsigned long long)jb.flags << 52));
-        }
-        n_jobs += nj;
-      }
-      psd_syncwarp();
-      // compact my chain's candidate slots (3 per interval, void ones dropped), in place
-      {
-        const int n_slots = 3 * K;
-        int Tn = 0;
-        for (int base = 0; base < n_slots; base += PSD_G) {
-          const int q = base + lane;
-          const int code = (q < n_slots) ? cand_s[q] : PSD_CAND_VOID;
-          const double x = (q < n_slots) ? cand_x[q] : 0.0;
-          const unsigned vm = psd_g_ballot(code != PSD_CAND_VOID);
-          psd_g_sync();   // every lane has read its slot before any lane overwrites one
-          if (code != PSD_CAND_VOID) { const int t = Tn + psd_popc(vm & ((1u << lane) - 1u)); cand_s[t] = code; cand_x[t] = x; }
-          Tn += psd_popc(vm);
-          psd_g_sync();
-        }
-        T0 = T1 = Tn;
-      }
-    }
-#else
-    const bool defer = false;
-#endif
 #if defined(PSD_TIMING) && !defined(PSD_EMU)
     int stat_jobs = 0, stat_rounds = 0;
 #endif
 #if defined(PSD_EMU_STATS)
     int stat_heavy = 0, stat_two = 0;
 #endif
-    for (int base = 0; base < total && !defer; base += 32) {
+    for (int base = 0; base < total; base += 32) {
       const int q = base + wl;
       const bool valid = q < total;
       const int c = (valid && q >= K0) ? 1 : 0;           // which chain this lane works for in this pass
@@ -1342,11 +1111,8 @@ PSD_DEV void dp_run_queue(const WarpWs& ws_s, const WarpWs& ws_g, const DpQueue&
         PSD_T0(tb);
         PList otmp; otmp.base = ws_list(ws, 4 + (grp ^ 1)); otmp.n = psd_shfl_i(tmp.n, lane ^ 16);   // the other chain's lists
         const PList oprev = grp ? upP : downP;
-#if defined(PSD_DEFER_NEWTON)
-        const PList odst = grp ? upN : downN;
-#endif
-        n_out = in_g ? min_env_op<false>(wg, tmp, prev, otmp, oprev, dst PSD_DEFER_ARG(odst), dmin, rs)
-                     : min_env_op<true>(wg, tmp, prev, otmp, oprev, dst PSD_DEFER_ARG(odst), dmin, rs);
+        n_out = in_g ? min_env_op<false>(wg, tmp, prev, otmp, oprev, dst, dmin, rs)
+                     : min_env_op<true>(wg, tmp, prev, otmp, oprev, dst, dmin, rs);
         PSD_T1(tb, 2 + grp);
       }
       psd_syncwarp();   // both chains done; their lists are visible to the whole warp

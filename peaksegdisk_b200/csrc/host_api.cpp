@@ -421,6 +421,13 @@ int psd_plan_add(psd_plan* plan, int64_t n_rows, const int32_t* chromStart, cons
     if (!std::isfinite(penalty)) return -PSD_ERR_PENALTY_NOT_FINITE;
     if (penalty < 0) return -PSD_ERR_PENALTY_NEGATIVE;
   }
+  // the file path's contract (src/PeakSegFPOPLog.cpp:180-186): rows are contiguous; in addition the
+  // in-memory entry insists on positive widths and non-negative coverage (a zero first width makes
+  // penalty / cumulative weight infinite in the kernel; psd_plan_add_counts rejects negatives too)
+  for (int64_t i = 0; i < n_rows; i++) {
+    if (i > 0 && chromStart[i] != chromEnd[i - 1]) return -PSD_ERR_INCONSISTENT_CHROMSTART_CHROMEND;
+    if (chromEnd[i] <= chromStart[i] || coverage[i] < 0) return -PSD_ERR_ARG;
+  }
   std::vector<HostProblem>& v = psd_plan_problems(plan);
   v.emplace_back();
   HostProblem& h = v.back();

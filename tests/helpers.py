@@ -50,3 +50,14 @@ def loss_fields(line):
     return {"penalty": f[0], "segments": int(f[1]), "peaks": int(f[2]), "bases": int(f[3]), "lines": int(f[4]),
             "mean_pen_cost": float(f[5]), "total_loss": float(f[6]), "equality": int(f[7]),
             "mean_intervals": float(f[8]), "max_intervals": float(f[9])}
+
+
+def c4_lite_problems(samples=2, scale=0.05):
+    """BASELINE config 4 at reduced scale: 24 hg19-shaped chromosomes x `samples`
+    samples, rows proportional to chromosome length (chr1 = 1e7 * scale), Mono27ac-like weights
+    (clipped to 2,000 bases so tiled coordinates stay below 2^31), one penalty per problem.
+    Returns [(chromStart, chromEnd, coverage, penalty)] in (chromosome, sample) order."""
+    from peaksegdisk_b200 import synth
+    _, s0, e0, c0 = synth.read_bedgraph(os.path.join(GOLD, "Mono27ac_coverage.bedGraph"))
+    w0 = np.minimum((e0 - s0).astype(np.int64), 2000)
+    return [synth.hg19_problem(ci, si, w0, c0.astype(np.float64), scale_rows=scale) for ci in range(24) for si in range(samples)]

@@ -103,25 +103,3 @@ def test_degenerate_rows_terminate(ec):
         assert st in (0, 101, 103, 104), st
         seen.add(st)
     assert 0 in seen
-
-
-def test_deferred_newton_variant_is_bit_identical(ec):
-    """-DPSD_DEFER_NEWTON (an experiment switch, off in the product): min_env runs one compacted
-    Newton round per call.  The variant must stay bit-identical to the oracle row by row, in both
-    lane orders, including calls that fall back to the pass-by-pass stage (small tier)."""
-    from peaksegdisk_b200 import synth
-    emu_dir = os.path.join(ROOT, "tests", "emu")
-    lib = os.path.join(ROOT, "tests", "_build", "libpsd_emu_defer.so")
-    subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-mfma", "-DPSD_DEFER_NEWTON",
-                           "-Wno-unused-variable", "-Wno-unused-function", "-I" + emu_dir, "-x", "c++", "-shared", "-o", lib,
-                           os.path.join(emu_dir, "emu_fpop.cpp"), os.path.join(emu_dir, "warp_emu.cpp")])
-    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
-            "import emu_compare as ec\nfrom peaksegdisk_b200 import synth\n"
-            "ok = True\n"
-            "for seed, n, pen, cap in [(2, 2000, 100.0, 48), (5, 4000, 3e4, 48), (3, 1200, 1e4, 16), (7, 1500, 0.0, 64)]:\n"
-            "    s, e, c = synth.poisson_problem(seed, n)\n"
-            "    ok = ok and ec.compare(s, e, c, pen, cap=cap, descending=0, trace=True) and ec.compare(s, e, c, pen, cap=cap, descending=1, trace=False)\n"
-            "sys.exit(0 if ok else 1)\n") % (os.path.join(ROOT, "tests"), ROOT)
-    env = dict(os.environ, PSD_EMU_LIB=lib)
-    out = subprocess.run([os.sys.executable, "-c", code], env=env, capture_output=True, text=True)
-    assert out.returncode == 0, out.stdout[-1500:] + out.stderr[-1500:]
