@@ -97,6 +97,8 @@ typedef struct psd_stats {
   double rle_ms;                    /* device time of the four RLE kernels */
   int64_t rle_positions;            /* count positions encoded */
   int64_t rle_bytes_algorithmic;    /* 4 B per position read + 12 B per row written */
+  int32_t n_latency_waves;          /* waves of the last solve that ran the latency kernel (one problem per block) */
+  int32_t pad_;
 } psd_stats;
 
 /* device < 0 selects the current CUDA device. */
@@ -131,11 +133,27 @@ int psd_plan_get_stats(const psd_plan *plan, psd_stats *out);
 /* Replaces problem id's penalty (used by the sequential search to re-solve the same rows). */
 int psd_plan_set_penalty(psd_plan *plan, int id, double penalty, int penalty_is_inf);
 
+/* Writes rows as the 4-column bedGraph text R/writeBedGraph.R:35-37 produces (tab separated, no
+ * header, one "chrom\tchromStart\tchromEnd\tcount" line per row).  Returns 0 or PSD_ERR_ARG when the
+ * file cannot be written. */
+int psd_write_bedgraph(const char *path, const char *chrom, int64_t n_rows, const int32_t *chromStart,
+                       const int32_t *chromEnd, const int32_t *count);
+
+/* Inspection of the cost-function store (replaces DiskVector::read, src/PeakSegFPOPLog.cpp:103-117,
+ * for tests and tools): the stored function `which` (0 = up, 1 = down) of bedGraph row `row` of
+ * problem id, in the reference's record fields (src/PeakSegFPOPLog.cpp:18-34: max_log_mean, data_i,
+ * prev_log_mean per piece).  *n_pieces receives the piece count; arrays need `cap` >= that many
+ * entries (PSD_ERR_ARG otherwise).  Valid after a solve whose store fitted one wave. */
+int psd_plan_store_function(psd_plan *plan, int id, int row, int which, int cap, int *n_pieces, double *max_log_mean,
+                            int *data_i, double *prev_log_mean);
+
 /* Tunables (call before psd_plan_create): "piece_cap" (shared-memory tier, default 48),
  * "overflow_cap" (global tier, default 8192), "store_gb" (HBM pool, default 0 = auto),
  * "chunk_kb" (store chunk, default 64), "spill_cap" (per-warp global workspace, default 512),
  * "host_spill_gb" (pinned-host overflow of the store: -1 = automatic, 0 = off),
  * "occupancy_mode" (0 = choose per batch, 1 = one block of 14 warps per SM, 2 = two blocks),
+ * "latency_mode" (0 = waves of at most "latency_max_blocks" (default 2) problems per SM run the latency
+ * kernel: one problem per block, one chain per warp; 1 = always; 2 = never),
  * "devices" (GPUs one psd_fpop_disk_batch call may use: 1 = the current device (default), k = the
  * first k, <= 0 = all; problems are dealt longest-first, one plan and host thread per GPU). */
 int psd_set_option(const char *name, double value);

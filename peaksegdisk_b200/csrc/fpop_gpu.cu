@@ -27,7 +27,7 @@
 #include <queue>
 #include <string>
 #include <vector>
-#include "fpop_warp.cuh"
+#include "dp_params.h"
 #include "rle_gpu.cuh"
 #include "plan_internal.h"
 
@@ -35,29 +35,12 @@
 #define PSD_MAX_WARPS_PER_BLOCK 16   /* __launch_bounds__(512): 128 registers per thread (fewer registers only add spills; 14-16 warps fit shared memory) */
 #endif
 #define PSD_BT_WARPS_PER_BLOCK 4
-#define PSD_TAB_BYTES 4096
 
 #if defined(PSD_TIMING)
 __device__ unsigned long long psd_blk_end[160];
 #endif
 __device__ const uint64_t d_exp_tab[256] = PSD_EXP_TAB_INIT;
 __device__ const uint64_t d_log_tab[256] = PSD_LOG_TAB_INIT;
-
-struct DpKernelParams {
-  const DpProblem* problems;
-  const int* order;           // problem ids, longest first
-  int n_order;
-  int* queue;                 // atomic cursor into order (one per block when bins != null)
-  const int* bins;            // null: one global queue.  Else {begin, end} into order per block: each block works
-                              // through its own share, longest first, and stops refilling when the share is empty
-  DpResult* results;
-  StorePool pool;
-  int cap_s, ccap_s;          // shared-memory tier (cap_s = 0: disabled, warps start in the global tier)
-  unsigned long long ws_s_bytes;   // per warp, >= PSD_WS_HDR (the header holds the warp's flag word)
-  unsigned char* gws;         // per-warp global-memory workspaces (null: none)
-  int cap_g, ccap_g;
-  unsigned long long ws_g_bytes;
-};
 
 static inline unsigned long long psd_ws_bytes(int cap, int ccap) { return cap > 0 ? PSD_WS_BYTES(cap, ccap) : PSD_WS_HDR; }
 
@@ -142,7 +125,7 @@ fpop_backtrack_kernel(const BtKernelParams P) {
 namespace {
 thread_local std::string g_last_error;
 std::mutex g_opt_mutex;
-struct Options { int piece_cap = 48; int overflow_cap = 8192; double store_gb = 0; int chunk_kb = 64; int max_warps_per_sm = 0; int blocks_per_sm = 1; int spill_cap = 512; double host_spill_gb = -1; int occupancy_mode = 0; int devices = 1; int queue_mode = 0; } g_opt;
+struct Options { int piece_cap = 48; int overflow_cap = 8192; double store_gb = 0; int chunk_kb = 64; int max_warps_per_sm = 0; int blocks_per_sm = 1; int spill_cap = 512; double host_spill_gb = -1; int occupancy_mode = 0; int devices = 1; int queue_mode = 0; int latency_mode = 0; int latency_max_blocks = 2; } g_opt;
 
 bool cuda_ok(cudaError_t e, const char* what) {
   if (e == cudaSuccess) return true;
@@ -171,6 +154,8 @@ int psd_set_option_impl(const char* name, double value) {
   else if (n == "host_spill_gb") g_opt.host_spill_gb = value;
   else if (n == "occupancy_mode") g_opt.occupancy_mode = (int)value;   // 0 auto, 1 one block/SM, 2 two blocks/SM
   else if (n == "queue_mode") g_opt.queue_mode = (int)value;           // experiment: 0 one global queue, 1 one share of the batch per block
+  else if (n == "latency_mode") g_opt.latency_mode = (int)value;       // 0 auto (small waves), 1 always the latency kernel, 2 never
+  else if (n == "latency_max_blocks") g_opt.latency_max_blocks = std::max(1, (int)value);   // auto: waves of up to this many problems per SM
   else if (n == "devices") g_opt.devices = (int)value;                 // 1 current device only, k first k GPUs, <= 0 all
   else return PSD_ERR_ARG;
   return 0;
@@ -271,13 +256,16 @@ static Options current_options() {
   if (const char* e = getenv("PSD_HOST_SPILL_GB")) o.host_spill_gb = atof(e);
   if (const char* e = getenv("PSD_OCCUPANCY_MODE")) o.occupancy_mode = atoi(e);
   if (const char* e = getenv("PSD_QUEUE_MODE")) o.queue_mode = atoi(e);
+  if (const char* e = getenv("PSD_LATENCY_MODE")) o.latency_mode = atoi(e);
+  if (const char* e = getenv("PSD_LATENCY_MAX_BLOCKS")) o.latency_max_blocks = std::max(1, atoi(e));
   return o;
 }
 
 static bool same_options(const Options& a, const Options& b) {
   return a.piece_cap == b.piece_cap && a.overflow_cap == b.overflow_cap && a.store_gb == b.store_gb && a.chunk_kb == b.chunk_kb &&
          a.max_warps_per_sm == b.max_warps_per_sm && a.blocks_per_sm == b.blocks_per_sm && a.spill_cap == b.spill_cap &&
-         a.host_spill_gb == b.host_spill_gb && a.occupancy_mode == b.occupancy_mode && a.queue_mode == b.queue_mode;
+         a.host_spill_gb == b.host_spill_gb && a.occupancy_mode == b.occupancy_mode && a.queue_mode == b.queue_mode &&
+         a.latency_mode == b.latency_mode && a.latency_max_blocks == b.latency_max_blocks;
 }
 
 psd_plan* psd_plan_create_impl(int device) {
@@ -662,7 +650,7 @@ int psd_plan_solve_impl(psd_plan* p, void* stream_v) {
   const size_t ng = p->gpu_ids.size();
   if (ng) CK(cudaSetDevice(p->device));
   psd_stats& S = p->stats;
-  S.dp_ms = S.backtrack_ms = 0; S.n_launches = 0; S.n_waves = 0; S.n_overflow_tier = 0;
+  S.dp_ms = S.backtrack_ms = 0; S.n_launches = 0; S.n_waves = 0; S.n_overflow_tier = 0; S.n_latency_waves = 0;
   S.rows_solved = 0; S.store_bytes_algorithmic = 0; S.store_bytes_written = 0; S.backtrack_bytes_read = 0; S.store_bytes_spilled_host = 0;
   p->results.assign(ng, DpResult());
   p->n_seg_total = 0;
@@ -719,7 +707,33 @@ int psd_plan_solve_impl(psd_plan* p, void* stream_v) {
     K.pool.base = p->d_pool; K.pool.cursor = p->d_cursors; K.pool.n_chunks = p->pool_bytes / chunk; K.pool.chunk_bytes = chunk;
     K.pool.host_base = p->d_spill; K.pool.host_cursor = p->d_cursors + 2; K.pool.host_chunks = p->spill_bytes / chunk;
     int grid; size_t smem; int wpb; int which = 0; int blocks = 1;
-    if (!global_tier) {
+    // Few problems (a sequential search on one chromosome, the worst-case sequences, single calls):
+    // the latency kernel, one problem per block and one chain per warp (fpop_lat.cu)
+    const int n_sm = p->prop.multiProcessorCount;
+    const int per_sm = (n + n_sm - 1) / n_sm;
+    const bool lat = p->opt.latency_mode == 1 || (p->opt.latency_mode == 0 && per_sm <= p->opt.latency_max_blocks);
+    if (lat) {
+      wpb = PSD_LAT_WARPS;
+      if (!global_tier) {
+        const int resident = std::max(1, std::min(per_sm, 8));
+        const size_t per_block = std::min((size_t)p->prop.sharedMemPerMultiprocessor / resident - 1024, (size_t)p->prop.sharedMemPerBlockOptin);
+        long cap = ((long)per_block - PSD_TAB_BYTES - PSD_LAT_SHARED_BYTES - 32) / 328;   // PSD_WS_BYTES(cap, 2 cap) = 16 + 328 cap
+        cap = std::min(640L, cap) & ~1L;
+        if (p->opt.piece_cap < 48) cap = std::min(cap, (long)((p->opt.piece_cap + 1) & ~1));   // a tier below the default is a request (tests force the global tier with it)
+        if (cap < 8) cap = 8;
+        K.cap_s = (int)cap; K.ccap_s = 2 * K.cap_s; K.ws_s_bytes = psd_ws_bytes(K.cap_s, K.ccap_s);
+        // the block's global workspace takes what outgrows shared memory: with one block per SM it is
+        // sized for the worst-case sequences (config 5) so that no host-level re-run is needed
+        K.cap_g = (n <= n_sm) ? std::max(p->opt.spill_cap, std::min(p->opt.overflow_cap, 32768)) : p->opt.spill_cap;
+        K.ccap_g = 3 * K.cap_g; K.ws_g_bytes = psd_ws_bytes(K.cap_g, K.ccap_g);
+      } else {
+        K.cap_s = 0; K.ccap_s = 0; K.ws_s_bytes = psd_ws_bytes(0, 0);
+        K.cap_g = gcap; K.ccap_g = 3 * gcap; K.ws_g_bytes = psd_ws_bytes(K.cap_g, K.ccap_g);
+      }
+      smem = PSD_TAB_BYTES + PSD_LAT_SHARED_BYTES + (size_t)K.ws_s_bytes;
+      grid = n;
+      S.piece_cap = K.cap_s; S.warps_per_sm = PSD_LAT_WARPS * std::min(per_sm, std::max(1, psd_lat_max_blocks_per_sm(smem)));
+    } else if (!global_tier) {
       // shared-memory tier, with a per-warp global workspace the kernel moves to (and back from)
       // when a row's functions outgrow shared memory
       which = choose_config(p, todo);
@@ -735,10 +749,10 @@ int psd_plan_solve_impl(psd_plan* p, void* stream_v) {
       wpb = std::min(8, PSD_MAX_WARPS_PER_BLOCK);
       smem = PSD_TAB_BYTES + (size_t)wpb * K.ws_s_bytes;
     }
-    grid = std::max(1, std::min(p->prop.multiProcessorCount * blocks, n));   // a small batch spreads one warp per SM
+    if (!lat) grid = std::max(1, std::min(p->prop.multiProcessorCount * blocks, n));   // a small batch spreads one warp per SM
     K.gws = nullptr;
     if (K.cap_g > 0) {
-      const unsigned long long need = (unsigned long long)grid * wpb * K.ws_g_bytes;
+      const unsigned long long need = (unsigned long long)grid * (lat ? 1 : wpb) * K.ws_g_bytes;
       if (need > p->gws_bytes) { dfree(p->d_gws); p->gws_bytes = 0; CK(cudaMalloc(&p->d_gws, need)); p->gws_bytes = need; }
       K.gws = p->d_gws;
     }
@@ -752,7 +766,7 @@ int psd_plan_solve_impl(psd_plan* p, void* stream_v) {
     }
     K.bins = nullptr;
     std::vector<int> binned;
-    if (!global_tier && p->opt.queue_mode == 1 && grid <= 1024 && n > grid * wpb) {
+    if (!lat && !global_tier && p->opt.queue_mode == 1 && grid <= 1024 && n > grid * wpb) {
       // EXPERIMENT (profiles/README.md): one share of the wave per block, longest-first onto the
       // least loaded block by rows.  A block that has emptied its share does not refill, so the warps
       // still working on long problems get the SM to themselves.
@@ -784,9 +798,15 @@ int psd_plan_solve_impl(psd_plan* p, void* stream_v) {
     CK(cudaMemsetAsync(p->d_cursors, 0, sizeof(unsigned long long), st));   // recycle the store pool
     CK(cudaMemsetAsync(p->d_cursors + 2, 0, sizeof(unsigned long long), st));
     CK(cudaEventRecord(p->ev[2], st));
-    if (which == 1) fpop_dp_kernel<14, 2><<<grid, wpb * 32, smem, st>>>(K);
-    else fpop_dp_kernel<PSD_MAX_WARPS_PER_BLOCK, 1><<<grid, wpb * 32, smem, st>>>(K);
-    CK(cudaGetLastError());
+    if (lat) {
+      CK((cudaError_t)psd_lat_set_smem(smem));
+      CK((cudaError_t)psd_lat_launch(K, grid, smem, st));
+      S.n_latency_waves++;
+    } else {
+      if (which == 1) fpop_dp_kernel<14, 2><<<grid, wpb * 32, smem, st>>>(K);
+      else fpop_dp_kernel<PSD_MAX_WARPS_PER_BLOCK, 1><<<grid, wpb * 32, smem, st>>>(K);
+      CK(cudaGetLastError());
+    }
     CK(cudaEventRecord(p->ev[3], st));
     BtKernelParams B;
     B.problems = p->d_problems; B.order = p->d_order; B.n_order = n; B.results = p->d_results; B.pool = K.pool;
@@ -923,6 +943,39 @@ int psd_plan_download_impl(psd_plan* p, void* stream_v) {
     h.seg_row.assign(p->p_seg_row + r.seg_offset, p->p_seg_row + r.seg_offset + r.n_segments);
     h.seg_x.assign(p->p_seg_x + r.seg_offset, p->p_seg_x + r.seg_offset + r.n_segments);
   }
+  return 0;
+}
+
+// Reads one stored cost function back (what DiskVector::read does in the reference,
+// src/PeakSegFPOPLog.cpp:103-117): the record of `row`, function `which` (0 up, 1 down), as the
+// reference's record fields max_log_mean / data_i / prev_log_mean.  Valid after a solve that needed
+// a single store wave (the pool then still holds every record).  A few small D2H copies per call:
+// an inspection path for tests and tools, not a hot path.
+int psd_plan_store_function_impl(psd_plan* p, int id, int row, int which, int cap, int* n_out, double* hi, int* back_i, double* back_x) {
+  if (!p->solved || p->stats.n_waves != 1) { g_last_error = "store inspection needs a solved plan whose store fitted one wave"; return PSD_ERR_ARG; }
+  if (id < 0 || id >= (int)p->probs.size() || which < 0 || which > 1 || !n_out) return PSD_ERR_ARG;
+  const HostProblem& h = p->probs[id];
+  if (h.status != 0 || h.trivial || h.result_status != 0 || row < 0 || row >= h.n_rows) return PSD_ERR_ARG;
+  CK(cudaSetDevice(p->device));
+  unsigned long long off = 0;
+  CK(cudaMemcpy(&off, p->d_index + h.row_off + row, sizeof off, cudaMemcpyDeviceToHost));
+  auto fetch = [&](void* dst, unsigned long long o, size_t bytes) -> cudaError_t {
+    if (o < p->pool_bytes) return cudaMemcpy(dst, p->d_pool + o, bytes, cudaMemcpyDeviceToHost);
+    memcpy(dst, p->h_spill + (o - p->pool_bytes), bytes);     // spilled record: already in pinned host memory
+    return cudaSuccess;
+  };
+  unsigned hdr[4];
+  CK(fetch(hdr, off, sizeof hdr));
+  if ((int)hdr[2] != row) { g_last_error = "store record does not belong to the requested row"; return PSD_ERR_INTERNAL; }
+  const int n_up = (int)hdr[0], n_down = (int)hdr[1];
+  const int n = which ? n_down : n_up;
+  *n_out = n;
+  if (n > cap) return PSD_ERR_ARG;
+  if (n == 0) return 0;
+  std::vector<double> pairs(2 * (size_t)n);
+  CK(fetch(pairs.data(), off + 16 + 16ull * (which ? n_up : 0), 16ull * n));
+  CK(fetch(back_i, off + 16 + 16ull * (n_up + n_down) + 4ull * (which ? n_up : 0), 4ull * n));
+  for (int k = 0; k < n; k++) { hi[k] = pairs[2 * k]; back_x[k] = pairs[2 * k + 1]; }
   return 0;
 }
 

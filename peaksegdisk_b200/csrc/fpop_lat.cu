@@ -1,0 +1,54 @@
+// fpop_lat.cu -- the LATENCY kernel (sm_100a): one problem per thread block, one chain per warp.
+//
+// Compiled with -DPSD_G32: the operators of fpop_warp.cuh then use a whole warp (32 lanes) per
+// chain instead of a half-warp, and dp_run_latency() (same header) drives the two warps of a block
+// through the problem with one block barrier per row.  Used when a wave has fewer problems than
+// the GPU has room for (a sequential search on one long chromosome, config 3; the worst-case
+// sequences, config 5; single calls of PeakSegFPOP_disk, config 1), where the one-warp-per-problem
+// kernel leaves most of the chip idle and a row is one long chain of dependent fp64 instructions.
+// 64 threads per block leave every thread up to 255 registers: no spills; the piece lists get the
+// block's whole shared memory (640 pieces per function with one block per SM).
+// Same arithmetic, same store records, same backtrack kernel as the throughput path.
+#include <cuda_runtime.h>
+#include "dp_params.h"
+
+#if !defined(PSD_G32)
+#error "fpop_lat.cu must be compiled with -DPSD_G32"
+#endif
+
+static __device__ const uint64_t d_lat_exp_tab[256] = PSD_EXP_TAB_INIT;
+static __device__ const uint64_t d_lat_log_tab[256] = PSD_LOG_TAB_INIT;
+
+__global__ void __launch_bounds__(PSD_LAT_WARPS * 32)
+fpop_dp_lat_kernel(const DpKernelParams P) {
+  uint64_t* etab = (uint64_t*)psd_smem;
+  uint64_t* ltab = etab + 256;
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) { etab[i] = d_lat_exp_tab[i]; ltab[i] = d_lat_log_tab[i]; }
+  LatShared* sh = (LatShared*)(psd_smem + PSD_TAB_BYTES);
+  __syncthreads();
+  const int b = (int)blockIdx.x;
+  if (b >= P.n_order) return;
+  const int id = P.order[b];
+  WarpWs ws_s, ws_g;
+  ws_s.base = psd_smem + PSD_TAB_BYTES + PSD_LAT_SHARED_BYTES;
+  ws_s.scratch = nullptr; ws_s.flags = (int*)ws_s.base; ws_s.cap = P.cap_s; ws_s.ccap = P.ccap_s;
+  ws_g.base = P.gws ? P.gws + (unsigned long long)b * P.ws_g_bytes : nullptr;
+  ws_g.scratch = nullptr; ws_g.flags = ws_s.flags; ws_g.cap = P.gws ? P.cap_g : 0; ws_g.ccap = P.ccap_g;
+  const DpProblem pb = P.problems[id];
+  dp_run_latency(ws_s, ws_g, pb, &P.results[id], P.pool, sh);
+}
+
+int psd_lat_set_smem(size_t smem_bytes) {
+  return (int)cudaFuncSetAttribute(fpop_dp_lat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+}
+
+int psd_lat_max_blocks_per_sm(size_t smem_bytes) {
+  int nb = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fpop_dp_lat_kernel, PSD_LAT_WARPS * 32, smem_bytes) != cudaSuccess) return 0;
+  return nb;
+}
+
+int psd_lat_launch(const DpKernelParams& P, int grid, size_t smem_bytes, void* stream) {
+  fpop_dp_lat_kernel<<<grid, PSD_LAT_WARPS * 32, smem_bytes, (cudaStream_t)stream>>>(P);
+  return (int)cudaGetLastError();
+}

@@ -46,8 +46,22 @@
 #include "warp_emu.h"
 #else
 #define PSD_DEV __device__ __forceinline__
-#define PSD_DEVNI __device__ __noinline__
+#define PSD_DEVNI static __device__ __noinline__
 PSD_DEV int psd_lane() { return (int)(threadIdx.x & 31u); }
+#if defined(PSD_G32)
+// latency kernel (fpop_lat.cu): one operator group per WARP -- the up chain and the down chain of a
+// problem run on two warps of 32 lanes each, so the group collectives are whole-warp collectives
+PSD_DEV int psd_glane() { return (int)(threadIdx.x & 31u); }
+PSD_DEV double psd_g_shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+PSD_DEV int psd_g_shfl_i(int v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+PSD_DEV double psd_g_shfl_up_d(double v, int d) { return __shfl_up_sync(0xffffffffu, v, d); }
+PSD_DEV double psd_g_shfl_down_d(double v, int d) { return __shfl_down_sync(0xffffffffu, v, d); }
+PSD_DEV int psd_g_shfl_up_i(int v, int d) { return __shfl_up_sync(0xffffffffu, v, d); }
+PSD_DEV unsigned psd_g_ballot(int p) { return __ballot_sync(0xffffffffu, p); }
+PSD_DEV void psd_g_sync() { __syncwarp(); }
+PSD_DEV void psd_cta_sync() { __syncthreads(); }
+PSD_DEV int psd_warp_in_block() { return (int)(threadIdx.x >> 5); }
+#else
 // 16-lane groups: the two half-warps of a problem's warp run the up- and the down-recursion
 PSD_DEV int psd_glane() { return (int)(threadIdx.x & 15u); }
 PSD_DEV unsigned psd_gmask_() { return 0xffffu << (threadIdx.x & 16u); }
@@ -58,6 +72,7 @@ PSD_DEV double psd_g_shfl_down_d(double v, int d) { return __shfl_down_sync(psd_
 PSD_DEV int psd_g_shfl_up_i(int v, int d) { return __shfl_up_sync(psd_gmask_(), v, d, 16); }
 PSD_DEV unsigned psd_g_ballot(int p) { return (__ballot_sync(psd_gmask_(), p) >> (threadIdx.x & 16u)) & 0xffffu; }
 PSD_DEV void psd_g_sync() { __syncwarp(psd_gmask_()); }
+#endif
 PSD_DEV double psd_shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 PSD_DEV int psd_shfl_i(int v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 PSD_DEV unsigned long long psd_shfl_u64(unsigned long long v, int src) { return __shfl_sync(0xffffffffu, v, src); }
@@ -98,8 +113,13 @@ extern unsigned long long psd_emu_stats[8][65];
 #define PSD_STAT(slot, leader, v) do {} while (0)
 #endif
 // While a flat stretch is open the pieces ahead are tested speculatively, PSD_SPEC lanes per round
+#if defined(PSD_G32)
+#define PSD_G 32             /* lanes per operator group: a whole warp (latency kernel) */
+#else
+#define PSD_G 16             /* lanes per operator group (half a warp) */
+#endif
 #ifndef PSD_SPEC
-#define PSD_SPEC 16
+#define PSD_SPEC PSD_G
 #endif
 // a problem running from its global workspace returns to shared memory when both functions have at
 // most PSD_RETURN_NUM/PSD_RETURN_DEN of the shared-memory capacity
@@ -107,7 +127,6 @@ extern unsigned long long psd_emu_stats[8][65];
 #define PSD_RETURN_NUM 1
 #define PSD_RETURN_DEN 2
 #endif
-#define PSD_G 16             /* lanes per operator group (half a warp) */
 #define PSD_EPS 1e-12        /* NEWTON_EPSILON, src/funPieceListLog.cpp:9 */
 #define PSD_MAX_STEPS 100    /* NEWTON_STEPS,   src/funPieceListLog.cpp:10 */
 
@@ -645,6 +664,38 @@ PSD_OP int min_env_op(const WarpWs ws, const PList f, const PList g, const PList
   psd_syncwarp();   // both chains' interval lists are visible to the whole warp
   PSD_T1(t1, 8);
   PSD_T0(t2);
+#if defined(PSD_G32)
+  // 2. crossing rule per interval -> candidate pieces: one lane per interval of THIS chain (the
+  // chain has the whole warp to itself in the latency kernel; of / og are unused)
+  int T = 0;
+  for (int base = 0; base < K; base += 32) {
+    const int q = base + lane;
+    const bool valid = q < K;
+    PairOut o; o.nc = 0; o.s0 = 0; o.x1 = 0; o.x2 = 0;
+    double lo = 0, hi = 0;
+    int i = 0, j = 0;
+    if (valid) {
+      const int code = ivl[q];
+      i = code & 0xffff; j = code >> 16;
+      o = pair_rule(cap, f, g, i, j, dmin, &lo, &hi);
+    }
+    const int mine_nc = valid ? o.nc : 0;
+    int incl = mine_nc;
+    for (int d = 1; d < 32; d <<= 1) { const int t = psd_g_shfl_up_i(incl, d); if (lane >= d) incl += t; }
+    const int tot = psd_g_shfl_i(incl, 31);
+    const int off = T + incl - mine_nc;
+    if (o.nc > 0) {
+      const int sf = i, sg = j | PSD_SRC_G;
+      const int c0 = o.s0 ? sg : sf, c1 = o.s0 ? sf : sg;
+      if (off + o.nc <= ccap) {
+        cand_s[off] = c0; cand_x[off] = (o.nc > 1) ? o.x1 : hi;
+        if (o.nc > 1) { cand_s[off + 1] = c1; cand_x[off + 1] = (o.nc > 2) ? o.x2 : hi; }
+        if (o.nc > 2) { cand_s[off + 2] = c0; cand_x[off + 2] = hi; }
+      } else ws_raise(ws, PSD_FLAG_OVERFLOW);
+    }
+    T += tot;
+  }
+#else
   // 2. crossing rule per interval -> candidate pieces.  The intervals of BOTH chains (this call is
   // converged: lanes 0-15 hold the up chain's arguments, lanes 16-31 the down chain's) are pooled
   // over the 32 lanes: a chain with 20 intervals next to one with 10 takes one pass, not two, and
@@ -745,6 +796,7 @@ PSD_OP int min_env_op(const WarpWs ws, const PList f, const PList g, const PList
     }
 #endif
   }
+#endif
   psd_syncwarp();   // every candidate of my chain is in place, whichever half-warp wrote it
   PSD_T1(t2, 9);
   PSD_T0(t3);
@@ -922,6 +974,7 @@ PSD_DEV unsigned char* store_ptr(const StorePool& sp, unsigned long long off) {
   return off < hbm ? sp.base + off : sp.host_base + (off - hbm);
 }
 
+#if !defined(PSD_G32)
 template <bool SH>
 PSD_DEV void store_write(const WarpWs ws, unsigned char* rec, int row, const PList up, const PList down) {
   if (SH) { PSD_ASSUME_SHARED(up.base); PSD_ASSUME_SHARED(down.base); }
@@ -940,6 +993,7 @@ PSD_DEV void store_write(const WarpWs ws, unsigned char* rec, int row, const PLi
     psd_st_cs_i(bis + k, PL_I(L, k));
   }
 }
+#endif
 
 // per-problem result of the DP (device -> host), and of the backtrack
 struct DpResult {
@@ -994,6 +1048,15 @@ struct DpProblem {
 #define psd_block_or(x) __syncthreads_or(x)
 #endif
 
+// Copies list `src` (n pieces, capacity scap) into list `dst` (capacity dcap); all 32 lanes.
+PSD_DEV void pl_move(const double* src, int scap, double* dst, int dcap, int n) {
+  for (int k = psd_lane(); k < n; k += 32) {
+    for (int a = 0; a < 5; a++) dst[a * dcap + k] = src[a * scap + k];
+    ((int*)(dst + 5 * dcap))[k] = ((const int*)(src + 5 * scap))[k];
+  }
+}
+
+#if !defined(PSD_G32)
 // order[] lists problem ids longest first.  Slot q = warp_in_block * n_blocks + block is taken
 // statically by that warp (so the longest problems land one per SM and a small batch spreads over
 // all SMs instead of filling a few blocks); the rest are popped from the atomic cursor, which the
@@ -1006,14 +1069,6 @@ struct DpQueue {
   DpResult* results;
   int first_slot;        // this warp's static slot
 };
-
-// Copies list `src` (n pieces, capacity scap) into list `dst` (capacity dcap); all 32 lanes.
-PSD_DEV void pl_move(const double* src, int scap, double* dst, int dcap, int n) {
-  for (int k = psd_lane(); k < n; k += 32) {
-    for (int a = 0; a < 5; a++) dst[a * dcap + k] = src[a * scap + k];
-    ((int*)(dst + 5 * dcap))[k] = ((const int*)(src + 5 * scap))[k];
-  }
-}
 
 // ws_s: the warp's shared-memory workspace (cap 0 = disabled), ws_g: its global-memory workspace
 // (cap 0 = none).  A problem runs from shared memory; when a row's functions outgrow it the warp
@@ -1192,6 +1247,199 @@ PSD_DEV void dp_run_queue(const WarpWs& ws_s, const WarpWs& ws_g, const DpQueue&
   }
 #undef PSD_BIND_TIER
 }
+#endif   // !PSD_G32
+
+#if defined(PSD_G32)
+// ---- latency mode: one problem per thread block, one chain per warp ---------------------------------
+// When a batch has fewer problems than the GPU has warp slots (one long chromosome, a sequential
+// search, the worst-case sequences), one warp per problem leaves the chip idle and the problem's
+// rows are a single chain of dependent fp64 instructions.  Here a block of two warps owns the
+// problem: warp 0 runs the up recursion (min_less, min_env), warp 1 the down recursion (min_more,
+// min_env), each with all 32 lanes (functions of up to 32 pieces / 32 overlap intervals take one
+// pass), their Newton solves overlap instead of serialising on two half-warps, and the piece lists
+// have the block's whole shared memory (hundreds of pieces before the global tier is needed).
+// A chain reads the other chain's PREVIOUS function only in min_less / min_more, so the two warps
+// meet at ONE block barrier per row.  Same operators, same arithmetic, same record format.
+struct LatShared {
+  int n_out[2][2];                  // [row parity][chain]: pieces of the new function
+  unsigned long long chunk_first;   // store chunk handed out by warp 0 to both warps
+  unsigned long long pad_;
+};
+
+// store chunk allocation for the block: both warps keep identical StoreWriter state; the atomic is
+// issued once (warp 0) and its result passed through shared memory
+PSD_DEV unsigned long long store_alloc_cta(const StorePool& sp, StoreWriter& w, unsigned long long bytes, LatShared* sh, int grp) {
+  if (w.cur + bytes > w.end) {
+    const unsigned long long need = (bytes + sp.chunk_bytes - 1) / sp.chunk_bytes;
+    if (grp == 0 && psd_lane() == 0) {
+      unsigned long long first = psd_atomic_add_ull(sp.cursor, need);
+      if (first + need > sp.n_chunks) {
+        first = ~0ull;
+        if (sp.host_chunks != 0) {
+          const unsigned long long h = psd_atomic_add_ull(sp.host_cursor, need);
+          if (h + need <= sp.host_chunks) first = sp.n_chunks + h;
+        }
+      }
+      sh->chunk_first = first;
+    }
+    psd_cta_sync();
+    const unsigned long long first = *(volatile unsigned long long*)&sh->chunk_first;
+    if (first == ~0ull) return ~0ull;
+    w.cur = first * sp.chunk_bytes;
+    w.end = w.cur + need * sp.chunk_bytes;
+  }
+  const unsigned long long off = w.cur;
+  w.cur += bytes;
+  return off;
+}
+
+// one function's part of a row's record, written by that chain's warp (layout: see StorePool)
+template <bool SH>
+PSD_DEV void store_write_fn(const WarpWs ws, unsigned char* rec, int row, const PList L, int which, int n_up, int n_down) {
+  if (SH) PSD_ASSUME_SHARED(L.base);
+  const int lane = psd_lane();
+  const int cap = ws.cap;
+  if (which == 0 && lane == 0) psd_st_cs_u4((unsigned*)rec, (unsigned)n_up, (unsigned)n_down, (unsigned)row, 0u);
+  double* pairs = (double*)(rec + 16) + (which ? 2 * n_up : 0);
+  int* bis = (int*)((double*)(rec + 16) + 2 * (n_up + n_down)) + (which ? n_up : 0);
+  for (int k = lane; k < L.n; k += 32) {
+    psd_st_cs_d2(pairs + 2 * k, PL_X(L, k), PL_P(L, k));
+    psd_st_cs_i(bis + k, PL_I(L, k));
+  }
+}
+
+PSD_DEV void dp_run_latency(const WarpWs& ws_s, const WarpWs& ws_g, const DpProblem& pb, DpResult* res, const StorePool& sp, LatShared* sh
+#if defined(PSD_EMU)
+                            , psd_trace_fn trace, void* trace_user
+#endif
+) {
+  const int lane = psd_lane();
+  const int grp = psd_warp_in_block();   // 0: up chain (min_less), 1: down chain (min_more)
+  const int N = pb.n_rows;
+  const int* weight = pb.weight; const int* coverage = pb.coverage; unsigned long long* index = pb.index;
+  const double penalty = pb.penalty, dmin = pb.dmin, dmax = pb.dmax;
+  int t = 0, status = PSD_ST_OK, max_iv = 0, w_l = 0, z_l = 0, n_spill = 0;
+  double cw = 0, cw_done = 0.0;
+  unsigned long long total_iv = 0, my_off = 0;
+  bool in_g = ws_s.cap == 0;
+  WarpWs ws, wg;
+  PList upP, downP, upN, downN, tmp;
+  upP.n = downP.n = upN.n = downN.n = tmp.n = 0;
+  // four flag words (the workspace header): [2 * row parity + chain].  A warp only ever writes its own
+  // words; the words of row t are read by both warps after row t's barrier and zeroed by their
+  // owner at the start of row t + 2, one barrier later.
+  int* const flag_words = ws_s.flags;
+#define PSD_BIND_TIER()                                                                              \
+  do {                                                                                               \
+    ws = in_g ? ws_g : ws_s;                                                                         \
+    wg = ws;                                                                                         \
+    wg.scratch = ws_scratch0(ws) + (unsigned long long)grp * PSD_WS_SCRATCH_BYTES(ws.cap, ws.ccap);  \
+    wg.flags = flag_words + 2 * (t & 1) + grp;                                                       \
+    upP.base = ws_list(ws, 0); downP.base = ws_list(ws, 1); upN.base = ws_list(ws, 2);               \
+    downN.base = ws_list(ws, 3); tmp.base = ws_list(ws, 4 + grp);                                    \
+  } while (0)
+  PSD_BIND_TIER();
+  StoreWriter sw; sw.cur = 0; sw.end = 0;
+  Rescale rs; rs.mul = rs.add_a = rs.add_b = rs.inv = 0;
+  for (;;) {
+    wg.flags = flag_words + 2 * (t & 1) + grp;
+    if (lane == 0) *wg.flags = 0;
+    psd_syncwarp();
+    if ((t & 31) == 0) {   // coalesced load of the next 32 rows (both warps keep their own copy)
+      const int r = t + lane;
+      w_l = (r < N) ? weight[r] : 0;
+      z_l = (r < N) ? coverage[r] : 0;
+    }
+    const int wi = psd_shfl_i(w_l, t & 31), z = psd_shfl_i(z_l, t & 31);
+    const double w = (double)wi;
+    cw = cw_done + w;
+    rs.mul = cw_done; rs.add_a = w; rs.add_b = (double)(-z) * w; rs.inv = 1 / cw;
+    int n_out = 0;
+    if (t == 0) {
+      if (grp == 1 && lane == 0) pl_emit(wg, downP, 0, 1.0, (double)(-z), 0.0, dmax, -5.0, -1);
+      downP.n = 1; upP.n = 0;
+    } else {
+      // my chain of row t: min_less(down_{t-1}) / min_more(up_{t-1}), then the envelope with my own
+      // previous function; nothing here depends on what the other warp computes for row t
+      if (grp == 0 || t >= 2)
+        tmp.n = in_g ? min_mono_op<false>(wg, grp ? upP : downP, tmp, dmin, t - 1, penalty / cw_done, grp)
+                     : min_mono_op<true>(wg, grp ? upP : downP, tmp, dmin, t - 1, penalty / cw_done, grp);
+      const PList prev = grp ? downP : upP;
+      const PList dst = grp ? downN : upN;
+      if (t == 1) n_out = in_g ? copy_rescale_op<false>(wg, grp ? downP : tmp, dst, rs) : copy_rescale_op<true>(wg, grp ? downP : tmp, dst, rs);
+      else n_out = in_g ? min_env_op<false>(wg, tmp, prev, tmp, prev, dst, dmin, rs) : min_env_op<true>(wg, tmp, prev, tmp, prev, dst, dmin, rs);
+      if (lane == 0) sh->n_out[t & 1][grp] = n_out;
+    }
+    psd_cta_sync();   // the row's one barrier: both new functions are complete and visible
+    const int flags = ((volatile int*)flag_words)[2 * (t & 1)] | ((volatile int*)flag_words)[2 * (t & 1) + 1];
+    bool redo = false;
+    if (flags) {
+      if ((flags & PSD_FLAG_OVERFLOW) && !(flags & PSD_FLAG_INTERNAL) && !in_g && ws_g.cap > 0) {
+        // this row does not fit the shared-memory tier: repeat it from the global workspace
+        if (grp == 0) pl_move(upP.base, ws_s.cap, ws_list(ws_g, 0), ws_g.cap, upP.n);
+        else pl_move(downP.base, ws_s.cap, ws_list(ws_g, 1), ws_g.cap, downP.n);
+        in_g = true; n_spill++;
+        PSD_BIND_TIER();
+        psd_cta_sync();   // both warps have read the flag words and moved their function
+        redo = true;
+      } else {
+        status = (flags & PSD_FLAG_INTERNAL) ? PSD_ST_INTERNAL : PSD_ST_PIECE_OVERFLOW;
+      }
+    }
+    if (redo) continue;
+    if (status == PSD_ST_OK) {
+      if (t >= 1) {   // the new functions become the previous ones
+        upN.n = ((volatile int*)sh->n_out[t & 1])[0];
+        downN.n = ((volatile int*)sh->n_out[t & 1])[1];
+        const PList u = upP, d = downP;
+        upP = upN; downP = downN; upN = u; downN = d;
+      }
+      cw_done = cw;
+      total_iv += (unsigned long long)(upP.n + downP.n);
+      if (max_iv < upP.n) max_iv = upP.n;
+      if (max_iv < downP.n) max_iv = downP.n;
+#if defined(PSD_EMU)
+      if (trace && lane == 0 && grp == 0) { trace(trace_user, t, 0, upP.n, ws.cap, upP.base); trace(trace_user, t, 1, downP.n, ws.cap, downP.base); }
+#endif
+      const unsigned long long off = store_alloc_cta(sp, sw, store_record_bytes(upP.n, downP.n), sh, grp);
+      if (off == ~0ull) status = PSD_ST_STORE_EXHAUSTED;
+      else {
+        if (in_g) store_write_fn<false>(ws, store_ptr(sp, off), t, grp ? downP : upP, grp, upP.n, downP.n);
+        else store_write_fn<true>(ws, store_ptr(sp, off), t, grp ? downP : upP, grp, upP.n, downP.n);
+        if (grp == 0) {
+          if (lane == (t & 31)) my_off = off;
+          if ((t & 31) == 31 || t == N - 1) {
+            const int r = (t & ~31) + lane;
+            if (r <= t) psd_st_cs_u64(index + r, my_off);
+          }
+        }
+      }
+    }
+    t++;
+    if (status != PSD_ST_OK || t == N) {
+      if (grp == 0) {
+        double bc = 0, bx = 0, bpx = 0; int bbi = -1;
+        if (status == PSD_ST_OK) best_piece(ws, downP, dmin, &bc, &bx, &bbi, &bpx);
+        if (lane == 0) {
+          res->status = status; res->back_i = bbi; res->best_cost = bc; res->best_x = bx; res->back_x = bpx;
+          res->total_intervals = total_iv; res->max_intervals = max_iv; res->n_segments = 0; res->n_equality = 0;
+          res->pad_ = n_spill;
+        }
+      }
+      break;
+    }
+    if (in_g && ws_s.cap > 0 && PSD_RETURN_DEN * upP.n <= PSD_RETURN_NUM * ws_s.cap && PSD_RETURN_DEN * downP.n <= PSD_RETURN_NUM * ws_s.cap) {
+      // both functions fit comfortably again: move back to shared memory
+      if (grp == 0) pl_move(upP.base, ws_g.cap, ws_list(ws_s, 0), ws_s.cap, upP.n);
+      else pl_move(downP.base, ws_g.cap, ws_list(ws_s, 1), ws_s.cap, downP.n);
+      in_g = false;
+      PSD_BIND_TIER();
+      psd_cta_sync();
+    }
+  }
+#undef PSD_BIND_TIER
+}
+#endif   // PSD_G32
 
 // ---- decode (src/PeakSegFPOPLog.cpp:400-442 + findMean :643-653) ------------------------------------
 // Walks the stored functions from the last row back.  Output, last segment first:

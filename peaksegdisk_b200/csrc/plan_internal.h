@@ -64,6 +64,7 @@ const psd_stats& psd_plan_stats_ref(const psd_plan* p);
 int psd_plan_upload_impl(psd_plan* p, void* stream);
 int psd_plan_solve_impl(psd_plan* p, void* stream);
 int psd_plan_download_impl(psd_plan* p, void* stream);
+int psd_plan_store_function_impl(psd_plan* p, int id, int row, int which, int cap, int* n_out, double* hi, int* back_i, double* back_x);
 int psd_device_count_impl();
 int psd_set_option_impl(const char* name, double value);
 int psd_option_devices();                      // option "devices" / env PSD_DEVICES: GPUs one batched file call may use

@@ -115,6 +115,17 @@ class Plan:
             raise RuntimeError(_lib.status_text(rc))
         return s, e, k, m
 
+    def store_function(self, pid, row, which, cap=65536):
+        """The stored cost function `which` (0 up, 1 down) of row `row`: (max_log_mean, data_i,
+        prev_log_mean) arrays, the fields of the reference's db record (src/PeakSegFPOPLog.cpp:18-34)."""
+        n = C.c_int32(0)
+        hi = np.zeros(cap); bi = np.zeros(cap, np.int32); bx = np.zeros(cap)
+        rc = _lib.lib.psd_plan_store_function(self._h, pid, row, which, cap, C.byref(n), hi.ctypes.data_as(C.POINTER(C.c_double)),
+                                              bi.ctypes.data_as(C.POINTER(C.c_int32)), bx.ctypes.data_as(C.POINTER(C.c_double)))
+        if rc:
+            raise RuntimeError(_lib.status_text(rc))
+        return hi[:n.value].copy(), bi[:n.value].copy(), bx[:n.value].copy()
+
     def stats(self):
         st = _lib.PsdStats()
         _lib.lib.psd_plan_get_stats(self._h, C.byref(st))

@@ -13,7 +13,20 @@ struct Job {
   psd_trace_fn trace; void* trace_user;
   int* seg_row; double* seg_x;
   int order0 = 0; int cursor = 1;
+#if defined(PSD_G32)
+  LatShared lat;
+#endif
 };
+#if defined(PSD_G32)
+// latency kernel: a block of two warps owns the problem (one chain per warp); the backtrack is one warp
+void lane_main(void* arg) {
+  Job* J = (Job*)arg;
+  dp_run_latency(J->ws, J->ws_g, J->pb, J->res, J->sp, &J->lat, J->trace, J->trace_user);
+  psd_cta_sync();
+  if (psd_warp_in_block() == 0) backtrack_problem(J->sp, J->pb.index, J->pb.n_rows, J->res, J->seg_row, J->seg_x);
+}
+#define PSD_EMU_WARPS 2
+#else
 void lane_main(void* arg) {
   Job* J = (Job*)arg;
   DpQueue Q;
@@ -22,6 +35,8 @@ void lane_main(void* arg) {
   psd_syncwarp();
   backtrack_problem(J->sp, J->pb.index, J->pb.n_rows, J->res, J->seg_row, J->seg_x);
 }
+#define PSD_EMU_WARPS 1
+#endif
 }  // namespace
 
 #if defined(PSD_EMU_STATS)
@@ -78,7 +93,7 @@ int emu_fpop_rows(int n_rows, const int* chrom_start, const int* chrom_end, cons
   J.res = &res; J.trace = trace; J.trace_user = trace_user;
   std::vector<int> seg_row(n_rows + 1); std::vector<double> seg_x(n_rows + 1);
   J.seg_row = seg_row.data(); J.seg_x = seg_x.data();
-  psd_emu::run_warp(lane_main, &J, descending);
+  psd_emu::run_block(lane_main, &J, PSD_EMU_WARPS, descending);
   if (res.status != 0) return res.status;
   const int ns = res.n_segments, np = (ns - 1) / 2;
   out_summary[0] = penalty; out_summary[1] = ns; out_summary[2] = np; out_summary[3] = W; out_summary[4] = n_rows;

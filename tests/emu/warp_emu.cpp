@@ -43,11 +43,10 @@ static void die(Warp& w, const char* what) {
   abort();
 }
 
-void run_warp(void (*entry)(void*), void* arg, int descending) {
+static void init_warp(Warp& w, void (*entry)(void*), void* arg, int descending, int warp_id, int n_warps) {
   static const size_t kStack = 1 << 20;
-  Warp w;
   memset(&w, 0, sizeof w);
-  w.entry = entry; w.arg = arg; w.descending = descending;
+  w.entry = entry; w.arg = arg; w.descending = descending; w.warp_id = warp_id; w.n_warps = n_warps;
   for (int i = 0; i < 32; i++) {
     w.f[i].stack = (char*)aligned_alloc(64, kStack);
     uintptr_t top = ((uintptr_t)w.f[i].stack + kStack) & ~(uintptr_t)63;
@@ -60,49 +59,80 @@ void run_warp(void (*entry)(void*), void* arg, int descending) {
     w.f[i].state = RUNNABLE;
     w.f[i].site = -1;
   }
-  Warp* outer = g_warp;
+}
+
+// One scheduling step of a warp: run every runnable lane to its next collective, then release the
+// groups / the warp whose lanes all wait at the same call site.  Returns true on progress.
+static bool step_warp(Warp& w) {
+  bool progress = false;
   g_warp = &w;
-  for (;;) {
-    bool progress = false;
-    for (int k = 0; k < 32; k++) {
-      const int i = descending ? 31 - k : k;
-      if (w.f[i].state != RUNNABLE) continue;
-      w.cur = i;
-      psd_emu_switch(&w.sched_sp, w.f[i].sp);
+  for (int k = 0; k < 32; k++) {
+    const int i = w.descending ? 31 - k : k;
+    if (w.f[i].state != RUNNABLE) continue;
+    w.cur = i;
+    psd_emu_switch(&w.sched_sp, w.f[i].sp);
+    progress = true;
+  }
+  // release a 16-lane group whose lanes all wait at the same group collective
+  for (int g = 0; g < 2; g++) {
+    bool all = true;
+    const int site = w.f[16 * g].site;
+    for (int i = 16 * g; i < 16 * g + 16; i++) all = all && w.f[i].state == WAIT_GROUP && w.f[i].site == site;
+    if (all) {
+      for (int i = 16 * g; i < 16 * g + 16; i++) w.f[i].state = RUNNABLE;
+      w.phase_g[g]++;
+      progress = true;
+    } else {
+      int n_wait = 0;
+      for (int i = 16 * g; i < 16 * g + 16; i++) n_wait += w.f[i].state == WAIT_GROUP;
+      if (n_wait == 16) die(w, "divergent group collective (lanes of one group wait at different lines)");
+    }
+  }
+  // release the warp when all lanes wait at the same whole-warp collective
+  {
+    bool all = true;
+    const int site = w.f[0].site;
+    for (int i = 0; i < 32; i++) all = all && w.f[i].state == WAIT_FULL && w.f[i].site == site;
+    if (all) {
+      for (int i = 0; i < 32; i++) w.f[i].state = RUNNABLE;
+      w.phase_full++;
       progress = true;
     }
-    int n_done = 0;
-    for (int i = 0; i < 32; i++) n_done += w.f[i].state == DONE;
-    if (n_done == 32) break;
-    // release a 16-lane group whose lanes all wait at the same group collective
-    for (int g = 0; g < 2; g++) {
-      bool all = true;
-      const int site = w.f[16 * g].site;
-      for (int i = 16 * g; i < 16 * g + 16; i++) all = all && w.f[i].state == WAIT_GROUP && w.f[i].site == site;
-      if (all) {
-        for (int i = 16 * g; i < 16 * g + 16; i++) w.f[i].state = RUNNABLE;
-        w.phase_g[g]++;
-        progress = true;
-      } else {
-        int n_wait = 0;
-        for (int i = 16 * g; i < 16 * g + 16; i++) n_wait += w.f[i].state == WAIT_GROUP;
-        if (n_wait == 16) die(w, "divergent group collective (lanes of one group wait at different lines)");
+  }
+  return progress;
+}
+
+void run_block(void (*entry)(void*), void* arg, int n_warps, int descending) {
+  Warp* ws = new Warp[n_warps];
+  for (int k = 0; k < n_warps; k++) init_warp(ws[k], entry, arg, descending, k, n_warps);
+  Warp* outer = g_warp;
+  for (;;) {
+    bool progress = false;
+    // warps advance in ascending or descending order too: a missing block barrier between a write
+    // by one warp and a read by another shows up in one of the two orders
+    for (int k = 0; k < n_warps; k++) progress = step_warp(ws[descending ? n_warps - 1 - k : k]) || progress;
+    int n_done = 0, n_bar = 0, site = -2;
+    bool same_site = true;
+    for (int k = 0; k < n_warps; k++)
+      for (int i = 0; i < 32; i++) {
+        const Fiber& f = ws[k].f[i];
+        n_done += f.state == DONE;
+        if (f.state == WAIT_BLOCK) { n_bar++; if (site == -2) site = f.site; else same_site = same_site && f.site == site; }
       }
+    if (n_done == 32 * n_warps) break;
+    if (n_bar > 0 && n_bar + n_done == 32 * n_warps) {
+      if (!same_site || n_done > 0) die(ws[0], "divergent block barrier (lanes wait at different lines, or some lanes have exited)");
+      for (int k = 0; k < n_warps; k++)
+        for (int i = 0; i < 32; i++) ws[k].f[i].state = RUNNABLE;
+      progress = true;
     }
-    // release the warp when all lanes wait at the same whole-warp collective
-    {
-      bool all = true;
-      const int site = w.f[0].site;
-      for (int i = 0; i < 32; i++) all = all && w.f[i].state == WAIT_FULL && w.f[i].site == site;
-      if (all) {
-        for (int i = 0; i < 32; i++) w.f[i].state = RUNNABLE;
-        w.phase_full++;
-        progress = true;
-      }
-    }
-    if (!progress) die(w, "deadlock: no lane can run and no collective is complete");
+    if (!progress) die(ws[0], "deadlock: no lane can run and no collective is complete");
   }
   g_warp = outer;
-  for (int i = 0; i < 32; i++) free(w.f[i].stack);
+  for (int k = 0; k < n_warps; k++)
+    for (int i = 0; i < 32; i++) free(ws[k].f[i].stack);
+  delete[] ws;
 }
+
+void run_warp(void (*entry)(void*), void* arg, int descending) { run_block(entry, arg, 1, descending); }
 }  // namespace psd_emu

@@ -18,7 +18,7 @@
 
 namespace psd_emu {
 
-enum { RUNNABLE = 0, WAIT_GROUP = 1, WAIT_FULL = 2, DONE = 3 };
+enum { RUNNABLE = 0, WAIT_GROUP = 1, WAIT_FULL = 2, DONE = 3, WAIT_BLOCK = 4 };
 struct Fiber { void* sp; char* stack; int state; int site; };
 struct Warp {
   Fiber f[32];
@@ -31,12 +31,16 @@ struct Warp {
   void (*entry)(void*);
   void* arg;
   int descending;
+  int warp_id;     // index of this warp in its block (run_block); 0 for run_warp
+  int n_warps;
 };
 extern Warp* g_warp;
 
 extern "C" void psd_emu_switch(void** save_sp, void* load_sp);
 
 inline int lane() { return g_warp->cur; }
+inline int warp_id() { return g_warp->warp_id; }
+inline int n_warps() { return g_warp->n_warps; }
 
 inline void block(int kind, int site) {
   Warp* w = g_warp;
@@ -82,6 +86,9 @@ inline uint32_t g_ballot(int pred, int site) {
 }
 
 void run_warp(void (*entry)(void*), void* arg, int descending);
+// A thread block of n_warps warps (the latency kernel: the warps of one problem).  Block barriers
+// (block(WAIT_BLOCK, site)) release when every lane of every warp waits at the same call site.
+void run_block(void (*entry)(void*), void* arg, int n_warps, int descending);
 
 }  // namespace psd_emu
 
@@ -91,10 +98,17 @@ void run_warp(void (*entry)(void*), void* arg, int descending);
 #define PSD_SITE __LINE__
 
 static inline int psd_lane() { return psd_emu::lane(); }
+#if defined(PSD_G32)
+static inline int psd_glane() { return psd_emu::lane(); }
+#else
 static inline int psd_glane() { return psd_emu::lane() & 15; }
+#endif
 static inline uint64_t psd_bits_(double v) { uint64_t u; memcpy(&u, &v, 8); return u; }
 static inline double psd_dbl_(uint64_t u) { double v; memcpy(&v, &u, 8); return v; }
 
+// block barrier (multi-warp blocks only; with one warp it degenerates to a warp barrier)
+#define psd_cta_sync() psd_emu::block(psd_emu::WAIT_BLOCK, PSD_SITE)
+static inline int psd_warp_in_block() { return psd_emu::warp_id(); }
 // whole-warp collectives
 #define psd_shfl_d(v, src) psd_dbl_(psd_emu::exchange(psd_bits_(v), (src), PSD_SITE))
 #define psd_shfl_i(v, src) ((int)(int64_t)psd_emu::exchange((uint64_t)(int64_t)(v), (src), PSD_SITE))
@@ -104,6 +118,17 @@ static inline double psd_dbl_(uint64_t u) { double v; memcpy(&v, &u, 8); return 
 #define psd_shfl_up_i(v, d) ((int)(int64_t)psd_emu::exchange((uint64_t)(int64_t)(v), (psd_lane() - (d) < 0 ? psd_lane() : psd_lane() - (d)), PSD_SITE))
 #define psd_ballot(p) psd_emu::ballot((p), PSD_SITE)
 #define psd_syncwarp() psd_emu::block(psd_emu::WAIT_FULL, PSD_SITE)
+#if defined(PSD_G32)
+// one operator group per warp (latency kernel): group collectives are whole-warp collectives
+static inline int psd_glane32_() { return psd_emu::lane(); }
+#define psd_g_shfl_d(v, src) psd_dbl_(psd_emu::exchange(psd_bits_(v), (src), PSD_SITE))
+#define psd_g_shfl_i(v, src) ((int)(int64_t)psd_emu::exchange((uint64_t)(int64_t)(v), (src), PSD_SITE))
+#define psd_g_shfl_up_d(v, d) psd_dbl_(psd_emu::exchange(psd_bits_(v), (psd_lane() - (d) < 0 ? psd_lane() : psd_lane() - (d)), PSD_SITE))
+#define psd_g_shfl_down_d(v, d) psd_dbl_(psd_emu::exchange(psd_bits_(v), (psd_lane() + (d) > 31 ? psd_lane() : psd_lane() + (d)), PSD_SITE))
+#define psd_g_shfl_up_i(v, d) ((int)(int64_t)psd_emu::exchange((uint64_t)(int64_t)(v), (psd_lane() - (d) < 0 ? psd_lane() : psd_lane() - (d)), PSD_SITE))
+#define psd_g_ballot(p) psd_emu::ballot((p), PSD_SITE)
+#define psd_g_sync() psd_emu::block(psd_emu::WAIT_FULL, PSD_SITE)
+#else
 // 16-lane group collectives; up/down: lanes whose source falls outside the group keep their value
 #define psd_g_shfl_d(v, src) psd_dbl_(psd_emu::g_exchange(psd_bits_(v), (src), PSD_SITE))
 #define psd_g_shfl_i(v, src) ((int)(int64_t)psd_emu::g_exchange((uint64_t)(int64_t)(v), (src), PSD_SITE))
@@ -112,6 +137,7 @@ static inline double psd_dbl_(uint64_t u) { double v; memcpy(&v, &u, 8); return 
 #define psd_g_shfl_up_i(v, d) ((int)(int64_t)psd_emu::g_exchange((uint64_t)(int64_t)(v), (psd_glane() - (d) < 0 ? psd_glane() : psd_glane() - (d)), PSD_SITE))
 #define psd_g_ballot(p) psd_emu::g_ballot((p), PSD_SITE)
 #define psd_g_sync() psd_emu::block(psd_emu::WAIT_GROUP, PSD_SITE)
+#endif
 
 static inline int psd_ffs(uint32_t m) { return __builtin_ffs((int)m); }
 static inline int psd_clz(uint32_t m) { return m ? __builtin_clz(m) : 32; }

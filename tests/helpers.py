@@ -52,12 +52,28 @@ def loss_fields(line):
             "mean_intervals": float(f[8]), "max_intervals": float(f[9])}
 
 
-def c4_lite_problems(samples=2, scale=0.05):
-    """BASELINE config 4 at reduced scale: 24 hg19-shaped chromosomes x `samples`
-    samples, rows proportional to chromosome length (chr1 = 1e7 * scale), Mono27ac-like weights
-    (clipped to 2,000 bases so tiled coordinates stay below 2^31), one penalty per problem.
-    Returns [(chromStart, chromEnd, coverage, penalty)] in (chromosome, sample) order."""
+_MONO_ROWS = None
+
+
+def _mono_rows():
+    global _MONO_ROWS
+    if _MONO_ROWS is None:
+        from peaksegdisk_b200 import synth
+        _, s0, e0, c0 = synth.read_bedgraph(os.path.join(GOLD, "Mono27ac_coverage.bedGraph"))
+        _MONO_ROWS = (np.minimum((e0 - s0).astype(np.int64), 2000), c0.astype(np.float64))
+    return _MONO_ROWS
+
+
+def c4_lite_problem(k, samples=2, scale=0.05):
+    """Problem k (= chromosome * samples + sample) of BASELINE config 4 at reduced scale (SURVEY.md 8d,
+    C4): rows proportional to the hg19 chromosome length (chr1 = 1e7 * scale), Mono27ac-like weights
+    (clipped to 2,000 bases so tiled coordinates stay below 2^31), its own penalty.
+    Returns (chromStart, chromEnd, coverage, penalty)."""
     from peaksegdisk_b200 import synth
-    _, s0, e0, c0 = synth.read_bedgraph(os.path.join(GOLD, "Mono27ac_coverage.bedGraph"))
-    w0 = np.minimum((e0 - s0).astype(np.int64), 2000)
-    return [synth.hg19_problem(ci, si, w0, c0.astype(np.float64), scale_rows=scale) for ci in range(24) for si in range(samples)]
+    w0, c0 = _mono_rows()
+    return synth.hg19_problem(k // samples, k % samples, w0, c0, scale_rows=scale)
+
+
+def c4_lite_problems(samples=2, scale=0.05):
+    """All 24 x `samples` problems of config 4 lite, in (chromosome, sample) order."""
+    return [c4_lite_problem(k, samples, scale) for k in range(24 * samples)]

@@ -25,6 +25,18 @@ def psd():
     return peaksegdisk_b200
 
 
+@pytest.fixture(autouse=True, params=[0.0, 2.0], ids=["auto", "throughput-kernel"])
+def kernel_mode(request, psd):
+    """Every test runs twice: with the automatic choice (small waves go to the latency kernel: one
+    problem per block, one chain per warp) and with the throughput kernel forced (one problem per
+    warp), so both kernels see every parity case."""
+    psd._lib.lib.psd_set_option(b"latency_mode", request.param)
+    os.environ["PSD_LATENCY_MODE"] = str(int(request.param))     # subprocess tools
+    yield request.param
+    psd._lib.lib.psd_set_option(b"latency_mode", 0.0)
+    os.environ.pop("PSD_LATENCY_MODE", None)
+
+
 def _disk(psd, path, pen, db=None):
     return psd._lib.lib.psd_fpop_disk(path.encode(), pen.encode(), (db or path + ".db").encode())
 
@@ -442,6 +454,34 @@ def test_reference_style_caller_runs_the_gpu_solver(psd, tmp_path):
     assert out.returncode == 0, out.stdout + out.stderr
     assert outputs(bg, "10.5") == (case["segments"], case["loss"])
     assert os.path.getsize(bg + ".db") > 0      # R reports its size as `megabytes` and deletes it
+
+
+def test_reference_interface_cpp_runs_the_gpu_solver(psd, tmp_path):
+    """The reference's OWN R glue -- src/interface.cpp compiled UNMODIFIED in the build container
+    (oracle/Makefile `interface`: R-header shim + a driver that plays R's .C()) and linked against
+    libpeaksegdisk_b200.so -- on the DP branch: R_init_PeakSegDisk registers the routine,
+    PeakSegFPOP_interface(char**, char**, char**) calls PeakSegFPOP_disk, the GPU solves, and the
+    files equal the reference's; an unwritable db surfaces as interface.cpp's Rf_error text."""
+    import subprocess
+    exe = os.path.join(ROOT, "oracle", "_ref", "ref_interface_b200")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/ref_interface_b200 not built (make -C oracle interface; needs /root/reference)")
+    env = dict(os.environ, PSD_LATENCY_MODE=os.environ.get("PSD_LATENCY_MODE", "0"))
+    for case in [c for c in golden("golden_small.json") if c["name"] in ("four", "hap3", "supp") and c["status"] == 0]:
+        bg = str(tmp_path / ("%s.bedGraph" % case["name"]))
+        open(bg, "w").write(case["input"])
+        out = subprocess.run([exe, bg, case["penalty"], bg + ".db"], capture_output=True, text=True, env=env)
+        assert out.returncode == 0 and out.stdout.endswith("ok\n"), (case["name"], case["penalty"], out.stderr)
+        assert outputs(bg, case["penalty"]) == (case["segments"], case["loss"]), (case["name"], case["penalty"])
+    g = golden("golden_mono27ac.json")["penalties"]["10.5"]
+    bg = str(tmp_path / "coverage.bedGraph")
+    open(bg, "w").write(open(os.path.join(GOLD, "Mono27ac_coverage.bedGraph")).read())
+    out = subprocess.run([exe, bg, "10.5", bg + ".db"], capture_output=True, text=True, env=env)
+    assert out.returncode == 0, out.stderr
+    seg, loss = outputs(bg, "10.5")
+    assert loss == g["loss"] and sha(seg) == g["segments_sha256"]
+    out = subprocess.run([exe, bg, "10.5", str(tmp_path)], capture_output=True, text=True, env=env)   # db path is a directory
+    assert out.returncode == 1 and out.stderr == "Error: unable to write to cost function database file %s\n" % str(tmp_path)
 
 
 def test_concurrent_single_problem_calls_from_host_threads(psd, tmp_path):

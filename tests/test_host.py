@@ -170,3 +170,63 @@ def test_reference_style_caller_links_against_the_library(tmp_path):
     assert outputs(bg, "Inf") == (case["segments"], case["loss"])
     out = subprocess.run([exe, bg, "-1", bg + ".db"], capture_output=True, text=True)
     assert out.returncode == 2
+
+
+@pytest.mark.parametrize("fixture,key,target", [("golden_fullsize.json", "c3", 100), ("golden_fullsize.json", "c3s", 30),
+                                                ("golden_mono27ac.json", "search19", 19)])
+def test_search_state_machine_follows_the_reference_chain(tmp_path, fixture, key, target):
+    """R/sequentialSearch_dir.R:31-98 on the host: fed with the reference's own _loss.tsv lines (the
+    1.0 M-row config-3 problem, the 75,892-row one, Mono27ac) the search must ask for exactly the
+    reference's next penalty string at every step -- the %.20g fields are parsed with correct
+    rounding, the quotient is formatted like R's paste()."""
+    import json
+    from peaksegdisk_b200 import api
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", fixture)))[key]
+    chain = g["chain"] if isinstance(g, dict) else g
+    by_pen = {c["penalty_str"]: c for c in chain}
+    st = api._Search("unused", target)
+    asked = []
+    while st.next_pen:
+        fits = []
+        for _, pen in st.requests():
+            asked.append(pen)
+            assert pen in by_pen, "the search asked for %s, which the reference never solved" % pen
+            f = tmp_path / "loss.tsv"
+            f.write_text(by_pen[pen]["loss"])
+            fits.append({"loss": api._read_loss(str(f))})
+        st.update(fits)
+    assert sorted(asked) == sorted(by_pen)
+    assert int(st.candidate["peaks"]) == chain[-1]["peaks"] and api.r_paste(float(st.candidate["penalty"])) == chain[-1]["penalty_str"]
+
+
+IFACE_BIN = os.path.join(ROOT, "oracle", "_ref", "ref_interface_b200")
+
+
+@pytest.mark.skipif(not os.path.exists(IFACE_BIN), reason="oracle/_ref/ref_interface_b200 not built (make -C oracle interface; needs /root/reference)")
+def test_reference_interface_cpp_linked_against_the_library(tmp_path):
+    """The reference's OWN src/interface.cpp (compiled unmodified by oracle/Makefile with an R-header
+    shim) linked against libpeaksegdisk_b200.so: R_init_PeakSegDisk registers the .C routine, the
+    driver calls PeakSegFPOP_interface(char**, char**, char**) as R's .C() does, and every input error
+    surfaces as the Rf_error text tests/testthat/test-CRAN-cpp-errors.R expects.  (Branches that end
+    before the DP need no GPU; the DP branch is covered by the -m gpu test of the same binary.)"""
+    import subprocess
+    from peaksegdisk_b200 import _lib
+    dbdir = tmp_path / "dbdir"
+    dbdir.mkdir()
+    n = 0
+    for k, case in enumerate(golden("golden_errors.json")):
+        if case["status"] == 0 and case["penalty"] != "Inf":
+            continue          # DP branch: needs the GPU
+        path = str(tmp_path / ("e%d.bedGraph" % k))
+        if not case["missing"]:
+            open(path, "w").write(case["input"])
+        db = str(dbdir) if case["db"] else path + ".db"
+        out = subprocess.run([IFACE_BIN, path, case["penalty"], db], capture_output=True, text=True)
+        if case["status"] == 0:
+            assert out.returncode == 0 and out.stdout.endswith("ok\n"), case["name"]
+        else:
+            assert out.returncode == 1, (case["name"], out.stderr)
+            assert out.stderr == "Error: " + _lib.status_text(case["status"], path, case["penalty"], db) + "\n", case["name"]
+        assert outputs(path, case["penalty"]) == (case["segments"], case["loss"]), case["name"]
+        n += 1
+    assert n >= 15
