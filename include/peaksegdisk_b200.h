@@ -99,6 +99,7 @@ typedef struct psd_stats {
   int64_t rle_bytes_algorithmic;    /* 4 B per position read + 12 B per row written */
   int32_t n_latency_waves;          /* waves of the last solve that ran the latency kernel (one problem per block) */
   int32_t pad_;
+  int64_t store_bytes_drained_dma;  /* of the spilled bytes: copied HBM ring -> pinned host by cudaMemcpyAsync on the side stream */
 } psd_stats;
 
 /* device < 0 selects the current CUDA device. */
@@ -133,6 +134,20 @@ int psd_plan_get_stats(const psd_plan *plan, psd_stats *out);
 /* Replaces problem id's penalty (used by the sequential search to re-solve the same rows). */
 int psd_plan_set_penalty(psd_plan *plan, int id, double penalty, int penalty_is_inf);
 
+/* Where the wall time of the process's last psd_fpop_disk / psd_fpop_disk_batch call went. */
+typedef struct psd_batch_stats {
+  double parse_ms;           /* bedGraph text -> rows (distinct files on all host cores) + penalty parsing */
+  double build_ms;           /* pass-1 totals, output files created, scratch db files */
+  double run_ms;             /* upload + DP + backtrack + download (wall) */
+  double write_ms;           /* _segments.bed / _loss.tsv rendered and written */
+  double release_ms;
+  double dp_ms, backtrack_ms;      /* device time inside run_ms (max over the GPUs used) */
+  int64_t rows_parsed, rows_solved;
+  int64_t h2d_bytes, d2h_bytes, store_bytes_algorithmic;
+  int32_t n_problems, n_files_parsed, n_devices, n_launches, n_waves, n_latency_waves;
+} psd_batch_stats;
+int psd_last_batch_stats(psd_batch_stats *out);
+
 /* Writes rows as the 4-column bedGraph text R/writeBedGraph.R:35-37 produces (tab separated, no
  * header, one "chrom\tchromStart\tchromEnd\tcount" line per row).  Returns 0 or PSD_ERR_ARG when the
  * file cannot be written. */
@@ -151,6 +166,8 @@ int psd_plan_store_function(psd_plan *plan, int id, int row, int which, int cap,
  * "overflow_cap" (global tier, default 8192), "store_gb" (HBM pool, default 0 = auto),
  * "chunk_kb" (store chunk, default 64), "spill_cap" (per-warp global workspace, default 512),
  * "host_spill_gb" (pinned-host overflow of the store: -1 = automatic, 0 = off),
+ * "spill_mode" (how spilled records reach the host: 0 = written into an HBM ring that a host thread drains
+ * with cudaMemcpyAsync on a side stream (default), 1 = zero-copy stores through the mapping), "ring_gb",
  * "occupancy_mode" (0 = choose per batch, 1 = one block of 14 warps per SM, 2 = two blocks),
  * "latency_mode" (0 = waves of at most "latency_max_blocks" (default 2) problems per SM run the latency
  * kernel: one problem per block, one chain per warp; 1 = always; 2 = never),
@@ -161,7 +178,7 @@ int psd_set_option(const char *name, double value);
 int psd_device_count(void);
 
 /* psd_fpop_disk / psd_fpop_disk_batch keep the plan of their last call parked (device buffers, store
- * pool and pinned staging, up to 32 GB of HBM) so that the next call does not allocate again; this
+ * pool and pinned staging, up to 100 GB of HBM) so that the next call does not allocate again; this
  * frees it.  Safe to call at any time from any thread. */
 void psd_release_cache(void);
 

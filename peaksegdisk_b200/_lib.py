@@ -25,14 +25,23 @@ class PsdStats(C.Structure):
                 ("n_launches", C.c_int32), ("n_waves", C.c_int32), ("n_overflow_tier", C.c_int32),
                 ("piece_cap", C.c_int32), ("warps_per_sm", C.c_int32), ("n_sm", C.c_int32),
                 ("n_rle_launches", C.c_int32), ("rle_ms", C.c_double), ("rle_positions", C.c_int64),
-                ("rle_bytes_algorithmic", C.c_int64), ("n_latency_waves", C.c_int32), ("pad_", C.c_int32)]
+                ("rle_bytes_algorithmic", C.c_int64), ("n_latency_waves", C.c_int32), ("pad_", C.c_int32),
+                ("store_bytes_drained_dma", C.c_int64)]
+
+
+class PsdBatchStats(C.Structure):
+    _fields_ = [("parse_ms", C.c_double), ("build_ms", C.c_double), ("run_ms", C.c_double), ("write_ms", C.c_double),
+                ("release_ms", C.c_double), ("dp_ms", C.c_double), ("backtrack_ms", C.c_double),
+                ("rows_parsed", C.c_int64), ("rows_solved", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
+                ("store_bytes_algorithmic", C.c_int64), ("n_problems", C.c_int32), ("n_files_parsed", C.c_int32),
+                ("n_devices", C.c_int32), ("n_launches", C.c_int32), ("n_waves", C.c_int32), ("n_latency_waves", C.c_int32)]
 
 
 # every symbol include/peaksegdisk_b200.h declares (tests check the library exports all of them)
 C_ABI_SYMBOLS = [
     "psd_fpop_disk", "psd_fpop_disk_batch", "psd_status_message", "psd_last_error", "psd_plan_create",
     "psd_plan_destroy", "psd_plan_add", "psd_plan_add_counts", "psd_plan_size", "psd_plan_upload", "psd_plan_solve", "psd_plan_download",
-    "psd_plan_run", "psd_plan_result", "psd_plan_segments", "psd_plan_get_stats", "psd_plan_set_penalty", "psd_plan_store_function", "psd_write_bedgraph",
+    "psd_plan_run", "psd_plan_result", "psd_plan_segments", "psd_plan_get_stats", "psd_plan_set_penalty", "psd_plan_store_function", "psd_write_bedgraph", "psd_last_batch_stats",
     "psd_set_option", "psd_device_count", "psd_release_cache",
     "_Z16PeakSegFPOP_diskPcS_S_",   # the reference's own C++-linkage entry (src/PeakSegFPOPLog.h:15)
 ]
@@ -79,6 +88,8 @@ def _load():
     lib.psd_plan_set_penalty.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_int]
     lib.psd_plan_store_function.restype = C.c_int
     lib.psd_plan_store_function.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, i32p, dp, i32p, dp]
+    lib.psd_last_batch_stats.restype = C.c_int
+    lib.psd_last_batch_stats.argtypes = [C.POINTER(PsdBatchStats)]
     lib.psd_write_bedgraph.restype = C.c_int
     lib.psd_write_bedgraph.argtypes = [C.c_char_p, C.c_char_p, C.c_int64, i32p, i32p, i32p]
     lib.psd_set_option.restype = C.c_int
@@ -105,3 +116,10 @@ def status_text(status, bedgraph="", penalty="", db=""):
         return fmt % status
     extra = lib.psd_last_error().decode()
     return fmt + (": " + extra if extra else "")
+
+
+def last_batch_stats():
+    """Stage times and device counters of the process's last file-batch call, as a dict."""
+    st = PsdBatchStats()
+    lib.psd_last_batch_stats(C.byref(st))
+    return {name: getattr(st, name) for name, _ in st._fields_}

@@ -23,9 +23,12 @@
 #include <cstdlib>
 #include <cstring>
 #include <chrono>
+#include <atomic>
 #include <mutex>
 #include <queue>
+#include <thread>
 #include <string>
+#include <unordered_map>
 #include <vector>
 #include "dp_params.h"
 #include "rle_gpu.cuh"
@@ -125,7 +128,7 @@ fpop_backtrack_kernel(const BtKernelParams P) {
 namespace {
 thread_local std::string g_last_error;
 std::mutex g_opt_mutex;
-struct Options { int piece_cap = 48; int overflow_cap = 8192; double store_gb = 0; int chunk_kb = 64; int max_warps_per_sm = 0; int blocks_per_sm = 1; int spill_cap = 512; double host_spill_gb = -1; int occupancy_mode = 0; int devices = 1; int queue_mode = 0; int latency_mode = 0; int latency_max_blocks = 2; } g_opt;
+struct Options { int piece_cap = 48; int overflow_cap = 8192; double store_gb = 0; int chunk_kb = 64; int max_warps_per_sm = 0; int blocks_per_sm = 1; int spill_cap = 512; double host_spill_gb = -1; int occupancy_mode = 0; int devices = 1; int queue_mode = 0; int latency_mode = 0; int latency_max_blocks = 2; int spill_mode = 0; double ring_gb = 0; } g_opt;
 
 bool cuda_ok(cudaError_t e, const char* what) {
   if (e == cudaSuccess) return true;
@@ -156,6 +159,8 @@ int psd_set_option_impl(const char* name, double value) {
   else if (n == "queue_mode") g_opt.queue_mode = (int)value;           // experiment: 0 one global queue, 1 one share of the batch per block
   else if (n == "latency_mode") g_opt.latency_mode = (int)value;       // 0 auto (small waves), 1 always the latency kernel, 2 never
   else if (n == "latency_max_blocks") g_opt.latency_max_blocks = std::max(1, (int)value);   // auto: waves of up to this many problems per SM
+  else if (n == "spill_mode") g_opt.spill_mode = (int)value;           // 0 DMA drain of an HBM ring (cudaMemcpyAsync on a side stream), 1 zero-copy stores
+  else if (n == "ring_gb") g_opt.ring_gb = value;                      // HBM ring of the DMA drain (0 = automatic)
   else if (n == "devices") g_opt.devices = (int)value;                 // 1 current device only, k first k GPUs, <= 0 all
   else return PSD_ERR_ARG;
   return 0;
@@ -180,7 +185,8 @@ struct psd_plan {
   int *d_scratch_row = nullptr, *d_seg_row = nullptr;
   double *d_scratch_x = nullptr, *d_seg_x = nullptr;
   unsigned char* d_pool = nullptr; unsigned long long pool_bytes = 0, pool_chunk = 0;
-  size_t d_rows_cap = 0, d_prob_cap = 0, d_seg_cap = 0;
+  size_t d_rows_cap = 0, d_index_cap = 0, d_prob_cap = 0, d_seg_cap = 0;
+  std::vector<std::pair<const RowData*, int64_t>> row_sets;   // distinct row sets of the uploaded problems and their device offsets
   unsigned char* d_gws = nullptr; unsigned long long gws_bytes = 0;
   // count-vector problems: raw counts, chromEnd rows, run-length-encoding descriptors
   int *d_raw = nullptr, *d_end = nullptr; size_t d_raw_cap = 0, d_end_cap = 0;
@@ -192,6 +198,10 @@ struct psd_plan {
   int* p_rle_nrows = nullptr; size_t p_rle_nrows_cap = 0;
   int64_t rows_plain = 0, total_pos = 0; size_t n_count_problems = 0;
   unsigned char* h_spill = nullptr; unsigned char* d_spill = nullptr; unsigned long long spill_bytes = 0;   // mapped pinned host region
+  // DMA drain of the spill (StoreRing): HBM ring, pinned queues, side stream
+  unsigned char* d_ring = nullptr; unsigned long long ring_slots = 0, ring_chunk = 0;
+  unsigned char* h_ringq = nullptr; unsigned char* d_ringq = nullptr; unsigned int ring_qlen = 0;   // [free_tail 64 B | free_q | done_q]
+  cudaStream_t drain_stream = nullptr;
   // pinned staging
   int32_t *p_weight = nullptr, *p_cov = nullptr;
   DpResult* p_results = nullptr;
@@ -201,7 +211,7 @@ struct psd_plan {
   size_t p_rows_cap = 0, p_res_cap = 0, p_seg_cap = 0;
   // bookkeeping
   std::vector<int> gpu_ids;                    // problem ids that go to the GPU
-  int64_t total_rows = 0;
+  int64_t total_rows = 0, total_index = 0;
   bool uploaded = false, solved = false, packed = false;
   std::vector<DpResult> results;               // per gpu problem (indexed like gpu_ids)
   std::vector<int> seg_row; std::vector<double> seg_x;
@@ -217,10 +227,10 @@ struct psd_plan {
   void release_device() {
     dfree(d_weight); dfree(d_cov); dfree(d_index); dfree(d_problems); dfree(d_results); dfree(d_order);
     dfree(d_queue); dfree(d_bins); d_queue_cap = 0; dfree(d_cursors); dfree(d_seg_scratch_off); dfree(d_scratch_row); dfree(d_seg_row);
-    dfree(d_scratch_x); dfree(d_seg_x); dfree(d_pool); dfree(d_gws);
+    dfree(d_scratch_x); dfree(d_seg_x); dfree(d_pool); dfree(d_gws); dfree(d_ring); ring_slots = 0;
     dfree(d_raw); dfree(d_end); dfree(d_end_off); dfree(d_rle_vecs); dfree(d_tile_vec); dfree(d_tile_state); dfree(d_rle_nrows);
     d_raw_cap = d_end_cap = d_rle_vec_cap = d_tile_cap = 0;
-    d_rows_cap = d_prob_cap = d_seg_cap = 0; pool_bytes = 0; gws_bytes = 0;
+    d_rows_cap = d_index_cap = d_prob_cap = d_seg_cap = 0; pool_bytes = 0; gws_bytes = 0;
     uploaded = false;
   }
   void release() {
@@ -229,6 +239,9 @@ struct psd_plan {
     if (p_results) cudaFreeHost(p_results); if (p_seg_row) cudaFreeHost(p_seg_row);
     if (p_seg_x) cudaFreeHost(p_seg_x); if (p_cursors) cudaFreeHost(p_cursors); if (p_queue_init) cudaFreeHost(p_queue_init);
     if (h_spill) cudaFreeHost(h_spill);
+    if (h_ringq) cudaFreeHost(h_ringq);
+    h_ringq = d_ringq = nullptr; ring_qlen = 0;
+    if (drain_stream) { cudaStreamDestroy(drain_stream); drain_stream = nullptr; }
     if (p_raw) cudaFreeHost(p_raw); if (p_rle_nrows) cudaFreeHost(p_rle_nrows);
     p_raw = nullptr; p_rle_nrows = nullptr; p_raw_cap = p_rle_nrows_cap = 0;
     h_spill = d_spill = nullptr; spill_bytes = 0;
@@ -256,6 +269,7 @@ static Options current_options() {
   if (const char* e = getenv("PSD_HOST_SPILL_GB")) o.host_spill_gb = atof(e);
   if (const char* e = getenv("PSD_OCCUPANCY_MODE")) o.occupancy_mode = atoi(e);
   if (const char* e = getenv("PSD_QUEUE_MODE")) o.queue_mode = atoi(e);
+  if (const char* e = getenv("PSD_SPILL_MODE")) o.spill_mode = atoi(e);
   if (const char* e = getenv("PSD_LATENCY_MODE")) o.latency_mode = atoi(e);
   if (const char* e = getenv("PSD_LATENCY_MAX_BLOCKS")) o.latency_max_blocks = std::max(1, atoi(e));
   return o;
@@ -265,7 +279,7 @@ static bool same_options(const Options& a, const Options& b) {
   return a.piece_cap == b.piece_cap && a.overflow_cap == b.overflow_cap && a.store_gb == b.store_gb && a.chunk_kb == b.chunk_kb &&
          a.max_warps_per_sm == b.max_warps_per_sm && a.blocks_per_sm == b.blocks_per_sm && a.spill_cap == b.spill_cap &&
          a.host_spill_gb == b.host_spill_gb && a.occupancy_mode == b.occupancy_mode && a.queue_mode == b.queue_mode &&
-         a.latency_mode == b.latency_mode && a.latency_max_blocks == b.latency_max_blocks;
+         a.latency_mode == b.latency_mode && a.latency_max_blocks == b.latency_max_blocks && a.spill_mode == b.spill_mode && a.ring_gb == b.ring_gb;
 }
 
 psd_plan* psd_plan_create_impl(int device) {
@@ -328,8 +342,8 @@ void psd_plan_release_parked(psd_plan* p) {
   const unsigned long long pinned = (unsigned long long)(p->p_rows_cap * 8 + p->p_raw_cap * 4 + p->p_seg_cap * 12 + p->p_res_cap * sizeof(DpResult));
   // freeing a multi-GB store pool and unpinning the staging costs 0.5-0.9 s per call (measured), far
   // more than keeping them for the next call of the same process; only very large plans are let go
-  const bool small = p->ev_ok && p->pool_bytes <= (32ull << 30) && pinned <= (2ull << 30) && p->spill_bytes == 0 &&
-                     p->gws_bytes <= (2ull << 30);
+  const bool small = p->ev_ok && p->pool_bytes <= (100ull << 30) && pinned <= (8ull << 30) && p->spill_bytes == 0 &&
+                     p->gws_bytes <= (4ull << 30);
   if (small) {
     p->probs.clear(); p->gpu_ids.clear(); p->results.clear(); p->seg_row.clear(); p->seg_x.clear();
     p->uploaded = p->solved = p->packed = false; p->last_mean_intervals = 0;
@@ -355,22 +369,34 @@ int psd_plan_upload_impl(psd_plan* p, void* stream_v) {
   p->gpu_ids.clear();
   int64_t total = 0, total_pos = 0;
   size_t n_counts = 0;
-  // row problems first: their (weight, coverage) rows are copied from the host; the rows of
-  // count-vector problems are produced on the device and only their raw counts are copied
+  // row problems first: their (weight, coverage) rows are copied from the host, ONCE per RowData (the
+  // penalties of one file share their rows on the host and on the device); the rows of count-vector
+  // problems are produced on the device and only their raw counts are copied.  The record index is
+  // per problem.
+  int64_t total_index = 0;
+  std::unordered_map<const RowData*, int64_t> off_of;
+  p->row_sets.clear();
   for (int pass = 0; pass < 2; pass++)
     for (size_t i = 0; i < p->probs.size(); i++) {
       HostProblem& hp = p->probs[i];
       if (hp.status != 0 || hp.trivial || (int)hp.from_counts != pass) continue;
-      hp.row_off = total; total += hp.n_rows;
-      if (pass == 1) { hp.raw_off = total_pos; total_pos += hp.n_pos; n_counts++; }
+      hp.index_off = total_index; total_index += hp.n_rows;
+      if (pass == 0) {
+        auto it = off_of.find(hp.rows.get());
+        if (it == off_of.end()) { it = off_of.emplace(hp.rows.get(), total).first; p->row_sets.push_back({hp.rows.get(), total}); total += hp.n_rows; }
+        hp.row_off = it->second;
+      } else {
+        hp.row_off = total; total += hp.n_rows;
+        hp.raw_off = total_pos; total_pos += hp.n_pos; n_counts++;
+      }
     }
   p->rows_plain = 0;
-  for (const HostProblem& hp : p->probs) if (hp.status == 0 && !hp.trivial && !hp.from_counts) p->rows_plain += hp.n_rows;
+  for (const auto& rs : p->row_sets) p->rows_plain += (int64_t)rs.first->coverage.size();
   for (size_t i = 0; i < p->probs.size(); i++) {
     const HostProblem& hp = p->probs[i];
     if (hp.status == 0 && !hp.trivial) p->gpu_ids.push_back((int)i);
   }
-  p->total_rows = total; p->total_pos = total_pos; p->n_count_problems = n_counts;
+  p->total_rows = total; p->total_index = total_index; p->total_pos = total_pos; p->n_count_problems = n_counts;
   p->stats.h2d_bytes = 0; p->stats.h2d_ms = 0;
   const size_t ng = p->gpu_ids.size();
   if (ng == 0) { p->uploaded = true; p->solved = false; return 0; }
@@ -396,20 +422,27 @@ int psd_plan_upload_impl(psd_plan* p, void* stream_v) {
   if (!p->packed) {
     for (int id : p->gpu_ids) {
       const HostProblem& hp = p->probs[id];
-      if (hp.from_counts) { memcpy(p->p_raw + hp.raw_off, hp.counts.data(), sizeof(int32_t) * hp.n_pos); continue; }
-      memcpy(p->p_weight + hp.row_off, hp.weight.data(), sizeof(int32_t) * hp.n_rows);
-      memcpy(p->p_cov + hp.row_off, hp.coverage.data(), sizeof(int32_t) * hp.n_rows);
+      if (hp.from_counts) memcpy(p->p_raw + hp.raw_off, hp.counts.data(), sizeof(int32_t) * hp.n_pos);
+    }
+    for (const auto& rs : p->row_sets) {
+      // row sets are laid out first and in order, so the device offset equals the staging offset
+      memcpy(p->p_weight + rs.second, rs.first->weight.data(), sizeof(int32_t) * rs.first->weight.size());
+      memcpy(p->p_cov + rs.second, rs.first->coverage.data(), sizeof(int32_t) * rs.first->coverage.size());
     }
     p->packed = true;
   }
   tr.mark("upload: pack rows");
   // device buffers are grow-only: a plan that is re-uploaded with the same shapes allocates nothing
   if ((size_t)total > p->d_rows_cap) {
-    dfree(p->d_weight); dfree(p->d_cov); dfree(p->d_index);
+    dfree(p->d_weight); dfree(p->d_cov); p->d_rows_cap = 0;
     CK(cudaMalloc(&p->d_weight, sizeof(int) * total));
     CK(cudaMalloc(&p->d_cov, sizeof(int) * total));
-    CK(cudaMalloc(&p->d_index, sizeof(unsigned long long) * total));
     p->d_rows_cap = total;
+  }
+  if ((size_t)total_index > p->d_index_cap) {
+    dfree(p->d_index); p->d_index_cap = 0;
+    CK(cudaMalloc(&p->d_index, sizeof(unsigned long long) * total_index));
+    p->d_index_cap = total_index;
   }
   if (ng > p->d_prob_cap) {
     dfree(p->d_problems); dfree(p->d_results); dfree(p->d_order); dfree(p->d_seg_scratch_off); dfree(p->d_end_off);
@@ -420,14 +453,14 @@ int psd_plan_upload_impl(psd_plan* p, void* stream_v) {
     CK(cudaMalloc(&p->d_seg_scratch_off, sizeof(unsigned long long) * ng));
     p->d_prob_cap = ng;
   }
-  if (!p->d_cursors) CK(cudaMalloc(&p->d_cursors, sizeof(unsigned long long) * 4));
-  if ((size_t)(total + ng) > p->d_seg_cap) {
-    dfree(p->d_scratch_row); dfree(p->d_scratch_x); dfree(p->d_seg_row); dfree(p->d_seg_x);
-    CK(cudaMalloc(&p->d_scratch_row, sizeof(int) * (total + ng)));
-    CK(cudaMalloc(&p->d_scratch_x, sizeof(double) * (total + ng)));
-    CK(cudaMalloc(&p->d_seg_row, sizeof(int) * (total + ng)));
-    CK(cudaMalloc(&p->d_seg_x, sizeof(double) * (total + ng)));
-    p->d_seg_cap = total + ng;
+  if (!p->d_cursors) CK(cudaMalloc(&p->d_cursors, sizeof(unsigned long long) * 8));   // [0] HBM chunk cursor [1] segment cursor [2] zero-copy host chunks [4] ring head [5] ring done head
+  if ((size_t)(total_index + ng) > p->d_seg_cap) {
+    dfree(p->d_scratch_row); dfree(p->d_scratch_x); dfree(p->d_seg_row); dfree(p->d_seg_x); p->d_seg_cap = 0;
+    CK(cudaMalloc(&p->d_scratch_row, sizeof(int) * (total_index + ng)));
+    CK(cudaMalloc(&p->d_scratch_x, sizeof(double) * (total_index + ng)));
+    CK(cudaMalloc(&p->d_seg_row, sizeof(int) * (total_index + ng)));
+    CK(cudaMalloc(&p->d_seg_x, sizeof(double) * (total_index + ng)));
+    p->d_seg_cap = total_index + ng;
   }
   // count-vector problems: raw counts in, rows made on the device
   std::vector<RleVec> rvecs; std::vector<int> tile_vec;
@@ -471,7 +504,7 @@ int psd_plan_upload_impl(psd_plan* p, void* stream_v) {
   }
   // (the pinned staging of the segments is sized at download, from the number of segments found:
   // pinning the worst case of one segment per row cost more than the whole D2H copy)
-  if (!p->p_cursors) CK(cudaMallocHost(&p->p_cursors, sizeof(unsigned long long) * 4));
+  if (!p->p_cursors) CK(cudaMallocHost(&p->p_cursors, sizeof(unsigned long long) * 8));
   if (!p->p_queue_init) CK(cudaMallocHost(&p->p_queue_init, sizeof(int) * 3 * 1024));   // cursors + bins of up to 1024 blocks
   tr.mark("upload: pinned result staging");
   // store pool: sized from free memory unless the option pins it
@@ -480,8 +513,9 @@ int psd_plan_upload_impl(psd_plan* p, void* stream_v) {
   unsigned long long want;
   if (p->opt.store_gb > 0) want = (unsigned long long)(p->opt.store_gb * (double)(1ull << 30));
   else {
-    // estimate: 16 B header + 20 B x ~2x16 pieces per row, x1.5 headroom; clamp to 80% of free memory
-    want = (unsigned long long)total * 1000ull + (64ull << 20);
+    // estimate: 16 B header + 8 B index + 20 B x 2 functions x ~11 pieces per row (config 2 writes 380 B
+    // per row, Mono27ac 300-560); a wave that still runs out grows the pool x4 and repeats; clamp to 80% of free memory
+    want = (unsigned long long)total_index * 520ull + (64ull << 20);
     const unsigned long long lim = (unsigned long long)((double)free_b * 0.80);
     if (want > lim) want = lim;
   }
@@ -510,7 +544,7 @@ int psd_plan_upload_impl(psd_plan* p, void* stream_v) {
     const HostProblem& h = p->probs[p->gpu_ids[g]];
     hp[g].weight = p->d_weight + h.row_off; hp[g].coverage = p->d_cov + h.row_off;
     hp[g].n_rows = (int)h.n_rows; hp[g].penalty = h.penalty; hp[g].dmin = h.dmin; hp[g].dmax = h.dmax;
-    hp[g].index = p->d_index + h.row_off;
+    hp[g].index = p->d_index + h.index_off;
     soff[g] = scratch_cursor; scratch_cursor += (unsigned long long)h.n_rows + 1ull;
     eoff[g] = h.from_counts ? (long long)h.row_off : -1;
   }
@@ -642,6 +676,79 @@ static int choose_config(psd_plan* p, const std::vector<int>& todo) {
   return t1 < 0.95 * t0 ? 1 : 0;
 }
 
+// ---- DMA drain of the store spill (host side of StoreRing, fpop_warp.cuh) --------------------------
+// While the DP kernel runs, a host thread polls the pinned done-queue; every published ring slot is
+// copied to its place in the pinned host region by cudaMemcpyAsync on a side stream, and once a batch
+// of copies has completed the slots go back to the device through the pinned free-queue.
+struct RingDrain {
+  psd_plan* p = nullptr;
+  unsigned long long chunk = 0;
+  std::atomic<unsigned long long> final_count{~0ull};   // set when the kernel has finished: total chunks published
+  std::atomic<int> error{0};
+  unsigned long long drained = 0;
+  std::thread th;
+  volatile unsigned long long* free_tail() const { return (volatile unsigned long long*)p->h_ringq; }
+  volatile unsigned int* free_q() const { return (volatile unsigned int*)(p->h_ringq + 64); }
+  volatile unsigned long long* done_q() const { return (volatile unsigned long long*)(p->h_ringq + 64 + 4ull * p->ring_qlen); }
+  void run() {
+    if (cudaSetDevice(p->device) != cudaSuccess) { error = 1; return; }
+    const unsigned mask = p->ring_qlen - 1;
+    unsigned long long next = 0, ftail = p->ring_slots;
+    std::vector<unsigned> batch;
+    int idle = 0;
+    for (;;) {
+      volatile unsigned long long* e = done_q() + 2ull * (next & mask);
+      if (e[0] == next + 1ull && batch.size() < 256) {
+        const unsigned long long payload = e[1];
+        const unsigned long long host_chunk = payload >> 32, slot = payload & 0xffffffffull;
+        if (cudaMemcpyAsync(p->h_spill + host_chunk * chunk, p->d_ring + slot * chunk, chunk, cudaMemcpyDeviceToHost, p->drain_stream) != cudaSuccess) error = 2;
+        batch.push_back((unsigned)slot);
+        next++; idle = 0;
+        continue;
+      }
+      if (!batch.empty()) {
+        if (cudaStreamSynchronize(p->drain_stream) != cudaSuccess) error = 3;
+        for (unsigned slot : batch) { free_q()[ftail & mask] = slot; ftail++; }
+        std::atomic_thread_fence(std::memory_order_release);
+        *free_tail() = ftail;
+        batch.clear();
+        continue;
+      }
+      const unsigned long long fin = final_count.load(std::memory_order_acquire);
+      if (fin != ~0ull && next >= fin) break;
+      if (++idle > 64) std::this_thread::sleep_for(std::chrono::microseconds(20)); else std::this_thread::yield();
+    }
+    drained = next;
+  }
+};
+
+// (re)creates the ring for a launch of `n_warps` writers; returns 0 when the ring is ready
+static int ring_prepare(psd_plan* p, unsigned long long chunk, unsigned long long n_writers) {
+  // every writer can hold one open ring chunk while it waits at a phase barrier for a warp that is
+  // waiting for a free slot: the ring must be larger than the number of writers (fpop_warp.cuh)
+  unsigned long long want_slots = 4ull * n_writers + 64ull;
+  size_t free_b = 0, total_b = 0;
+  CK(cudaMemGetInfo(&free_b, &total_b));
+  unsigned long long auto_bytes = p->opt.ring_gb > 0 ? (unsigned long long)(p->opt.ring_gb * (double)(1ull << 30)) : std::min<unsigned long long>(2ull << 30, (free_b + p->ring_slots * p->ring_chunk) / 8);
+  want_slots = std::max(want_slots, auto_bytes / chunk);
+  if (want_slots > 0xfffffff0ull) want_slots = 0xfffffff0ull;
+  if (p->ring_slots < want_slots || p->ring_chunk != chunk) {
+    dfree(p->d_ring); p->ring_slots = 0;
+    CK(cudaMalloc(&p->d_ring, want_slots * chunk));
+    p->ring_slots = want_slots; p->ring_chunk = chunk;
+  }
+  unsigned qlen = 64; while ((unsigned long long)qlen < 4ull * p->ring_slots) qlen <<= 1;
+  if (qlen != p->ring_qlen) {
+    if (p->h_ringq) cudaFreeHost(p->h_ringq);
+    p->h_ringq = p->d_ringq = nullptr; p->ring_qlen = 0;
+    CK(cudaHostAlloc((void**)&p->h_ringq, 64 + 20ull * qlen, cudaHostAllocMapped | cudaHostAllocPortable));
+    CK(cudaHostGetDevicePointer((void**)&p->d_ringq, p->h_ringq, 0));
+    p->ring_qlen = qlen;
+  }
+  if (!p->drain_stream) CK(cudaStreamCreateWithFlags(&p->drain_stream, cudaStreamNonBlocking));
+  return 0;
+}
+
 // DP + backtrack for every uploaded problem.  Device-only: no host<->device row traffic.
 int psd_plan_solve_impl(psd_plan* p, void* stream_v) {
   cudaStream_t st = (cudaStream_t)stream_v;
@@ -651,7 +758,7 @@ int psd_plan_solve_impl(psd_plan* p, void* stream_v) {
   if (ng) CK(cudaSetDevice(p->device));
   psd_stats& S = p->stats;
   S.dp_ms = S.backtrack_ms = 0; S.n_launches = 0; S.n_waves = 0; S.n_overflow_tier = 0; S.n_latency_waves = 0;
-  S.rows_solved = 0; S.store_bytes_algorithmic = 0; S.store_bytes_written = 0; S.backtrack_bytes_read = 0; S.store_bytes_spilled_host = 0;
+  S.rows_solved = 0; S.store_bytes_algorithmic = 0; S.store_bytes_written = 0; S.backtrack_bytes_read = 0; S.store_bytes_spilled_host = 0; S.store_bytes_drained_dma = 0;
   p->results.assign(ng, DpResult());
   p->n_seg_total = 0;
   if (ng == 0) { p->solved = true; return 0; }
@@ -666,7 +773,7 @@ int psd_plan_solve_impl(psd_plan* p, void* stream_v) {
       const HostProblem& h = p->probs[p->gpu_ids[g]];
       hp[g].weight = p->d_weight + h.row_off; hp[g].coverage = p->d_cov + h.row_off;
       hp[g].n_rows = (int)h.n_rows; hp[g].penalty = h.penalty; hp[g].dmin = h.dmin; hp[g].dmax = h.dmax;
-      hp[g].index = p->d_index + h.row_off;
+      hp[g].index = p->d_index + h.index_off;
     }
     CK(cudaMemcpyAsync(p->d_problems, hp.data(), sizeof(DpProblem) * ng, cudaMemcpyHostToDevice, st));
     CK(cudaStreamSynchronize(st));
@@ -680,7 +787,7 @@ int psd_plan_solve_impl(psd_plan* p, void* stream_v) {
   });
   std::vector<int> deferred;            // same tier, waiting for the store pool to be recycled
   std::vector<int> overflow_acc;        // need the next piece-list tier
-  CK(cudaMemsetAsync(p->d_cursors, 0, sizeof(unsigned long long) * 4, st));
+  CK(cudaMemsetAsync(p->d_cursors, 0, sizeof(unsigned long long) * 8, st));
   bool global_tier = false;
   int gcap = p->opt.overflow_cap;
   if (gcap > 32768) gcap = 32768;
@@ -706,6 +813,7 @@ int psd_plan_solve_impl(psd_plan* p, void* stream_v) {
     K.problems = p->d_problems; K.order = p->d_order; K.n_order = n; K.queue = p->d_queue; K.results = p->d_results;
     K.pool.base = p->d_pool; K.pool.cursor = p->d_cursors; K.pool.n_chunks = p->pool_bytes / chunk; K.pool.chunk_bytes = chunk;
     K.pool.host_base = p->d_spill; K.pool.host_cursor = p->d_cursors + 2; K.pool.host_chunks = p->spill_bytes / chunk;
+    memset(&K.pool.ring, 0, sizeof K.pool.ring);
     int grid; size_t smem; int wpb; int which = 0; int blocks = 1;
     // Few problems (a sequential search on one chromosome, the worst-case sequences, single calls):
     // the latency kernel, one problem per block and one chain per warp (fpop_lat.cu)
@@ -797,6 +905,26 @@ int psd_plan_solve_impl(psd_plan* p, void* stream_v) {
     K.queue = p->d_queue;
     CK(cudaMemsetAsync(p->d_cursors, 0, sizeof(unsigned long long), st));   // recycle the store pool
     CK(cudaMemsetAsync(p->d_cursors + 2, 0, sizeof(unsigned long long), st));
+    // spill through the DMA drain: an HBM ring that a host thread empties into the pinned host region
+    const bool use_ring = p->d_spill != nullptr && p->opt.spill_mode == 0 && K.pool.host_chunks > 0;
+    RingDrain drain;
+    if (use_ring) {
+      rc = ring_prepare(p, chunk, (unsigned long long)grid * (unsigned long long)(lat ? 1 : wpb));
+      if (rc) return rc;
+      const unsigned qlen = p->ring_qlen;
+      memset(p->h_ringq, 0, 64 + 20ull * qlen);
+      unsigned int* fq = (unsigned int*)(p->h_ringq + 64);
+      for (unsigned long long i = 0; i < p->ring_slots; i++) fq[i] = (unsigned int)i;
+      *(volatile unsigned long long*)p->h_ringq = p->ring_slots;
+      CK(cudaMemsetAsync(p->d_cursors + 4, 0, 2 * sizeof(unsigned long long), st));
+      K.pool.ring.base = p->d_ring; K.pool.ring.n_slots = p->ring_slots;
+      K.pool.ring.head = p->d_cursors + 4; K.pool.ring.done_head = p->d_cursors + 5;
+      K.pool.ring.free_tail = (volatile unsigned long long*)p->d_ringq;
+      K.pool.ring.free_q = (volatile unsigned int*)(p->d_ringq + 64);
+      K.pool.ring.done_q = (volatile unsigned long long*)(p->d_ringq + 64 + 4ull * qlen);
+      K.pool.ring.q_mask = qlen - 1;
+      drain.p = p; drain.chunk = chunk;
+    }
     CK(cudaEventRecord(p->ev[2], st));
     if (lat) {
       CK((cudaError_t)psd_lat_set_smem(smem));
@@ -808,6 +936,19 @@ int psd_plan_solve_impl(psd_plan* p, void* stream_v) {
       CK(cudaGetLastError());
     }
     CK(cudaEventRecord(p->ev[3], st));
+    if (use_ring) {
+      // the drain runs while the kernel does; the backtrack may only start when every published chunk is on the host
+      drain.th = std::thread([&drain]() { drain.run(); });
+      const cudaError_t e1 = cudaEventSynchronize(p->ev[3]);
+      unsigned long long done_total = 0;
+      const cudaError_t e2 = (e1 == cudaSuccess) ? cudaMemcpyAsync(&done_total, p->d_cursors + 5, sizeof done_total, cudaMemcpyDeviceToHost, p->drain_stream) : e1;
+      const cudaError_t e3 = (e2 == cudaSuccess) ? cudaStreamSynchronize(p->drain_stream) : e2;
+      drain.final_count.store(e3 == cudaSuccess ? done_total : 0ull, std::memory_order_release);
+      drain.th.join();
+      CK(e3);
+      if (drain.error.load()) { g_last_error = "store drain: a DMA copy failed"; return PSD_ERR_CUDA; }
+      S.store_bytes_drained_dma += (int64_t)(drain.drained * chunk);
+    }
     BtKernelParams B;
     B.problems = p->d_problems; B.order = p->d_order; B.n_order = n; B.results = p->d_results; B.pool = K.pool;
     B.seg_scratch_off = p->d_seg_scratch_off; B.scratch_row = p->d_scratch_row; B.scratch_x = p->d_scratch_x;
@@ -819,7 +960,7 @@ int psd_plan_solve_impl(psd_plan* p, void* stream_v) {
     S.n_launches += 2; S.n_waves++;
     // the wave's status words decide what (if anything) has to be re-run
     CK(cudaMemcpyAsync(p->p_results, p->d_results, sizeof(DpResult) * ng, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(p->p_cursors, p->d_cursors, sizeof(unsigned long long) * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(p->p_cursors, p->d_cursors, sizeof(unsigned long long) * 8, cudaMemcpyDeviceToHost, st));
     tr.mark("solve: launches enqueued");
     CK(cudaStreamSynchronize(st));
     tr.mark("solve: kernels + status D2H");
@@ -827,7 +968,7 @@ int psd_plan_solve_impl(psd_plan* p, void* stream_v) {
     cudaEventElapsedTime(&ms, p->ev[2], p->ev[3]); S.dp_ms += ms;
     cudaEventElapsedTime(&ms, p->ev[3], p->ev[4]); S.backtrack_ms += ms;
     S.store_bytes_written += (int64_t)(std::min<unsigned long long>(p->p_cursors[0], K.pool.n_chunks) * chunk);
-    S.store_bytes_spilled_host += (int64_t)(std::min<unsigned long long>(p->p_cursors[2], K.pool.host_chunks) * chunk);
+    S.store_bytes_spilled_host += (int64_t)(std::min<unsigned long long>(p->p_cursors[2] + (use_ring ? p->p_cursors[5] : 0ull), K.pool.host_chunks) * chunk);
     std::vector<int> exhausted;
     for (int g : todo) {
       const DpResult& r = p->p_results[g];
@@ -958,7 +1099,7 @@ int psd_plan_store_function_impl(psd_plan* p, int id, int row, int which, int ca
   if (h.status != 0 || h.trivial || h.result_status != 0 || row < 0 || row >= h.n_rows) return PSD_ERR_ARG;
   CK(cudaSetDevice(p->device));
   unsigned long long off = 0;
-  CK(cudaMemcpy(&off, p->d_index + h.row_off + row, sizeof off, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(&off, p->d_index + h.index_off + row, sizeof off, cudaMemcpyDeviceToHost));
   auto fetch = [&](void* dst, unsigned long long o, size_t bytes) -> cudaError_t {
     if (o < p->pool_bytes) return cudaMemcpy(dst, p->d_pool + o, bytes, cudaMemcpyDeviceToHost);
     memcpy(dst, p->h_spill + (o - p->pool_bytes), bytes);     // spilled record: already in pinned host memory

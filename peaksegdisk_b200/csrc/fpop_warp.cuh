@@ -93,6 +93,9 @@ PSD_DEV void psd_st_cs_d2(double* p, double x, double y) { __stcs((double2*)p, m
 PSD_DEV void psd_st_cs_i(int* p, int v) { __stcs(p, v); }
 PSD_DEV void psd_st_cs_u64(unsigned long long* p, unsigned long long v) { __stcs(p, v); }
 PSD_DEV void psd_st_cs_u4(unsigned* p, unsigned a, unsigned b, unsigned c, unsigned d) { __stcs((uint4*)p, make_uint4(a, b, c, d)); }
+PSD_DEV void psd_fence_system() { __threadfence_system(); }
+// a warp waits (one lane spinning) until the host has handed back a ring slot for free-queue position pos
+#define PSD_RING_WAIT(sp, pos) do { unsigned ns_ = 64; while (*(sp).ring.free_tail <= (pos)) { __nanosleep(ns_); if (ns_ < 8192) ns_ <<= 1; } } while (0)
 #endif
 
 // PSD_TIMING (experiment builds only): per-section cycle counters, accumulated by lane 0 / lane 16
@@ -927,40 +930,92 @@ PSD_DEVNI void best_piece(const WarpWs ws, const PList f, double dmin, double* b
 //            (n_up + n_down) x i32 back_i, padded to 16 bytes
 // index[t] = byte offset of the record in the pool.  The reference's record
 // (src/PeakSegFPOPLog.cpp:12-34) carries the same fields at 8 + 20 bytes per piece per function.
-// When the HBM pool is exhausted and a host region is configured, chunks are taken from mapped
-// pinned host memory instead: records then stream over PCIe with the same 128-bit stores, and the
-// backtrack reads the few records it needs through the same mapping (offsets >= hbm bytes).
+// When the HBM pool is exhausted and a pinned host region is configured the store SPILLS: chunk numbers
+// past the HBM region address the host region (the backtrack reads the few records it needs through
+// the mapping).  How the records get there:
+//   * DMA drain (default): such a chunk is written into a slot of an HBM RING; when the warp leaves
+//     the chunk it publishes (host chunk, slot) in a pinned done-queue, a host thread copies the slot
+//     to its place in the host region with cudaMemcpyAsync on a side stream and hands the slot back
+//     through a pinned free-queue.  The DP's stores stay HBM stores; PCIe sees 64 KB DMA transfers.
+//   * zero-copy (ring off, or records larger than a chunk): the 128-bit stores go through the mapping.
+struct StoreRing {
+  unsigned char* base;                      // HBM ring: n_slots slots of chunk_bytes (n_slots = 0: ring off)
+  unsigned long long n_slots;
+  unsigned long long* head;                 // device counter: next free-queue position to take
+  unsigned long long* done_head;            // device counter: next done-queue position to fill
+  volatile unsigned long long* free_tail;   // pinned, written by the host: free-queue positions below this are valid
+  volatile unsigned int* free_q;            // pinned, written by the host: slot ids
+  volatile unsigned long long* done_q;      // pinned, written by the device: { position + 1, host chunk << 32 | slot }
+  unsigned int q_mask;
+};
 struct StorePool {
   unsigned char* base;            // HBM region
   unsigned long long* cursor;     // next free HBM chunk
   unsigned long long n_chunks;
   unsigned long long chunk_bytes;
   unsigned char* host_base;       // device-visible pinned host region (null: no spill)
-  unsigned long long* host_cursor;
+  unsigned long long* host_cursor;   // zero-copy chunks handed out (from the top of the host region when the ring is on)
   unsigned long long host_chunks;
+  StoreRing ring;
 };
-struct StoreWriter { unsigned long long cur, end; };
+struct StoreWriter { unsigned long long cur, end; long long slot; };   // slot: ring slot of the open chunk, -1 = none
 
 PSD_DEV unsigned long long store_record_bytes(int n_up, int n_down) {
   const unsigned long long np = (unsigned long long)(n_up + n_down);
   return 16ull + 16ull * np + ((4ull * np + 15ull) & ~15ull);
 }
 
+// ONE thread: publish the ring chunk a writer is leaving (its stores must already be visible system-wide)
+PSD_DEV void store_ring_publish(const StorePool& sp, unsigned long long host_chunk, long long slot) {
+  const unsigned long long pos = psd_atomic_add_ull(sp.ring.done_head, 1ull);
+  volatile unsigned long long* e = sp.ring.done_q + 2ull * (pos & sp.ring.q_mask);
+  e[1] = (host_chunk << 32) | (unsigned long long)slot;
+  psd_fence_system();
+  e[0] = pos + 1ull;
+}
+
+// ONE thread: take `need` contiguous chunks.  Returns the first chunk number (~0: exhausted); *slot
+// receives the ring slot when the chunk has to be written through the ring.
+PSD_DEV unsigned long long store_take(const StorePool& sp, unsigned long long need, long long* slot) {
+  *slot = -1;
+  const unsigned long long first = psd_atomic_add_ull(sp.cursor, need);
+  if (first + need <= sp.n_chunks) return first;
+  if (sp.host_chunks == 0) return ~0ull;
+  if (sp.ring.n_slots != 0 && need == 1) {
+    const unsigned long long pos = psd_atomic_add_ull(sp.ring.head, 1ull);
+    // host chunks: ring positions from the bottom, zero-copy allocations from the top
+    if (pos + 1ull + *(volatile unsigned long long*)sp.host_cursor > sp.host_chunks) return ~0ull;
+    PSD_RING_WAIT(sp, pos);
+    psd_fence_system();   // the slot id was written before free_tail was advanced
+    *slot = (long long)sp.ring.free_q[pos & sp.ring.q_mask];
+    return sp.n_chunks + pos;
+  }
+  const unsigned long long h = psd_atomic_add_ull(sp.host_cursor, need);
+  if (sp.ring.n_slots == 0) return (h + need > sp.host_chunks) ? ~0ull : sp.n_chunks + h;
+  if (h + need + *(volatile unsigned long long*)sp.ring.head > sp.host_chunks) return ~0ull;
+  return sp.n_chunks + sp.host_chunks - h - need;
+}
+
+// the writer's open chunk, if it is a ring chunk, is complete: make the warp's stores visible, publish
+PSD_DEV void store_close(const StorePool& sp, StoreWriter& w) {
+  if (w.slot < 0) return;
+  psd_fence_system();
+  psd_syncwarp();
+  if (psd_lane() == 0) store_ring_publish(sp, w.end / sp.chunk_bytes - 1ull - sp.n_chunks, w.slot);
+  w.slot = -1;
+}
+
 // returns the record offset or ~0 when the pool is exhausted
 PSD_DEV unsigned long long store_alloc(const StorePool& sp, StoreWriter& w, unsigned long long bytes) {
   if (w.cur + bytes > w.end) {
     const unsigned long long need = (bytes + sp.chunk_bytes - 1) / sp.chunk_bytes;
-    unsigned long long first = 0;
-    if (psd_lane() == 0) first = psd_atomic_add_ull(sp.cursor, need);
+    store_close(sp, w);
+    unsigned long long first = 0; long long slot = -1;
+    if (psd_lane() == 0) first = store_take(sp, need, &slot);
     first = psd_shfl_u64(first, 0);
-    if (first + need > sp.n_chunks) {          // HBM pool exhausted: spill to pinned host memory
-      if (sp.host_chunks == 0) return ~0ull;
-      unsigned long long h = 0;
-      if (psd_lane() == 0) h = psd_atomic_add_ull(sp.host_cursor, need);
-      h = psd_shfl_u64(h, 0);
-      if (h + need > sp.host_chunks) return ~0ull;
-      first = sp.n_chunks + h;
-    }
+    slot = (long long)psd_shfl_u64((unsigned long long)slot, 0);
+    if (first == ~0ull) return ~0ull;
+    w.slot = slot;
     w.cur = first * sp.chunk_bytes;
     w.end = w.cur + need * sp.chunk_bytes;
   }
@@ -969,9 +1024,15 @@ PSD_DEV unsigned long long store_alloc(const StorePool& sp, StoreWriter& w, unsi
   return off;
 }
 
+// where a record at offset `off` is READ (backtrack, inspection): HBM or the pinned host region
 PSD_DEV unsigned char* store_ptr(const StorePool& sp, unsigned long long off) {
   const unsigned long long hbm = sp.n_chunks * sp.chunk_bytes;
   return off < hbm ? sp.base + off : sp.host_base + (off - hbm);
+}
+// where the writer WRITES the record it just allocated: its ring slot while the chunk is open
+PSD_DEV unsigned char* store_wptr(const StorePool& sp, const StoreWriter& w, unsigned long long off) {
+  if (w.slot >= 0) return sp.ring.base + (unsigned long long)w.slot * sp.chunk_bytes + (off - (w.end - sp.chunk_bytes));
+  return store_ptr(sp, off);
 }
 
 #if !defined(PSD_G32)
@@ -1103,7 +1164,7 @@ PSD_DEV void dp_run_queue(const WarpWs& ws_s, const WarpWs& ws_g, const DpQueue&
     downN.base = ws_list(ws, 3); tmp.base = ws_list(ws, 4 + grp);                                    \
   } while (0)
   PSD_BIND_TIER();
-  StoreWriter sw; sw.cur = 0; sw.end = 0;
+  StoreWriter sw; sw.cur = 0; sw.end = 0; sw.slot = -1;
   Rescale rs; rs.mul = rs.add_a = rs.add_b = rs.inv = 0;
   bool fetch = true;
   int first_q = Q.first_slot;
@@ -1211,8 +1272,8 @@ PSD_DEV void dp_run_queue(const WarpWs& ws_s, const WarpWs& ws_g, const DpQueue&
           const unsigned long long off = store_alloc(sp, sw, store_record_bytes(upP.n, downP.n));
           if (off == ~0ull) status = PSD_ST_STORE_EXHAUSTED;
           else {
-            if (in_g) store_write<false>(ws, store_ptr(sp, off), t, upP, downP);
-            else store_write<true>(ws, store_ptr(sp, off), t, upP, downP);
+            if (in_g) store_write<false>(ws, store_wptr(sp, sw, off), t, upP, downP);
+            else store_write<true>(ws, store_wptr(sp, sw, off), t, upP, downP);
             if (lane == (t & 31)) my_off = off;
             if ((t & 31) == 31 || t == N - 1) {
               const int r = (t & ~31) + lane;
@@ -1245,6 +1306,7 @@ PSD_DEV void dp_run_queue(const WarpWs& ws_s, const WarpWs& ws_g, const DpQueue&
     PSD_T1(tc, 4);
 
   }
+  store_close(sp, sw);   // a ring chunk still open when the warp retires goes to the host like the others
 #undef PSD_BIND_TIER
 }
 #endif   // !PSD_G32
@@ -1263,28 +1325,26 @@ PSD_DEV void dp_run_queue(const WarpWs& ws_s, const WarpWs& ws_g, const DpQueue&
 struct LatShared {
   int n_out[2][2];                  // [row parity][chain]: pieces of the new function
   unsigned long long chunk_first;   // store chunk handed out by warp 0 to both warps
-  unsigned long long pad_;
+  long long chunk_slot;             // its ring slot (-1: none)
 };
 
-// store chunk allocation for the block: both warps keep identical StoreWriter state; the atomic is
-// issued once (warp 0) and its result passed through shared memory
+// store chunk allocation for the block: both warps keep identical StoreWriter state; the chunk is
+// taken (and a ring chunk being left is published) once, by warp 0, and the result passed through
+// shared memory.  Both warps write into the open chunk, so both make their stores visible first.
 PSD_DEV unsigned long long store_alloc_cta(const StorePool& sp, StoreWriter& w, unsigned long long bytes, LatShared* sh, int grp) {
   if (w.cur + bytes > w.end) {
     const unsigned long long need = (bytes + sp.chunk_bytes - 1) / sp.chunk_bytes;
+    if (w.slot >= 0) { psd_fence_system(); psd_cta_sync(); }
     if (grp == 0 && psd_lane() == 0) {
-      unsigned long long first = psd_atomic_add_ull(sp.cursor, need);
-      if (first + need > sp.n_chunks) {
-        first = ~0ull;
-        if (sp.host_chunks != 0) {
-          const unsigned long long h = psd_atomic_add_ull(sp.host_cursor, need);
-          if (h + need <= sp.host_chunks) first = sp.n_chunks + h;
-        }
-      }
-      sh->chunk_first = first;
+      if (w.slot >= 0) store_ring_publish(sp, w.end / sp.chunk_bytes - 1ull - sp.n_chunks, w.slot);
+      long long slot = -1;
+      sh->chunk_first = store_take(sp, need, &slot);
+      sh->chunk_slot = slot;
     }
     psd_cta_sync();
     const unsigned long long first = *(volatile unsigned long long*)&sh->chunk_first;
-    if (first == ~0ull) return ~0ull;
+    w.slot = *(volatile long long*)&sh->chunk_slot;
+    if (first == ~0ull) { w.slot = -1; return ~0ull; }
     w.cur = first * sp.chunk_bytes;
     w.end = w.cur + need * sp.chunk_bytes;
   }
@@ -1339,7 +1399,7 @@ PSD_DEV void dp_run_latency(const WarpWs& ws_s, const WarpWs& ws_g, const DpProb
     downN.base = ws_list(ws, 3); tmp.base = ws_list(ws, 4 + grp);                                    \
   } while (0)
   PSD_BIND_TIER();
-  StoreWriter sw; sw.cur = 0; sw.end = 0;
+  StoreWriter sw; sw.cur = 0; sw.end = 0; sw.slot = -1;
   Rescale rs; rs.mul = rs.add_a = rs.add_b = rs.inv = 0;
   for (;;) {
     wg.flags = flag_words + 2 * (t & 1) + grp;
@@ -1404,8 +1464,8 @@ PSD_DEV void dp_run_latency(const WarpWs& ws_s, const WarpWs& ws_g, const DpProb
       const unsigned long long off = store_alloc_cta(sp, sw, store_record_bytes(upP.n, downP.n), sh, grp);
       if (off == ~0ull) status = PSD_ST_STORE_EXHAUSTED;
       else {
-        if (in_g) store_write_fn<false>(ws, store_ptr(sp, off), t, grp ? downP : upP, grp, upP.n, downP.n);
-        else store_write_fn<true>(ws, store_ptr(sp, off), t, grp ? downP : upP, grp, upP.n, downP.n);
+        if (in_g) store_write_fn<false>(ws, store_wptr(sp, sw, off), t, grp ? downP : upP, grp, upP.n, downP.n);
+        else store_write_fn<true>(ws, store_wptr(sp, sw, off), t, grp ? downP : upP, grp, upP.n, downP.n);
         if (grp == 0) {
           if (lane == (t & 31)) my_off = off;
           if ((t & 31) == 31 || t == N - 1) {
@@ -1436,6 +1496,11 @@ PSD_DEV void dp_run_latency(const WarpWs& ws_s, const WarpWs& ws_g, const DpProb
       PSD_BIND_TIER();
       psd_cta_sync();
     }
+  }
+  if (sw.slot >= 0) {   // the ring chunk still open at the end goes to the host like the others
+    psd_fence_system();
+    psd_cta_sync();
+    if (grp == 0 && lane == 0) store_ring_publish(sp, sw.end / sp.chunk_bytes - 1ull - sp.n_chunks, sw.slot);
   }
 #undef PSD_BIND_TIER
 }

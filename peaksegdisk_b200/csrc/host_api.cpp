@@ -17,6 +17,7 @@
 #include <cstring>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <thread>
@@ -71,7 +72,7 @@ struct Parsed {
   int status = 0;
   int bad_items = 0, bad_line = 0;
   std::string chrom;
-  std::vector<int32_t> start, end, cov;
+  std::shared_ptr<RowData> rows = std::make_shared<RowData>();   // shared by every penalty solved on this file
 };
 
 // Pass 1 of the reference with its first-error semantics; the text is scanned once.
@@ -114,7 +115,7 @@ void parse_bedgraph(const char* path, Parsed& P) {
     if (q < e) { P.status = PSD_ERR_NON_INTEGER_DATA; return; }   // "%d%s": trailing text after the 4th column
     if (line_i > 1 && cs != prev_end) { P.status = PSD_ERR_INCONSISTENT_CHROMSTART_CHROMEND; return; }
     prev_end = ce;
-    P.start.push_back(cs); P.end.push_back(ce); P.cov.push_back(cv);
+    P.rows->chrom_start.push_back(cs); P.rows->chrom_end.push_back(ce); P.rows->coverage.push_back(cv);
     p = nl ? nl + 1 : fend;
   }
   if (line_i == 0) { P.status = PSD_ERR_NO_DATA; return; }
@@ -122,25 +123,31 @@ void parse_bedgraph(const char* path, Parsed& P) {
   P.chrom.assign(chrom_b, len);
 }
 
-// Fills the derived fields of a problem from its rows (pass-1 totals, log range, triviality).
-void finish_problem(HostProblem& h) {
-  const int64_t n = h.n_rows;
-  h.weight.resize(n);
+// Pass-1 totals of a row set: weights, sum of weights, sum of weight x coverage, log range.
+void finish_rows(RowData& r) {
+  const int64_t n = (int64_t)r.coverage.size();
+  r.weight.resize(n);
   double W = 0, SWZ = 0, xmin = INFINITY, xmax = -INFINITY;
   int32_t last_cov = 0; double last_log = 0; bool have = false;
   for (int64_t t = 0; t < n; t++) {
-    const int32_t wi = h.chrom_end[t] - h.chrom_start[t];
-    h.weight[t] = wi;
+    const int32_t wi = r.chrom_end[t] - r.chrom_start[t];
+    r.weight[t] = wi;
     const double w = (double)wi;
     W += w;
-    SWZ += w * h.coverage[t];
-    const int32_t z = h.coverage[t];
+    SWZ += w * r.coverage[t];
+    const int32_t z = r.coverage[t];
     if (!have || z != last_cov) { last_log = hlog((double)z); last_cov = z; have = true; }
     if (last_log < xmin) xmin = last_log;
     if (xmax < last_log) xmax = last_log;
   }
-  h.bases = W; h.sum_wz = SWZ; h.dmin = xmin; h.dmax = xmax;
-  h.trivial = h.penalty_is_inf || xmin == xmax;
+  r.bases = W; r.sum_wz = SWZ; r.dmin = xmin; r.dmax = xmax;
+}
+
+// Fills the derived fields of a problem from its (finished) rows.
+void finish_problem(HostProblem& h) {
+  const RowData& r = *h.rows;
+  h.bases = r.bases; h.sum_wz = r.sum_wz; h.dmin = r.dmin; h.dmax = r.dmax;
+  h.trivial = h.penalty_is_inf || r.dmin == r.dmax;
 }
 
 void format_g(std::string& out, const char* fmt, double v) {
@@ -194,6 +201,19 @@ bool write_all(FILE* f, const std::string& s) {
   return ok;
 }
 
+// wall-clock stages of the last file batch of this process (psd_last_batch_stats)
+std::mutex g_batch_stats_mutex;
+psd_batch_stats g_batch_stats;
+struct StageClock {
+  std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+  double lap() {
+    const auto n = std::chrono::steady_clock::now();
+    const double ms = std::chrono::duration<double, std::milli>(n - t).count();
+    t = n;
+    return ms;
+  }
+};
+
 struct FileJob {
   std::string bedgraph, penalty_str, db;
   int status = 0;
@@ -233,6 +253,10 @@ bool write_file(const std::string& path, const std::string& text) {
 int run_file_batch(int n, const char* const* bedgraphs, const char* const* penalties, const char* const* dbs, int* status_out) {
   std::vector<FileJob> jobs(n);
   Trace tr;
+  StageClock clk;
+  psd_batch_stats BS;
+  memset(&BS, 0, sizeof BS);
+  BS.n_problems = n;
   // several penalties on one bedGraph parse it once; distinct files are parsed on all host cores
   std::map<std::string, std::shared_ptr<Parsed>> cache;
   std::vector<std::shared_ptr<Parsed>> to_parse;
@@ -249,8 +273,14 @@ int run_file_batch(int n, const char* const* bedgraphs, const char* const* penal
     }
     j.parsed = it->second;
   }
-  parallel_for((int)to_parse.size(), [&](int k) { parse_bedgraph(to_parse_name[k].c_str(), *to_parse[k]); });
+  parallel_for((int)to_parse.size(), [&](int k) {
+    parse_bedgraph(to_parse_name[k].c_str(), *to_parse[k]);
+    if (to_parse[k]->status == 0) finish_rows(*to_parse[k]->rows);
+  });
   tr.mark("files: parse");
+  BS.parse_ms = clk.lap();
+  BS.n_files_parsed = (int)to_parse.size();
+  for (const auto& P : to_parse) BS.rows_parsed += (int64_t)P->rows->coverage.size();
   int fatal = 0;
   for (int i = 0; i < n; i++) {
     FileJob& j = jobs[i];
@@ -276,12 +306,12 @@ int run_file_batch(int n, const char* const* bedgraphs, const char* const* penal
   if (n_dev > 1) {
     std::vector<int> order;
     for (int i = 0; i < n; i++) if (!jobs[i].status) order.push_back(i);
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return jobs[a].parsed->cov.size() > jobs[b].parsed->cov.size(); });
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return jobs[a].parsed->rows->coverage.size() > jobs[b].parsed->rows->coverage.size(); });
     std::vector<double> load(n_dev, 0.0);
     for (int i : order) {
       int best = 0;
       for (int d = 1; d < n_dev; d++) if (load[d] < load[best]) best = d;
-      jobs[i].dev_slot = best; load[best] += (double)jobs[i].parsed->cov.size();
+      jobs[i].dev_slot = best; load[best] += (double)jobs[i].parsed->rows->coverage.size();
     }
   }
   tr.mark("files: create outputs");
@@ -296,7 +326,7 @@ int run_file_batch(int n, const char* const* bedgraphs, const char* const* penal
       if (!plan) { fatal = PSD_ERR_CUDA; break; }
     }
     const Parsed& P = *j.parsed;
-    if (P.cov.empty() || P.cov.size() > 0x3fffffff) { j.status = PSD_ERR_ARG; continue; }
+    if (P.rows->coverage.empty() || P.rows->coverage.size() > 0x3fffffff) { j.status = PSD_ERR_ARG; continue; }
     std::vector<HostProblem>& v = psd_plan_problems(plan);
     j.plan_id = (int)v.size();
     v.emplace_back();
@@ -307,8 +337,8 @@ int run_file_batch(int n, const char* const* bedgraphs, const char* const* penal
       if (j.status || j.plan_id < 0) return;
       const Parsed& P = *j.parsed;
       HostProblem& h = psd_plan_problems(plans[j.dev_slot])[j.plan_id];
-      h.n_rows = (int64_t)P.cov.size(); h.penalty = j.penalty; h.penalty_is_inf = j.is_inf;
-      h.chrom_start = P.start; h.chrom_end = P.end; h.coverage = P.cov;
+      h.n_rows = (int64_t)P.rows->coverage.size(); h.penalty = j.penalty; h.penalty_is_inf = j.is_inf;
+      h.rows = P.rows;          // shared, not copied: parsed, summed and uploaded once per file
       finish_problem(h);
       if (!h.trivial) {
         // the reference creates its scratch db here; keep that contract (error 7 when unwritable)
@@ -327,6 +357,7 @@ int run_file_batch(int n, const char* const* bedgraphs, const char* const* penal
     for (psd_plan* plan : plans) if (plan) psd_plan_invalidate(plan);
   }
   tr.mark("files: build plan");
+  BS.build_ms = clk.lap();
   if (!fatal) {
     if (n_dev == 1) {
       if (plans[0]) fatal = psd_plan_run(plans[0], nullptr);
@@ -341,6 +372,17 @@ int run_file_batch(int n, const char* const* bedgraphs, const char* const* penal
     }
   }
   tr.mark("files: upload + solve + download");
+  BS.run_ms = clk.lap();
+  BS.n_devices = 0;
+  for (psd_plan* plan : plans) {
+    if (!plan) continue;
+    const psd_stats& d = psd_plan_stats_ref(plan);
+    BS.n_devices++;
+    BS.dp_ms = std::max(BS.dp_ms, d.dp_ms); BS.backtrack_ms = std::max(BS.backtrack_ms, d.backtrack_ms);
+    BS.h2d_bytes += d.h2d_bytes; BS.d2h_bytes += d.d2h_bytes; BS.rows_solved += d.rows_solved;
+    BS.n_launches += d.n_launches; BS.n_waves += d.n_waves; BS.n_latency_waves += d.n_latency_waves;
+    BS.store_bytes_algorithmic += d.store_bytes_algorithmic;
+  }
   // render and write the result files on all host cores
   parallel_for(n, [&](int i) {
     FileJob& j = jobs[i];
@@ -361,9 +403,12 @@ int run_file_batch(int n, const char* const* bedgraphs, const char* const* penal
     status_out[i] = j.status;
   });
   tr.mark("files: render + write");
+  BS.write_ms = clk.lap();
   for (psd_plan* plan : plans)
     if (plan) { if (fatal || n_dev > 1) psd_plan_destroy_impl(plan); else psd_plan_release_parked(plan); }
   tr.mark("files: park / release the plan");
+  BS.release_ms = clk.lap();
+  { std::lock_guard<std::mutex> lk(g_batch_stats_mutex); g_batch_stats = BS; }
   return fatal;
 }
 
@@ -432,9 +477,11 @@ int psd_plan_add(psd_plan* plan, int64_t n_rows, const int32_t* chromStart, cons
   v.emplace_back();
   HostProblem& h = v.back();
   h.n_rows = n_rows; h.penalty = penalty; h.penalty_is_inf = penalty_is_inf != 0;
-  h.chrom_start.assign(chromStart, chromStart + n_rows);
-  h.chrom_end.assign(chromEnd, chromEnd + n_rows);
-  h.coverage.assign(coverage, coverage + n_rows);
+  h.rows = std::make_shared<RowData>();
+  h.rows->chrom_start.assign(chromStart, chromStart + n_rows);
+  h.rows->chrom_end.assign(chromEnd, chromEnd + n_rows);
+  h.rows->coverage.assign(coverage, coverage + n_rows);
+  finish_rows(*h.rows);
   finish_problem(h);
   psd_plan_invalidate(plan);
   return (int)v.size() - 1;
@@ -584,6 +631,13 @@ int psd_write_bedgraph(const char* path, const char* chrom, int64_t n_rows, cons
   if (!buf.empty()) ok = ok && fwrite(buf.data(), 1, buf.size(), f) == buf.size();
   if (fclose(f) != 0) ok = false;
   return ok ? 0 : PSD_ERR_ARG;
+}
+
+int psd_last_batch_stats(psd_batch_stats* out) {
+  if (!out) return PSD_ERR_ARG;
+  std::lock_guard<std::mutex> lk(g_batch_stats_mutex);
+  *out = g_batch_stats;
+  return 0;
 }
 
 int psd_set_option(const char* name, double value) { return name ? psd_set_option_impl(name, value) : PSD_ERR_ARG; }

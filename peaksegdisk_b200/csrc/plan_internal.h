@@ -5,9 +5,19 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <memory>
 #include <string>
 #include <vector>
 #include "../../include/peaksegdisk_b200.h"
+
+// The rows of one bedGraph (or one psd_plan_add call) and their pass-1 totals.  Problems that solve
+// the same file at different penalties share one RowData: it is parsed, summed, packed and copied to
+// the device once.
+struct RowData {
+  std::vector<int32_t> chrom_start, chrom_end, coverage, weight;
+  double bases = 0, sum_wz = 0;   // pass-1 totals (src/PeakSegFPOPLog.cpp:187-189)
+  double dmin = 0, dmax = 0;      // log(min coverage), log(max coverage)
+};
 
 struct HostProblem {
   int status = 0;                 // reference-style input status (0 ok)
@@ -15,7 +25,7 @@ struct HostProblem {
   bool penalty_is_inf = false;
   double penalty = 0;
   int64_t n_rows = 0;
-  std::vector<int32_t> chrom_start, chrom_end, coverage, weight;
+  std::shared_ptr<RowData> rows;  // row problems (null for count-vector problems)
   // count-vector problems (psd_plan_add_counts): no row arrays on the host, the device run-length
   // encodes `counts`; positions are 0..n_pos and seg_row then holds coordinates, not row numbers
   bool from_counts = false;
@@ -24,7 +34,8 @@ struct HostProblem {
   int64_t raw_off = 0;            // offset into the packed device count buffer
   double bases = 0, sum_wz = 0;   // pass-1 totals (src/PeakSegFPOPLog.cpp:187-189)
   double dmin = 0, dmax = 0;      // log(min coverage), log(max coverage)
-  int64_t row_off = 0;            // offset into the packed device row arrays
+  int64_t row_off = 0;            // offset into the packed device row arrays (shared by the problems of one RowData)
+  int64_t index_off = 0;          // offset into the device record-index array (one entry per row per PROBLEM)
   // results
   int result_status = -1;         // -1 not solved yet
   int n_segments = 0, n_equality = 0;
@@ -33,10 +44,10 @@ struct HostProblem {
   std::vector<double> seg_x;      // log-mean per segment
 };
 
-inline int hp_first_start(const HostProblem& h) { return h.from_counts ? 0 : h.chrom_start[0]; }
-inline int hp_last_end(const HostProblem& h) { return h.from_counts ? (int)h.n_pos : h.chrom_end[h.n_rows - 1]; }
+inline int hp_first_start(const HostProblem& h) { return h.from_counts ? 0 : h.rows->chrom_start[0]; }
+inline int hp_last_end(const HostProblem& h) { return h.from_counts ? (int)h.n_pos : h.rows->chrom_end[h.n_rows - 1]; }
 // chromStart of segment s (segments are stored last first; s < n_segments - 1)
-inline int hp_seg_start(const HostProblem& h, int s) { return h.from_counts ? h.seg_row[s] : h.chrom_end[h.seg_row[s]]; }
+inline int hp_seg_start(const HostProblem& h, int s) { return h.from_counts ? h.seg_row[s] : h.rows->chrom_end[h.seg_row[s]]; }
 
 // PSD_TRACE=1: wall-clock stage marks on stderr (where does a small solve's latency go?)
 struct Trace {

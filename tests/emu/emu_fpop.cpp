@@ -17,11 +17,28 @@ struct Job {
   LatShared lat;
 #endif
 };
+// The host side of the store's DMA drain (fpop_gpu.cu: RingDrain), done synchronously: copy every
+// published ring slot to its place in the "host" region and hand the slot back.
+struct EmuRing { unsigned long long next = 0, ftail = 0, drained = 0; } g_ring;
+void emu_ring_drain(const StorePool* sp) {
+  const StoreRing& r = sp->ring;
+  for (;;) {
+    volatile unsigned long long* e = r.done_q + 2ull * (g_ring.next & r.q_mask);
+    if (e[0] != g_ring.next + 1ull) break;
+    const unsigned long long host_chunk = e[1] >> 32, slot = e[1] & 0xffffffffull;
+    memcpy(sp->host_base + host_chunk * sp->chunk_bytes, r.base + slot * sp->chunk_bytes, sp->chunk_bytes);
+    ((unsigned int*)r.free_q)[g_ring.ftail & r.q_mask] = (unsigned int)slot;
+    g_ring.ftail++; g_ring.next++; g_ring.drained++;
+    *(unsigned long long*)r.free_tail = g_ring.ftail;
+  }
+}
 #if defined(PSD_G32)
 // latency kernel: a block of two warps owns the problem (one chain per warp); the backtrack is one warp
 void lane_main(void* arg) {
   Job* J = (Job*)arg;
   dp_run_latency(J->ws, J->ws_g, J->pb, J->res, J->sp, &J->lat, J->trace, J->trace_user);
+  psd_cta_sync();
+  if (J->sp.ring.n_slots && psd_warp_in_block() == 0 && psd_lane() == 0) emu_ring_drain(&J->sp);
   psd_cta_sync();
   if (psd_warp_in_block() == 0) backtrack_problem(J->sp, J->pb.index, J->pb.n_rows, J->res, J->seg_row, J->seg_x);
 }
@@ -32,6 +49,8 @@ void lane_main(void* arg) {
   DpQueue Q;
   Q.problems = &J->pb; Q.order = &J->order0; Q.n_order = 1; Q.cursor = &J->cursor; Q.results = J->res; Q.first_slot = 0;
   dp_run_queue(J->ws, J->ws_g, Q, J->sp, J->trace, J->trace_user);
+  psd_syncwarp();
+  if (J->sp.ring.n_slots && psd_lane() == 0) emu_ring_drain(&J->sp);
   psd_syncwarp();
   backtrack_problem(J->sp, J->pb.index, J->pb.n_rows, J->res, J->seg_row, J->seg_x);
 }
@@ -89,6 +108,24 @@ int emu_fpop_rows(int n_rows, const int* chrom_start, const int* chrom_end, cons
   if (const char* e = getenv("PSD_EMU_HBM_CHUNKS")) { const unsigned long long v = strtoull(e, 0, 10); if (v < hbm_chunks) hbm_chunks = v; }
   J.sp.base = pool.data(); J.sp.cursor = &cursor; J.sp.n_chunks = hbm_chunks; J.sp.chunk_bytes = chunk;
   J.sp.host_base = pool.data() + hbm_chunks * chunk; J.sp.host_cursor = &host_cursor; J.sp.host_chunks = pool.size() / chunk - hbm_chunks;
+  // PSD_EMU_RING_SLOTS (test knob): spilled chunks go through a ring of that many "HBM" slots and the
+  // drain protocol instead of being written in place
+  memset(&J.sp.ring, 0, sizeof J.sp.ring);
+  std::vector<unsigned char> ring_mem; std::vector<unsigned int> free_q; std::vector<unsigned long long> done_q;
+  unsigned long long ring_head = 0, done_head = 0, free_tail = 0;
+  if (const char* e = getenv("PSD_EMU_RING_SLOTS")) {
+    const unsigned long long ns = strtoull(e, 0, 10);
+    if (ns > 0) {
+      unsigned q_len = 4; while (q_len < 4 * ns) q_len <<= 1;
+      ring_mem.resize(ns * chunk); free_q.assign(q_len, 0); done_q.assign(2ull * q_len, 0);
+      for (unsigned long long i = 0; i < ns; i++) free_q[i] = (unsigned int)i;
+      free_tail = ns;
+      J.sp.ring.base = ring_mem.data(); J.sp.ring.n_slots = ns; J.sp.ring.head = &ring_head; J.sp.ring.done_head = &done_head;
+      J.sp.ring.free_tail = &free_tail; J.sp.ring.free_q = free_q.data(); J.sp.ring.done_q = done_q.data(); J.sp.ring.q_mask = q_len - 1;
+      g_ring = EmuRing(); g_ring.ftail = ns;
+      psd_emu_ring_drain = emu_ring_drain;
+    }
+  }
   DpResult res; res.status = -1;
   J.res = &res; J.trace = trace; J.trace_user = trace_user;
   std::vector<int> seg_row(n_rows + 1); std::vector<double> seg_x(n_rows + 1);
@@ -100,6 +137,7 @@ int emu_fpop_rows(int n_rows, const int* chrom_start, const int* chrom_end, cons
   out_summary[5] = res.best_cost; out_summary[6] = res.best_cost * W - penalty * np; out_summary[7] = res.n_equality;
   out_summary[8] = (double)res.total_intervals / (n_rows * 2); out_summary[9] = res.max_intervals;
   if (n_spills) *n_spills = res.pad_;
+  if (getenv("PSD_EMU_RING_SLOTS") && getenv("PSD_EMU_RING_REPORT")) fprintf(stderr, "emu ring: %llu chunks drained\n", g_ring.drained);
   int prev_end = chrom_end[n_rows - 1];
   for (int s = 0; s < ns; s++) {
     const int st = (s < ns - 1) ? chrom_end[seg_row[s]] : chrom_start[0];

@@ -1,6 +1,8 @@
 // TEST TOOL: fiber scheduler behind warp_emu.h (x86-64 SysV only).
 #include "warp_emu.h"
 
+void (*psd_emu_ring_drain)(const StorePool* sp) = nullptr;
+
 namespace psd_emu {
 Warp* g_warp = nullptr;
 

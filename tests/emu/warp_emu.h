@@ -146,6 +146,12 @@ static inline unsigned long long psd_atomic_add_ull(unsigned long long* p, unsig
   unsigned long long old = *p; *p = old + v; return old;
 }
 static inline int psd_atomic_add_int(int* p, int v) { int old = *p; *p = old + v; return old; }
+static inline void psd_fence_system() {}
+// ring drain (store spill): the emulator has no concurrent host thread, so a warp that finds the
+// free queue empty runs the host's drain step itself (emu_fpop.cpp)
+struct StorePool;
+extern void (*psd_emu_ring_drain)(const StorePool* sp);
+#define PSD_RING_WAIT(sp, pos) do { if (*(sp).ring.free_tail <= (pos)) psd_emu_ring_drain(&(sp)); if (*(sp).ring.free_tail <= (pos)) { fprintf(stderr, "warp_emu: ring drain freed nothing\n"); abort(); } } while (0)
 // streaming (evict-first) stores of the cost-function store: plain stores here
 static inline void psd_st_cs_d2(double* p, double x, double y) { p[0] = x; p[1] = y; }
 static inline void psd_st_cs_i(int* p, int v) { *p = v; }

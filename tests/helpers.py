@@ -77,3 +77,24 @@ def c4_lite_problem(k, samples=2, scale=0.05):
 def c4_lite_problems(samples=2, scale=0.05):
     """All 24 x `samples` problems of config 4 lite, in (chromosome, sample) order."""
     return [c4_lite_problem(k, samples, scale) for k in range(24 * samples)]
+
+
+def parse_reference_db(path, n_rows):
+    """The reference's scratch db (src/PeakSegFPOPLog.cpp:12-34, 76-141): 2N std::streampos entries
+    (16 bytes: offset + mbstate; up functions at [0,N), down at [N,2N); 0 = never written), then the
+    appended records  int32 size | int32 n_pieces | int32 chromEnd | n x {f64 max_log_mean, i32 data_i,
+    f64 prev_log_mean}.  Returns {(row, which): (chromEnd, max_log_mean[], data_i[], prev_log_mean[])}."""
+    raw = open(path, "rb").read()
+    pos = np.frombuffer(raw, dtype="<i8", count=4 * n_rows).reshape(2 * n_rows, 2)[:, 0]
+    rec = np.dtype([("hi", "<f8"), ("bi", "<i4"), ("bx", "<f8")], align=False)
+    assert rec.itemsize == 20
+    out = {}
+    for el in range(2 * n_rows):
+        p = int(pos[el])
+        if p == 0:
+            continue
+        size, n_pieces, chrom_end = np.frombuffer(raw, dtype="<i4", count=3, offset=p)
+        assert size == 8 + 20 * n_pieces
+        a = np.frombuffer(raw, dtype=rec, count=int(n_pieces), offset=p + 12)
+        out[(el % n_rows, el // n_rows)] = (int(chrom_end), a["hi"].copy(), a["bi"].copy(), a["bx"].copy())
+    return out

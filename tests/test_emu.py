@@ -103,3 +103,70 @@ def test_degenerate_rows_terminate(ec):
         assert st in (0, 101, 103, 104), st
         seen.add(st)
     assert 0 in seen
+
+
+@pytest.fixture()
+def lat(ec, monkeypatch):
+    """The latency kernel's layout (fpop_lat.cu: -DPSD_G32, a block of two warps per problem, one chain
+    per warp, one block barrier per row) under the multi-warp emulator."""
+    monkeypatch.setenv("PSD_EMU_LIB", os.path.join(ROOT, "tests", "_build", "libpsd_emu_lat.so"))
+    return ec
+
+
+@pytest.mark.parametrize("seed,n,pen,cap", [(0, 1500, 0.0, 64), (1, 1500, 4.0, 64), (2, 2000, 100.0, 64), (3, 1200, 1e4, 64),
+                                            (4, 900, 1e6, 64), (5, 3000, 3e4, 48)])
+def test_latency_layout_poisson_row_by_row(lat, seed, n, pen, cap):
+    from peaksegdisk_b200 import synth
+    s, e, c = synth.poisson_problem(seed, n)
+    assert lat.compare(s, e, c, pen, cap=cap, descending=0)
+    assert lat.compare(s, e, c, pen, cap=cap, descending=1, trace=False)   # warps and lanes scheduled in the opposite order
+
+
+def test_latency_layout_reference_vectors_and_many_pieces(lat):
+    from peaksegdisk_b200 import synth
+    for case in golden("golden_small.json"):
+        if case["status"] != 0 or case["penalty"] == "Inf":
+            continue
+        s, e, c = parse_rows(case["input"])
+        if len(set(c.tolist())) < 2:
+            continue
+        assert lat.compare(s, e, c, float(case["penalty"]), cap=16, descending=k_order(case)), (case["name"], case["penalty"])
+    for n, pen in [(100, 0.0), (200, 1e2), (300, 1e4), (300, 1e6)]:   # > 32 pieces: the chunked loops at 32 lanes per chain
+        s, e, c = synth.increasing_problem(n)
+        assert lat.compare(s, e, c, pen, cap=512)
+
+
+def k_order(case):
+    return len(case["input"]) & 1
+
+
+@pytest.mark.parametrize("cap,pen", [(4, 50.0), (6, 1e3), (8, 1e4), (4, 0.0)])
+def test_latency_layout_tier_switch(lat, cap, pen):
+    """both warps must take the tier switch together (flag words are per warp and per row parity)"""
+    from peaksegdisk_b200 import synth
+    s, e, c = synth.poisson_problem(31, 1200)
+    info = {}
+    assert lat.compare(s, e, c, pen, cap=cap, spill_cap=256, info=info)
+    assert info["spills"] >= 1
+    assert lat.compare(s, e, c, pen, cap=cap, spill_cap=256, descending=1, trace=False)
+    orc, emu = lat.load()
+    st, _, _, _ = lat.run_emu(emu, *synth.increasing_problem(300), 1e4, cap=16, spill_cap=64)
+    assert st == 101
+
+
+@pytest.mark.parametrize("libname", ["libpsd_emu.so", "libpsd_emu_lat.so"])
+def test_store_ring_drain_protocol(ec, monkeypatch, libname):
+    """The store spill's DMA-drain protocol (StoreRing in fpop_warp.cuh): with 2 "HBM" chunks and a
+    ring of 3 slots every further chunk is written into a ring slot, published in the done-queue,
+    copied to the "host" region by the (emulated, synchronous) drain and its slot handed back through
+    the free-queue; the backtrack then reads the host region.  Both kernels' layouts."""
+    from peaksegdisk_b200 import synth
+    monkeypatch.setenv("PSD_EMU_LIB", os.path.join(ROOT, "tests", "_build", libname))
+    monkeypatch.setenv("PSD_EMU_HBM_CHUNKS", "2")
+    monkeypatch.setenv("PSD_EMU_RING_SLOTS", "3")
+    for seed, n, pen in [(2, 2000, 100.0), (5, 3000, 3e4)]:
+        s, e, c = synth.poisson_problem(seed, n)
+        assert ec.compare(s, e, c, pen, cap=64, descending=0)
+        assert ec.compare(s, e, c, pen, cap=64, descending=1, trace=False)
+    s, e, c = synth.increasing_problem(300)
+    assert ec.compare(s, e, c, 1e4, cap=512)

@@ -12,7 +12,7 @@ import os
 import numpy as np
 import pytest
 import oracle_bind
-from helpers import ROOT, GOLD, golden, sha, outputs, synth_rows, rows_text, parse_rows, loss_fields
+from helpers import ROOT, GOLD, golden, sha, outputs, synth_rows, rows_text, parse_rows, loss_fields, parse_reference_db
 
 pytestmark = pytest.mark.gpu
 LOSS_RTOL = 1e-9   # north_star tolerance for the fp64 total loss
@@ -373,23 +373,36 @@ def test_batched_sequential_search_follows_single_chains(psd, tmp_path):
         assert fit["others"]["penalty"].tolist() == single["others"]["penalty"].tolist()
 
 
-def test_store_spills_to_pinned_host_memory(psd):
+@pytest.mark.parametrize("spill_mode", [0.0, 1.0], ids=["dma-drain", "zero-copy"])
+def test_store_spills_to_pinned_host_memory(psd, spill_mode):
     """With an HBM pool far too small for the batch (and fixed, so it cannot grow) the cost-function
-    records overflow into mapped pinned host memory; the backtrack reads them back through the same
-    mapping.  Results must be identical to the all-HBM run and no extra wave may be needed."""
+    records spill to pinned host memory: by default through an HBM ring that a host thread drains
+    with cudaMemcpyAsync on a side stream while the DP kernel runs (spill_mode 0), or by zero-copy
+    stores through the mapping (spill_mode 1); the backtrack reads them back through the mapping.
+    Results must be identical to the all-HBM run and no extra wave may be needed."""
     from peaksegdisk_b200 import synth
     probs = [synth.poisson_problem(seed, 5000) + (pen,) for seed, pen in [(500, 0.0), (501, 20.0), (502, 1e3), (503, 1e5)]]
+    probs += [synth.increasing_problem(1000) + (1e4,)]         # records larger than an 8 KB chunk: written zero-copy in both modes
     base, ids = psd.solve_batch(probs)
     want = [(base.loss_row(i), base.segments(i)) for i in ids]
     lib = psd._lib.lib
     try:
         lib.psd_set_option(b"store_gb", 0.002)       # 2 MB of HBM: a fraction of one problem
         lib.psd_set_option(b"host_spill_gb", 0.25)
+        lib.psd_set_option(b"chunk_kb", 8.0)
+        lib.psd_set_option(b"spill_mode", spill_mode)
         plan, ids2 = psd.solve_batch(probs)
+        st = plan.stats()
+        assert (st["store_bytes_drained_dma"] > 0) == (spill_mode == 0.0), st
+        # the inspection path reads spilled records from the host region
+        hi, bi, bx = plan.store_function(ids2[0], len(probs[0][2]) - 1, 1)
+        hi0, bi0, bx0 = base.store_function(ids[0], len(probs[0][2]) - 1, 1)
+        assert np.array_equal(hi, hi0) and np.array_equal(bi, bi0) and np.array_equal(bx, bx0)
     finally:
         lib.psd_set_option(b"store_gb", 0.0)
         lib.psd_set_option(b"host_spill_gb", -1.0)
-    st = plan.stats()
+        lib.psd_set_option(b"chunk_kb", 64.0)
+        lib.psd_set_option(b"spill_mode", 0.0)
     assert st["store_bytes_spilled_host"] > 0, st
     for i, (loss, seg) in zip(ids2, want):
         assert plan.loss_row(i) == loss
@@ -482,6 +495,41 @@ def test_reference_interface_cpp_runs_the_gpu_solver(psd, tmp_path):
     assert loss == g["loss"] and sha(seg) == g["segments_sha256"]
     out = subprocess.run([exe, bg, "10.5", str(tmp_path)], capture_output=True, text=True, env=env)   # db path is a directory
     assert out.returncode == 1 and out.stderr == "Error: unable to write to cost function database file %s\n" % str(tmp_path)
+
+
+def test_store_contents_equal_the_reference_db(psd, tmp_path):
+    """Row a10 of the scope table: the HBM cost-function store must hold what the reference's
+    DiskVector holds.  The reference binary (oracle/_ref/ref_fpop, unmodified sources) solves
+    Mono27ac at 10.5 and a synthetic problem and leaves its db; every one of the 2N-1 stored
+    functions -- piece count, max_log_mean, data_i, prev_log_mean of every piece, bit for bit --
+    is read back from the GPU store (psd_plan_store_function) and compared."""
+    import subprocess
+    from peaksegdisk_b200 import synth
+    if not os.path.exists(oracle_bind.REF_BIN):
+        pytest.skip("oracle/_ref/ref_fpop not built")
+    _, ms, me, mc = synth.read_bedgraph(os.path.join(GOLD, "Mono27ac_coverage.bedGraph"))
+    probs = [(ms, me, mc, "10.5"), synth.poisson_problem(11, 3000) + ("250",), synth.increasing_problem(150) + ("1000",)]
+    plan = psd.Plan(0)
+    ids = [plan.add(s, e, c, float(pen)) for (s, e, c, pen) in probs]
+    plan.run()
+    assert plan.stats()["n_waves"] == 1
+    for k, (pid, (s, e, c, pen)) in enumerate(zip(ids, probs)):
+        bg = str(tmp_path / ("p%d.bedGraph" % k))
+        synth.write_bedgraph(bg, s, e, c)
+        assert subprocess.call([oracle_bind.REF_BIN, bg, pen, bg + ".db"], stdout=subprocess.DEVNULL) == 0
+        ref = parse_reference_db(bg + ".db", len(c))
+        assert len(ref) == 2 * len(c) - 1 and (0, 0) not in ref      # up_0 does not exist
+        n_pieces = 0
+        for (row, which), (chrom_end, hi, bi, bx) in ref.items():
+            ghi, gbi, gbx = plan.store_function(pid, row, which)
+            assert chrom_end == e[row]
+            assert len(ghi) == len(hi), (k, row, which)
+            assert np.array_equal(ghi.view(np.uint64), hi.view(np.uint64)) and np.array_equal(gbi, bi) and \
+                np.array_equal(gbx.view(np.uint64), bx.view(np.uint64)), (k, row, which)
+            n_pieces += len(hi)
+        assert n_pieces == round(plan.loss_row(pid)["mean.intervals"] * 2 * len(c))
+        hi0, _, _ = plan.store_function(pid, 0, 0)
+        assert len(hi0) == 0
 
 
 def test_concurrent_single_problem_calls_from_host_threads(psd, tmp_path):
