@@ -158,7 +158,8 @@ int psd_write_bedgraph(const char *path, const char *chrom, int64_t n_rows, cons
  * for tests and tools): the stored function `which` (0 = up, 1 = down) of bedGraph row `row` of
  * problem id, in the reference's record fields (src/PeakSegFPOPLog.cpp:18-34: max_log_mean, data_i,
  * prev_log_mean per piece).  *n_pieces receives the piece count; arrays need `cap` >= that many
- * entries (PSD_ERR_ARG otherwise).  Valid after a solve whose store fitted one wave. */
+ * entries (PSD_ERR_ARG otherwise).  Valid for problems solved in the plan's last store wave (all of them
+ * unless the store had to be recycled). */
 int psd_plan_store_function(psd_plan *plan, int id, int row, int which, int cap, int *n_pieces, double *max_log_mean,
                             int *data_i, double *prev_log_mean);
 

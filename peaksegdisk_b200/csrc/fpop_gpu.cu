@@ -214,6 +214,8 @@ struct psd_plan {
   int64_t total_rows = 0, total_index = 0;
   bool uploaded = false, solved = false, packed = false;
   std::vector<DpResult> results;               // per gpu problem (indexed like gpu_ids)
+  std::vector<int> result_wave;                // the store wave that produced each result (the pool holds only the last wave's records)
+  unsigned long long last_hbm_bytes = 0;       // HBM part of the store in the last wave (offsets beyond it address the host region)
   std::vector<int> seg_row; std::vector<double> seg_x;
   unsigned long long n_seg_total = 0;
   psd_stats stats;
@@ -605,7 +607,7 @@ template <int MAXW, int MINB>
 static int configure_one(psd_plan* p, psd_plan::LaunchCfg& L, int cap0, int blocks) {
   int cap = cap0;
   if (cap < 8) cap = 8;
-  cap = (cap + 1) & ~1;
+  cap = (cap + 3) & ~3;   // multiples of 4 keep every list array 16-byte aligned (bulk copies of the record store)
   for (;;) {
     const int ccap = 2 * cap;
     const size_t per_warp = psd_ws_bytes(cap, ccap);
@@ -621,7 +623,7 @@ static int configure_one(psd_plan* p, psd_plan::LaunchCfg& L, int cap0, int bloc
       CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fpop_dp_kernel<MAXW, MINB>, w * 32, smem));
       if (nb >= blocks) { L.ok = true; L.blocks = blocks; L.wpb = w; L.cap = cap; L.ccap = ccap; L.smem = smem; return 0; }
     }
-    cap /= 2;
+    cap = ((cap / 2) + 3) & ~3;
     if (cap < 8) { L.ok = false; return 0; }
   }
 }
@@ -760,6 +762,7 @@ int psd_plan_solve_impl(psd_plan* p, void* stream_v) {
   S.dp_ms = S.backtrack_ms = 0; S.n_launches = 0; S.n_waves = 0; S.n_overflow_tier = 0; S.n_latency_waves = 0;
   S.rows_solved = 0; S.store_bytes_algorithmic = 0; S.store_bytes_written = 0; S.backtrack_bytes_read = 0; S.store_bytes_spilled_host = 0; S.store_bytes_drained_dma = 0;
   p->results.assign(ng, DpResult());
+  p->result_wave.assign(ng, -1);
   p->n_seg_total = 0;
   if (ng == 0) { p->solved = true; return 0; }
   int rc = configure_kernel(p);
@@ -826,8 +829,8 @@ int psd_plan_solve_impl(psd_plan* p, void* stream_v) {
         const int resident = std::max(1, std::min(per_sm, 8));
         const size_t per_block = std::min((size_t)p->prop.sharedMemPerMultiprocessor / resident - 1024, (size_t)p->prop.sharedMemPerBlockOptin);
         long cap = ((long)per_block - PSD_TAB_BYTES - PSD_LAT_SHARED_BYTES - 32) / 328;   // PSD_WS_BYTES(cap, 2 cap) = 16 + 328 cap
-        cap = std::min(640L, cap) & ~1L;
-        if (p->opt.piece_cap < 48) cap = std::min(cap, (long)((p->opt.piece_cap + 1) & ~1));   // a tier below the default is a request (tests force the global tier with it)
+        cap = std::min(640L, cap) & ~3L;
+        if (p->opt.piece_cap < 48) cap = std::min(cap, (long)((p->opt.piece_cap + 3) & ~3));   // a tier below the default is a request (tests force the global tier with it)
         if (cap < 8) cap = 8;
         K.cap_s = (int)cap; K.ccap_s = 2 * K.cap_s; K.ws_s_bytes = psd_ws_bytes(K.cap_s, K.ccap_s);
         // the block's global workspace takes what outgrows shared memory: with one block per SM it is
@@ -958,6 +961,7 @@ int psd_plan_solve_impl(psd_plan* p, void* stream_v) {
     CK(cudaGetLastError());
     CK(cudaEventRecord(p->ev[4], st));
     S.n_launches += 2; S.n_waves++;
+    p->last_hbm_bytes = K.pool.n_chunks * chunk;
     // the wave's status words decide what (if anything) has to be re-run
     CK(cudaMemcpyAsync(p->p_results, p->d_results, sizeof(DpResult) * ng, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(p->p_cursors, p->d_cursors, sizeof(unsigned long long) * 8, cudaMemcpyDeviceToHost, st));
@@ -974,7 +978,7 @@ int psd_plan_solve_impl(psd_plan* p, void* stream_v) {
       const DpResult& r = p->p_results[g];
       if (r.status == PSD_ST_PIECE_OVERFLOW) overflow_acc.push_back(g);
       else if (r.status == PSD_ST_STORE_EXHAUSTED) exhausted.push_back(g);
-      else { p->results[g] = r; if (r.pad_ > 0) S.n_overflow_tier++; }
+      else { p->results[g] = r; p->result_wave[g] = S.n_waves; if (r.pad_ > 0) S.n_overflow_tier++; }
     }
     if (!exhausted.empty()) {
       // Some problems ran out of store.  In order of preference: a bigger HBM pool (the automatic
@@ -1093,16 +1097,23 @@ int psd_plan_download_impl(psd_plan* p, void* stream_v) {
 // a single store wave (the pool then still holds every record).  A few small D2H copies per call:
 // an inspection path for tests and tools, not a hot path.
 int psd_plan_store_function_impl(psd_plan* p, int id, int row, int which, int cap, int* n_out, double* hi, int* back_i, double* back_x) {
-  if (!p->solved || p->stats.n_waves != 1) { g_last_error = "store inspection needs a solved plan whose store fitted one wave"; return PSD_ERR_ARG; }
+  if (!p->solved) { g_last_error = "store inspection needs a solved plan"; return PSD_ERR_ARG; }
   if (id < 0 || id >= (int)p->probs.size() || which < 0 || which > 1 || !n_out) return PSD_ERR_ARG;
   const HostProblem& h = p->probs[id];
   if (h.status != 0 || h.trivial || h.result_status != 0 || row < 0 || row >= h.n_rows) return PSD_ERR_ARG;
+  {
+    const auto it = std::find(p->gpu_ids.begin(), p->gpu_ids.end(), id);
+    if (it == p->gpu_ids.end() || p->result_wave[it - p->gpu_ids.begin()] != p->stats.n_waves) {
+      g_last_error = "store inspection: this problem was solved in an earlier store wave, its records have been recycled";
+      return PSD_ERR_ARG;
+    }
+  }
   CK(cudaSetDevice(p->device));
   unsigned long long off = 0;
   CK(cudaMemcpy(&off, p->d_index + h.index_off + row, sizeof off, cudaMemcpyDeviceToHost));
   auto fetch = [&](void* dst, unsigned long long o, size_t bytes) -> cudaError_t {
-    if (o < p->pool_bytes) return cudaMemcpy(dst, p->d_pool + o, bytes, cudaMemcpyDeviceToHost);
-    memcpy(dst, p->h_spill + (o - p->pool_bytes), bytes);     // spilled record: already in pinned host memory
+    if (o < p->last_hbm_bytes) return cudaMemcpy(dst, p->d_pool + o, bytes, cudaMemcpyDeviceToHost);
+    memcpy(dst, p->h_spill + (o - p->last_hbm_bytes), bytes);     // spilled record: already in pinned host memory
     return cudaSuccess;
   };
   unsigned hdr[4];
@@ -1113,10 +1124,10 @@ int psd_plan_store_function_impl(psd_plan* p, int id, int row, int which, int ca
   *n_out = n;
   if (n > cap) return PSD_ERR_ARG;
   if (n == 0) return 0;
-  std::vector<double> pairs(2 * (size_t)n);
-  CK(fetch(pairs.data(), off + 16 + 16ull * (which ? n_up : 0), 16ull * n));
-  CK(fetch(back_i, off + 16 + 16ull * (n_up + n_down) + 4ull * (which ? n_up : 0), 4ull * n));
-  for (int k = 0; k < n; k++) { hi[k] = pairs[2 * k]; back_x[k] = pairs[2 * k + 1]; }
+  const RecLayout R = rec_layout(n_up, n_down);
+  CK(fetch(hi, off + R.hi[which], 8ull * n));
+  CK(fetch(back_x, off + R.bx[which], 8ull * n));
+  CK(fetch(back_i, off + R.bi[which], 4ull * n));
   return 0;
 }
 

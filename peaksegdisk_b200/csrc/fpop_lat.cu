@@ -52,3 +52,14 @@ int psd_lat_launch(const DpKernelParams& P, int grid, size_t smem_bytes, void* s
   fpop_dp_lat_kernel<<<grid, PSD_LAT_WARPS * 32, smem_bytes, (cudaStream_t)stream>>>(P);
   return (int)cudaGetLastError();
 }
+
+#if defined(PSD_TIMING)
+#include <cstring>
+extern "C" int psd_debug_read_lat(unsigned long long* out, int n, int reset) {
+  unsigned long long tmp[32];
+  if (cudaMemcpyFromSymbol(tmp, psd_dbg, sizeof tmp) != cudaSuccess) return -1;
+  for (int i = 0; i < n && i < 32; i++) out[i] = tmp[i];
+  if (reset) { memset(tmp, 0, sizeof tmp); cudaMemcpyToSymbol(psd_dbg, tmp, sizeof tmp); }
+  return 0;
+}
+#endif

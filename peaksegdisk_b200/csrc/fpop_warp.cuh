@@ -37,7 +37,7 @@
 // tests/emu/warp_emu.h (PSD_EMU) where 32 fibers stand in for the lanes -- a test tool only.
 // Experiment switches (never set in the product build): PSD_TIMING (cycle counters), PSD_SPEC,
 // PSD_RETURN_NUM/DEN, PSD_INLINE_MATH / PSD_INLINE_EXP / PSD_INLINE_LOG, PSD_NOINLINE_ROOTS,
-// PSD_NOINLINE_OPS, PSD_NO_SHARED_HINT;
+// PSD_NOINLINE_OPS, PSD_NO_SHARED_HINT, PSD_NO_BULK_STORE;
 // what they showed is in profiles/README.md.
 #pragma once
 #include "psd_math.h"
@@ -94,15 +94,32 @@ PSD_DEV void psd_st_cs_i(int* p, int v) { __stcs(p, v); }
 PSD_DEV void psd_st_cs_u64(unsigned long long* p, unsigned long long v) { __stcs(p, v); }
 PSD_DEV void psd_st_cs_u4(unsigned* p, unsigned a, unsigned b, unsigned c, unsigned d) { __stcs((uint4*)p, make_uint4(a, b, c, d)); }
 PSD_DEV void psd_fence_system() { __threadfence_system(); }
+// Bulk asynchronous copies shared -> global (the copy engine of the SM moves the bytes; the issuing
+// lane goes on).  Sizes are multiples of 16 bytes, both addresses 16-byte aligned.  One lane issues
+// the copies of a record as one bulk group and later waits until the engine has READ the sources.
+PSD_DEV void psd_bulk_s2g(void* dst_global, const void* src_shared, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+               :: "l"(dst_global), "r"((unsigned)__cvta_generic_to_shared(src_shared)), "r"(bytes) : "memory");
+}
+PSD_DEV void psd_bulk_fence() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }   // lanes' shared-memory writes -> visible to the copy engine
+PSD_DEV void psd_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+PSD_DEV void psd_bulk_wait_read_1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }   // all but the newest group have read their sources
+PSD_DEV void psd_bulk_wait_read_0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+PSD_DEV void psd_bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }           // ... and written their destinations
 // a warp waits (one lane spinning) until the host has handed back a ring slot for free-queue position pos
-#define PSD_RING_WAIT(sp, pos) do { unsigned ns_ = 64; while (*(sp).ring.free_tail <= (pos)) { __nanosleep(ns_); if (ns_ < 8192) ns_ <<= 1; } } while (0)
+// (gives up after ~10 s without a slot -- a dead host thread must not hang the GPU; the problem then reports status 102)
+#define PSD_RING_WAIT(sp, pos) do { unsigned ns_ = 64, spins_ = 0; while (*(sp).ring.free_tail <= (pos) && spins_ < (1u << 20)) { __nanosleep(ns_); if (ns_ < 8192) ns_ <<= 1; spins_++; } } while (0)
 #endif
 
 // PSD_TIMING (experiment builds only): per-section cycle counters, accumulated by lane 0 / lane 16
 #if defined(PSD_TIMING) && !defined(PSD_EMU)
 __device__ unsigned long long psd_dbg[32];
 #define PSD_T0(v) const long long v = clock64()
+#if defined(PSD_G32)
+#define PSD_T1(v, slot) do { if ((threadIdx.x & 31u) == 0) atomicAdd(&psd_dbg[slot], (unsigned long long)(clock64() - v)); } while (0)
+#else
 #define PSD_T1(v, slot) do { if ((threadIdx.x & 15u) == 0) atomicAdd(&psd_dbg[slot], (unsigned long long)(clock64() - v)); } while (0)
+#endif
 #else
 #define PSD_T0(v) do {} while (0)
 #define PSD_T1(v, slot) do {} while (0)
@@ -129,6 +146,11 @@ extern unsigned long long psd_emu_stats[8][65];
 #ifndef PSD_RETURN_NUM
 #define PSD_RETURN_NUM 1
 #define PSD_RETURN_DEN 2
+#endif
+#if defined(PSD_NO_BULK_STORE)   /* experiment switch: records written by the lanes even from shared memory */
+#define PSD_BULK_STORE false
+#else
+#define PSD_BULK_STORE true
 #endif
 #define PSD_EPS 1e-12        /* NEWTON_EPSILON, src/funPieceListLog.cpp:9 */
 #define PSD_MAX_STEPS 100    /* NEWTON_STEPS,   src/funPieceListLog.cpp:10 */
@@ -924,10 +946,13 @@ PSD_DEVNI void best_piece(const WarpWs ws, const PList f, double dmin, double* b
 // ---- HBM cost-function store ------------------------------------------------------------------------
 // A pool of fixed-size chunks; a warp appends its rows' records to its current chunk and takes a new
 // one (atomicAdd on the pool cursor) when the next record does not fit.  Record of row t, 16-byte
-// aligned:   u32 n_up | u32 n_down | u32 row | u32 0
-//            n_up   x { f64 hi, f64 back_x }      (128-bit stores, one piece per lane)
-//            n_down x { f64 hi, f64 back_x }
-//            (n_up + n_down) x i32 back_i, padded to 16 bytes
+// aligned, every array padded to a multiple of 16 bytes (U = n_up rounded up to 2, Ui = to 4; D, Di alike):
+//   u32 n_up | u32 n_down | u32 row | u32 0
+//   f64 up.hi[U] | f64 up.back_x[U] | f64 down.hi[D] | f64 down.back_x[D] | i32 up.back_i[Ui] | i32 down.back_i[Di]
+// These are the arrays of the shared-memory piece lists as they lie there, so a record is written by
+// SIX BULK COPIES shared -> global (cp.async.bulk) issued by one lane; the lists are not overwritten
+// before row t+2, by which time the copy engine has read them.  (Lists in the global-memory tier and
+// records that go to host memory through the mapping are written by the lanes instead.)
 // index[t] = byte offset of the record in the pool.  The reference's record
 // (src/PeakSegFPOPLog.cpp:12-34) carries the same fields at 8 + 20 bytes per piece per function.
 // When the HBM pool is exhausted and a pinned host region is configured the store SPILLS: chunk numbers
@@ -960,9 +985,18 @@ struct StorePool {
 };
 struct StoreWriter { unsigned long long cur, end; long long slot; };   // slot: ring slot of the open chunk, -1 = none
 
+struct RecLayout { unsigned hi[2], bx[2], bi[2]; };   // byte offsets of the six arrays inside a record
+PSD_HD RecLayout rec_layout(int n_up, int n_down) {
+  const unsigned U = (unsigned)(n_up + 1) & ~1u, D = (unsigned)(n_down + 1) & ~1u, Ui = (unsigned)(n_up + 3) & ~3u;
+  RecLayout L;
+  L.hi[0] = 16u; L.bx[0] = 16u + 8u * U; L.hi[1] = 16u + 16u * U; L.bx[1] = 16u + 16u * U + 8u * D;
+  L.bi[0] = 16u + 16u * (U + D); L.bi[1] = L.bi[0] + 4u * Ui;
+  return L;
+}
 PSD_DEV unsigned long long store_record_bytes(int n_up, int n_down) {
-  const unsigned long long np = (unsigned long long)(n_up + n_down);
-  return 16ull + 16ull * np + ((4ull * np + 15ull) & ~15ull);
+  const unsigned long long U = (unsigned long long)((n_up + 1) & ~1), D = (unsigned long long)((n_down + 1) & ~1);
+  const unsigned long long Ui = (unsigned long long)((n_up + 3) & ~3), Di = (unsigned long long)((n_down + 3) & ~3);
+  return 16ull + 16ull * (U + D) + 4ull * (Ui + Di);
 }
 
 // ONE thread: publish the ring chunk a writer is leaving (its stores must already be visible system-wide)
@@ -986,6 +1020,7 @@ PSD_DEV unsigned long long store_take(const StorePool& sp, unsigned long long ne
     // host chunks: ring positions from the bottom, zero-copy allocations from the top
     if (pos + 1ull + *(volatile unsigned long long*)sp.host_cursor > sp.host_chunks) return ~0ull;
     PSD_RING_WAIT(sp, pos);
+    if (*sp.ring.free_tail <= pos) return ~0ull;
     psd_fence_system();   // the slot id was written before free_tail was advanced
     *slot = (long long)sp.ring.free_q[pos & sp.ring.q_mask];
     return sp.n_chunks + pos;
@@ -999,6 +1034,7 @@ PSD_DEV unsigned long long store_take(const StorePool& sp, unsigned long long ne
 // the writer's open chunk, if it is a ring chunk, is complete: make the warp's stores visible, publish
 PSD_DEV void store_close(const StorePool& sp, StoreWriter& w) {
   if (w.slot < 0) return;
+  if (psd_lane() == 0) psd_bulk_wait_all();   // bulk copies into the chunk have landed
   psd_fence_system();
   psd_syncwarp();
   if (psd_lane() == 0) store_ring_publish(sp, w.end / sp.chunk_bytes - 1ull - sp.n_chunks, w.slot);
@@ -1035,24 +1071,44 @@ PSD_DEV unsigned char* store_wptr(const StorePool& sp, const StoreWriter& w, uns
   return store_ptr(sp, off);
 }
 
-#if !defined(PSD_G32)
+// one function of a record written by lanes (global-tier lists, or a destination in host memory)
 template <bool SH>
-PSD_DEV void store_write(const WarpWs ws, unsigned char* rec, int row, const PList up, const PList down) {
-  if (SH) { PSD_ASSUME_SHARED(up.base); PSD_ASSUME_SHARED(down.base); }
-  // lanes 0-15 write the up function, lanes 16-31 the down function: one loop, one 128-bit store
-  // {hi, back_x} and one 32-bit store {back_i} per piece
-  const int lane = psd_lane();
-  const int cap = ws.cap;
-  const int grp = lane >> 4, gl = lane & 15;
-  if (lane == 0) psd_st_cs_u4((unsigned*)rec, (unsigned)up.n, (unsigned)down.n, (unsigned)row, 0u);
-  const PList L = grp ? down : up;
+PSD_DEV void store_fn_lanes(const WarpWs ws, unsigned char* rec, const RecLayout R, const PList L, int which, int lane, int n_lanes) {
   if (SH) PSD_ASSUME_SHARED(L.base);
-  double* pairs = (double*)(rec + 16) + (grp ? 2 * up.n : 0);
-  int* bis = (int*)((double*)(rec + 16) + 2 * (up.n + down.n)) + (grp ? up.n : 0);
-  for (int k = gl; k < L.n; k += PSD_G) {
-    psd_st_cs_d2(pairs + 2 * k, PL_X(L, k), PL_P(L, k));
-    psd_st_cs_i(bis + k, PL_I(L, k));
+  const int cap = ws.cap;
+  double* hi = (double*)(rec + R.hi[which]); double* bx = (double*)(rec + R.bx[which]); int* bi = (int*)(rec + R.bi[which]);
+  for (int k = lane; k < L.n; k += n_lanes) { hi[k] = PL_X(L, k); bx[k] = PL_P(L, k); psd_st_cs_i(bi + k, PL_I(L, k)); }
+}
+// ... and by three bulk copies shared -> global (issued by ONE lane, after psd_bulk_fence)
+PSD_DEV void store_fn_bulk(const WarpWs ws, unsigned char* rec, const RecLayout R, const PList L, int which) {
+  const int cap = ws.cap;
+  if (L.n == 0) return;
+  const unsigned nd = 8u * ((unsigned)(L.n + 1) & ~1u), ni = 4u * ((unsigned)(L.n + 3) & ~3u);
+  psd_bulk_s2g(rec + R.hi[which], &PL_X(L, 0), nd);
+  psd_bulk_s2g(rec + R.bx[which], &PL_P(L, 0), nd);
+  psd_bulk_s2g(rec + R.bi[which], &PL_I(L, 0), ni);
+}
+
+#if !defined(PSD_G32)
+// bulk: the lists are in shared memory and the record in device memory
+template <bool SH>
+PSD_DEV void store_write(const WarpWs ws, unsigned char* rec, int row, const PList up, const PList down, bool bulk) {
+  const int lane = psd_lane();
+  const RecLayout R = rec_layout(up.n, down.n);
+  if (lane == 0) psd_st_cs_u4((unsigned*)rec, (unsigned)up.n, (unsigned)down.n, (unsigned)row, 0u);
+  if (SH && bulk) {
+    // the lists were completed before the phase barrier; one lane hands them to the copy engine
+    if (lane == 0) {
+      psd_bulk_fence();
+      store_fn_bulk(ws, rec, R, up, 0);
+      store_fn_bulk(ws, rec, R, down, 1);
+      psd_bulk_commit();
+      psd_bulk_wait_read_1();   // the record of row t-1 has left its lists (they are written again in row t+1)
+    }
+    return;
   }
+  // lanes 0-15 write the up function, lanes 16-31 the down function
+  store_fn_lanes<SH>(ws, rec, R, (lane >> 4) ? down : up, lane >> 4, lane & 15, 16);
 }
 #endif
 
@@ -1242,6 +1298,7 @@ PSD_DEV void dp_run_queue(const WarpWs& ws_s, const WarpWs& ws_g, const DpQueue&
       if (flags) {
         if ((flags & PSD_FLAG_OVERFLOW) && !(flags & PSD_FLAG_INTERNAL) && !in_g && ws_g.cap > 0) {
           // this row does not fit the shared-memory tier: repeat it from the global workspace
+          if (lane == 0) psd_bulk_wait_read_0();   // no record copy is still reading the shared-memory lists
           psd_syncwarp();
           pl_move(upP.base, ws_s.cap, ws_list(ws_g, 0), ws_g.cap, upP.n);
           pl_move(downP.base, ws_s.cap, ws_list(ws_g, 1), ws_g.cap, downP.n);
@@ -1272,8 +1329,10 @@ PSD_DEV void dp_run_queue(const WarpWs& ws_s, const WarpWs& ws_g, const DpQueue&
           const unsigned long long off = store_alloc(sp, sw, store_record_bytes(upP.n, downP.n));
           if (off == ~0ull) status = PSD_ST_STORE_EXHAUSTED;
           else {
-            if (in_g) store_write<false>(ws, store_wptr(sp, sw, off), t, upP, downP);
-            else store_write<true>(ws, store_wptr(sp, sw, off), t, upP, downP);
+            // bulk copies need a device-memory destination: HBM, or the writer's ring slot
+            const bool dev_dst = PSD_BULK_STORE && (sw.slot >= 0 || off < sp.n_chunks * sp.chunk_bytes);
+            if (in_g) store_write<false>(ws, store_wptr(sp, sw, off), t, upP, downP, false);
+            else store_write<true>(ws, store_wptr(sp, sw, off), t, upP, downP, dev_dst);
             if (lane == (t & 31)) my_off = off;
             if ((t & 31) == 31 || t == N - 1) {
               const int r = (t & ~31) + lane;
@@ -1285,6 +1344,7 @@ PSD_DEV void dp_run_queue(const WarpWs& ws_s, const WarpWs& ws_g, const DpQueue&
         if (status != PSD_ST_OK || t == N) {
           double bc = 0, bx = 0, bpx = 0; int bbi = -1;
           if (status == PSD_ST_OK) best_piece(ws, downP, dmin, &bc, &bx, &bbi, &bpx);
+          if (lane == 0) psd_bulk_wait_read_0();   // the next problem starts in the same lists
           if (lane == 0) {
             DpResult* res = &Q.results[id];
             res->status = status; res->back_i = bbi; res->best_cost = bc; res->best_x = bx; res->back_x = bpx;
@@ -1334,7 +1394,7 @@ struct LatShared {
 PSD_DEV unsigned long long store_alloc_cta(const StorePool& sp, StoreWriter& w, unsigned long long bytes, LatShared* sh, int grp) {
   if (w.cur + bytes > w.end) {
     const unsigned long long need = (bytes + sp.chunk_bytes - 1) / sp.chunk_bytes;
-    if (w.slot >= 0) { psd_fence_system(); psd_cta_sync(); }
+    if (w.slot >= 0) { if (psd_lane() == 0) psd_bulk_wait_all(); psd_fence_system(); psd_cta_sync(); }
     if (grp == 0 && psd_lane() == 0) {
       if (w.slot >= 0) store_ring_publish(sp, w.end / sp.chunk_bytes - 1ull - sp.n_chunks, w.slot);
       long long slot = -1;
@@ -1355,17 +1415,20 @@ PSD_DEV unsigned long long store_alloc_cta(const StorePool& sp, StoreWriter& w, 
 
 // one function's part of a row's record, written by that chain's warp (layout: see StorePool)
 template <bool SH>
-PSD_DEV void store_write_fn(const WarpWs ws, unsigned char* rec, int row, const PList L, int which, int n_up, int n_down) {
-  if (SH) PSD_ASSUME_SHARED(L.base);
+PSD_DEV void store_write_fn(const WarpWs ws, unsigned char* rec, int row, const PList L, int which, int n_up, int n_down, bool bulk) {
   const int lane = psd_lane();
-  const int cap = ws.cap;
+  const RecLayout R = rec_layout(n_up, n_down);
   if (which == 0 && lane == 0) psd_st_cs_u4((unsigned*)rec, (unsigned)n_up, (unsigned)n_down, (unsigned)row, 0u);
-  double* pairs = (double*)(rec + 16) + (which ? 2 * n_up : 0);
-  int* bis = (int*)((double*)(rec + 16) + 2 * (n_up + n_down)) + (which ? n_up : 0);
-  for (int k = lane; k < L.n; k += 32) {
-    psd_st_cs_d2(pairs + 2 * k, PL_X(L, k), PL_P(L, k));
-    psd_st_cs_i(bis + k, PL_I(L, k));
+  if (SH && bulk) {
+    if (lane == 0) {
+      psd_bulk_fence();
+      store_fn_bulk(ws, rec, R, L, which);
+      psd_bulk_commit();
+      psd_bulk_wait_read_1();
+    }
+    return;
   }
+  store_fn_lanes<SH>(ws, rec, R, L, which, lane, 32);
 }
 
 PSD_DEV void dp_run_latency(const WarpWs& ws_s, const WarpWs& ws_g, const DpProblem& pb, DpResult* res, const StorePool& sp, LatShared* sh
@@ -1421,21 +1484,29 @@ PSD_DEV void dp_run_latency(const WarpWs& ws_s, const WarpWs& ws_g, const DpProb
     } else {
       // my chain of row t: min_less(down_{t-1}) / min_more(up_{t-1}), then the envelope with my own
       // previous function; nothing here depends on what the other warp computes for row t
+      PSD_T0(ta);
       if (grp == 0 || t >= 2)
         tmp.n = in_g ? min_mono_op<false>(wg, grp ? upP : downP, tmp, dmin, t - 1, penalty / cw_done, grp)
                      : min_mono_op<true>(wg, grp ? upP : downP, tmp, dmin, t - 1, penalty / cw_done, grp);
+      PSD_T1(ta, grp);
       const PList prev = grp ? downP : upP;
       const PList dst = grp ? downN : upN;
+      PSD_T0(tb);
       if (t == 1) n_out = in_g ? copy_rescale_op<false>(wg, grp ? downP : tmp, dst, rs) : copy_rescale_op<true>(wg, grp ? downP : tmp, dst, rs);
       else n_out = in_g ? min_env_op<false>(wg, tmp, prev, tmp, prev, dst, dmin, rs) : min_env_op<true>(wg, tmp, prev, tmp, prev, dst, dmin, rs);
+      PSD_T1(tb, 2 + grp);
       if (lane == 0) sh->n_out[t & 1][grp] = n_out;
     }
+    PSD_T0(tw);
     psd_cta_sync();   // the row's one barrier: both new functions are complete and visible
+    PSD_T1(tw, 5);
+    PSD_T0(tc);
     const int flags = ((volatile int*)flag_words)[2 * (t & 1)] | ((volatile int*)flag_words)[2 * (t & 1) + 1];
     bool redo = false;
     if (flags) {
       if ((flags & PSD_FLAG_OVERFLOW) && !(flags & PSD_FLAG_INTERNAL) && !in_g && ws_g.cap > 0) {
         // this row does not fit the shared-memory tier: repeat it from the global workspace
+        if (lane == 0) psd_bulk_wait_read_0();   // no record copy is still reading the shared-memory lists
         if (grp == 0) pl_move(upP.base, ws_s.cap, ws_list(ws_g, 0), ws_g.cap, upP.n);
         else pl_move(downP.base, ws_s.cap, ws_list(ws_g, 1), ws_g.cap, downP.n);
         in_g = true; n_spill++;
@@ -1464,8 +1535,9 @@ PSD_DEV void dp_run_latency(const WarpWs& ws_s, const WarpWs& ws_g, const DpProb
       const unsigned long long off = store_alloc_cta(sp, sw, store_record_bytes(upP.n, downP.n), sh, grp);
       if (off == ~0ull) status = PSD_ST_STORE_EXHAUSTED;
       else {
-        if (in_g) store_write_fn<false>(ws, store_wptr(sp, sw, off), t, grp ? downP : upP, grp, upP.n, downP.n);
-        else store_write_fn<true>(ws, store_wptr(sp, sw, off), t, grp ? downP : upP, grp, upP.n, downP.n);
+        const bool dev_dst = PSD_BULK_STORE && (sw.slot >= 0 || off < sp.n_chunks * sp.chunk_bytes);
+        if (in_g) store_write_fn<false>(ws, store_wptr(sp, sw, off), t, grp ? downP : upP, grp, upP.n, downP.n, false);
+        else store_write_fn<true>(ws, store_wptr(sp, sw, off), t, grp ? downP : upP, grp, upP.n, downP.n, dev_dst);
         if (grp == 0) {
           if (lane == (t & 31)) my_off = off;
           if ((t & 31) == 31 || t == N - 1) {
@@ -1475,6 +1547,7 @@ PSD_DEV void dp_run_latency(const WarpWs& ws_s, const WarpWs& ws_g, const DpProb
         }
       }
     }
+    PSD_T1(tc, 4);
     t++;
     if (status != PSD_ST_OK || t == N) {
       if (grp == 0) {
@@ -1497,6 +1570,7 @@ PSD_DEV void dp_run_latency(const WarpWs& ws_s, const WarpWs& ws_g, const DpProb
       psd_cta_sync();
     }
   }
+  if (lane == 0) psd_bulk_wait_all();   // no bulk copy may outlive the block's shared memory
   if (sw.slot >= 0) {   // the ring chunk still open at the end goes to the host like the others
     psd_fence_system();
     psd_cta_sync();
@@ -1526,8 +1600,10 @@ PSD_DEV void backtrack_problem(const StorePool& sp, const unsigned long long* in
     const int n_up = (int)hdr[0], n_down = (int)hdr[1];
     const int n = use_down ? n_down : n_up;
     bytes += 24ull + 20ull * (unsigned)n;
-    const double* pairs = (const double*)(rec + 16) + (use_down ? 2 * n_up : 0);
-    const int* bis = (const int*)((const double*)(rec + 16) + 2 * (n_up + n_down)) + (use_down ? n_up : 0);
+    const RecLayout R = rec_layout(n_up, n_down);
+    const double* his = (const double*)(rec + R.hi[use_down]);
+    const double* bxs = (const double*)(rec + R.bx[use_down]);
+    const int* bis = (const int*)(rec + R.bi[use_down]);
     if (lane == 0) { seg_row[n_seg - 1] = back_i; seg_x[n_seg - 1] = best_x; }
     n_seg++;
     use_down ^= 1;
@@ -1537,12 +1613,12 @@ PSD_DEV void backtrack_problem(const StorePool& sp, const unsigned long long* in
     for (int base = 0; base < n && !found; base += 32) {
       const int k = base + lane;
       double hi = 0, lo = -PSD_INF;
-      if (k < n) { hi = pairs[2 * k]; if (k > 0) lo = pairs[2 * (k - 1)]; }
+      if (k < n) { hi = his[k]; if (k > 0) lo = his[k - 1]; }
       const unsigned mask = psd_ballot(k < n && lo <= best_x && best_x <= hi);
       if (mask) {
         const int kk = base + psd_ffs(mask) - 1;
         back_i = bis[kk];
-        back_x = pairs[2 * kk + 1];
+        back_x = bxs[kk];
         found = 1;
       }
     }

@@ -147,6 +147,13 @@ static inline unsigned long long psd_atomic_add_ull(unsigned long long* p, unsig
 }
 static inline int psd_atomic_add_int(int* p, int v) { int old = *p; *p = old + v; return old; }
 static inline void psd_fence_system() {}
+// bulk shared -> global copies of the record store: immediate copies here
+static inline void psd_bulk_s2g(void* dst, const void* src, unsigned bytes) { memcpy(dst, src, bytes); }
+static inline void psd_bulk_fence() {}
+static inline void psd_bulk_commit() {}
+static inline void psd_bulk_wait_read_1() {}
+static inline void psd_bulk_wait_read_0() {}
+static inline void psd_bulk_wait_all() {}
 // ring drain (store spill): the emulator has no concurrent host thread, so a warp that finds the
 // free queue empty runs the host's drain step itself (emu_fpop.cpp)
 struct StorePool;
