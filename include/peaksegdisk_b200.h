@@ -170,8 +170,9 @@ int psd_plan_store_function(psd_plan *plan, int id, int row, int which, int cap,
  * "spill_mode" (how spilled records reach the host: 0 = written into an HBM ring that a host thread drains
  * with cudaMemcpyAsync on a side stream (default), 1 = zero-copy stores through the mapping), "ring_gb",
  * "occupancy_mode" (0 = choose per batch, 1 = one block of 14 warps per SM, 2 = two blocks),
- * "latency_mode" (0 = waves of at most "latency_max_blocks" (default 2) problems per SM run the latency
- * kernel: one problem per block, one chain per warp; 1 = always; 2 = never),
+ * "latency_mode" (0 = per wave, whichever of the two kernels a makespan model predicts to finish first:
+ * the latency kernel -- one problem per block, one chain per warp -- for few or long problems, never beyond
+ * "latency_max_blocks" (16) problems per SM; 1 = always the latency kernel; 2 = never),
  * "devices" (GPUs one psd_fpop_disk_batch call may use: 1 = the current device (default), k = the
  * first k, <= 0 = all; problems are dealt longest-first, one plan and host thread per GPU). */
 int psd_set_option(const char *name, double value);

@@ -128,7 +128,7 @@ fpop_backtrack_kernel(const BtKernelParams P) {
 namespace {
 thread_local std::string g_last_error;
 std::mutex g_opt_mutex;
-struct Options { int piece_cap = 48; int overflow_cap = 8192; double store_gb = 0; int chunk_kb = 64; int max_warps_per_sm = 0; int blocks_per_sm = 1; int spill_cap = 512; double host_spill_gb = -1; int occupancy_mode = 0; int devices = 1; int queue_mode = 0; int latency_mode = 0; int latency_max_blocks = 2; int spill_mode = 0; double ring_gb = 0; } g_opt;
+struct Options { int piece_cap = 48; int overflow_cap = 8192; double store_gb = 0; int chunk_kb = 64; int max_warps_per_sm = 0; int blocks_per_sm = 1; int spill_cap = 512; double host_spill_gb = -1; int occupancy_mode = 0; int devices = 1; int queue_mode = 0; int latency_mode = 0; int latency_max_blocks = 16; int spill_mode = 0; double ring_gb = 0; } g_opt;
 
 bool cuda_ok(cudaError_t e, const char* what) {
   if (e == cudaSuccess) return true;
@@ -751,6 +751,33 @@ static int ring_prepare(psd_plan* p, unsigned long long chunk, unsigned long lon
   return 0;
 }
 
+// Which kernel for a wave?  Makespan model from measurements on B200 (profiles/README.md, round 2):
+//   throughput kernel (one problem per warp, 14 per SM): 53 M rows/s when all 2,072 slots are busy, but a
+//   row of ONE problem takes 17.6 us with <= 148 problems in flight and 38 us at full load;
+//   latency kernel (one problem per block): 13.7 / 15.2 / 19 / 24 us per row with 1 / 2 / 3 / 4 blocks per
+//   SM, no gain beyond 4 resident blocks (instruction cache), further blocks queue behind them.
+// Both makespans = max(work bound, critical path of the longest problem); todo is sorted longest first.
+static bool choose_latency_kernel(const psd_plan* p, const std::vector<int>& todo) {
+  if (p->opt.latency_mode == 1) return true;
+  if (p->opt.latency_mode == 2 || todo.empty()) return false;
+  const double n_sm = (double)p->prop.multiProcessorCount, n = (double)todo.size();
+  const int b = (int)((todo.size() + (size_t)n_sm - 1) / (size_t)n_sm);
+  if (b <= 2) return true;
+  if (b > p->opt.latency_max_blocks) return false;
+  double total = 0;
+  for (int g : todo) total += (double)p->probs[p->gpu_ids[g]].n_rows;
+  const double longest = (double)p->probs[p->gpu_ids[todo[0]]].n_rows;
+  const double L = b == 3 ? 19.0 : 24.0;                                   // us per row of one problem
+  const double t_lat = std::max(total * L / (n_sm * std::min(b, 4)), longest * L);
+  static const double xs[] = {148, 296, 592, 1184, 2072}, ys[] = {17.6, 21.1, 28.4, 30.5, 38.0};
+  const double load = n * 148.0 / n_sm;                                    // problems in flight, scaled to 148 SMs
+  double l_thr = ys[4];
+  if (load <= xs[0]) l_thr = ys[0];
+  else for (int k = 1; k < 5; k++) if (load <= xs[k]) { l_thr = ys[k - 1] + (ys[k] - ys[k - 1]) * (load - xs[k - 1]) / (xs[k] - xs[k - 1]); break; }
+  const double t_thr = std::max(total / (53.0 * n_sm / 148.0), longest * l_thr);
+  return t_lat < 0.9 * t_thr;
+}
+
 // DP + backtrack for every uploaded problem.  Device-only: no host<->device row traffic.
 int psd_plan_solve_impl(psd_plan* p, void* stream_v) {
   cudaStream_t st = (cudaStream_t)stream_v;
@@ -822,11 +849,11 @@ int psd_plan_solve_impl(psd_plan* p, void* stream_v) {
     // the latency kernel, one problem per block and one chain per warp (fpop_lat.cu)
     const int n_sm = p->prop.multiProcessorCount;
     const int per_sm = (n + n_sm - 1) / n_sm;
-    const bool lat = p->opt.latency_mode == 1 || (p->opt.latency_mode == 0 && per_sm <= p->opt.latency_max_blocks);
+    const bool lat = choose_latency_kernel(p, todo);
     if (lat) {
       wpb = PSD_LAT_WARPS;
       if (!global_tier) {
-        const int resident = std::max(1, std::min(per_sm, 8));
+        const int resident = std::max(1, std::min(per_sm, 4));   // more than 4 resident blocks per SM gain nothing (measured)
         const size_t per_block = std::min((size_t)p->prop.sharedMemPerMultiprocessor / resident - 1024, (size_t)p->prop.sharedMemPerBlockOptin);
         long cap = ((long)per_block - PSD_TAB_BYTES - PSD_LAT_SHARED_BYTES - 32) / 328;   // PSD_WS_BYTES(cap, 2 cap) = 16 + 328 cap
         cap = std::min(640L, cap) & ~3L;

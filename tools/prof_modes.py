@@ -25,7 +25,7 @@ def run(probs, mode, max_blocks=2):
     st = plan.stats()
     res = [(plan.loss_row(i), plan.segments(i)) for i in range(len(plan))]
     plan.close()
-    lib.psd_set_option(b"latency_mode", 0.0); lib.psd_set_option(b"latency_max_blocks", 2.0)
+    lib.psd_set_option(b"latency_mode", 0.0); lib.psd_set_option(b"latency_max_blocks", 16.0)
     return st, res
 
 
@@ -50,7 +50,7 @@ for name, probs in cases:
     rows = sum(len(p[2]) for p in probs)
     longest = max(len(p[2]) for p in probs)
     st_t, res_t = run(probs, 2)
-    st_l, res_l = run(probs, 1, 8)
+    st_l, res_l = run(probs, 1, 16)
     rec = {"case": name, "problems": len(probs), "rows": rows,
            "throughput_kernel_ms": round(st_t["dp_ms"], 3), "latency_kernel_ms": round(st_l["dp_ms"], 3),
            "throughput_us_per_row_longest": round(1e3 * st_t["dp_ms"] / longest, 3), "latency_us_per_row_longest": round(1e3 * st_l["dp_ms"] / longest, 3),

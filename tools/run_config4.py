@@ -120,6 +120,8 @@ def main():
     helpers._mono_rows()      # fill the cache before the threads start
     with ThreadPoolExecutor(min(32, out["host_threads"])) as ex:
         probs = list(ex.map(lambda k: helpers.c4_lite_problem(k, args.samples, args.scale), range(n_prob)))
+    # the reference (and R) see the penalty as its 15-digit string (R/PeakSegFPOP_dir.R:64): solve exactly that value
+    probs = [(s, e, c, float(psd.r_paste(pen))) for (s, e, c, pen) in probs]
     rows = sum(len(p[2]) for p in probs)
     out.update(problems=n_prob, rows=int(rows), longest=int(max(len(p[2]) for p in probs)), row_scale=args.scale, samples=args.samples,
                generate_s=round(time.time() - t0, 1))
