@@ -61,9 +61,9 @@ fpop_dp_kernel(const DpKernelParams P) {
   const int wpb = blockDim.x >> 5;
   WarpWs ws_s, ws_g;
   ws_s.base = psd_smem + PSD_TAB_BYTES + (unsigned long long)warp * P.ws_s_bytes;
-  ws_s.scratch = nullptr; ws_s.flags = (int*)ws_s.base; ws_s.cap = P.cap_s; ws_s.ccap = P.ccap_s;
+  ws_s.scratch = nullptr; ws_s.flags = (int*)ws_s.base; ws_s.cap = P.cap_s; ws_s.ccap = P.ccap_s; ws_s.help = nullptr;
   ws_g.base = P.gws ? P.gws + ((unsigned long long)blockIdx.x * wpb + warp) * P.ws_g_bytes : nullptr;
-  ws_g.scratch = nullptr; ws_g.flags = ws_s.flags; ws_g.cap = P.gws ? P.cap_g : 0; ws_g.ccap = P.ccap_g;
+  ws_g.scratch = nullptr; ws_g.flags = ws_s.flags; ws_g.cap = P.gws ? P.cap_g : 0; ws_g.ccap = P.ccap_g; ws_g.help = nullptr;
   DpQueue Q;
   Q.problems = P.problems; Q.order = P.order; Q.n_order = P.n_order; Q.cursor = P.queue; Q.results = P.results;
   Q.first_slot = warp * (int)gridDim.x + (int)blockIdx.x;
@@ -778,6 +778,34 @@ static bool choose_latency_kernel(const psd_plan* p, const std::vector<int>& tod
   return t_lat < 0.9 * t_thr;
 }
 
+// Pinned host region of the store spill (mapped: the backtrack reads it, zero-copy writers write it).
+// want_gb <= 0: nothing.  Pinning costs ~0.3 s per GB, so callers ask for what the records need.
+static bool alloc_host_spill(psd_plan* p, double want_gb, unsigned long long chunk) {
+  if (p->d_spill || want_gb <= 0) return p->d_spill != nullptr;
+  const unsigned long long want = ((unsigned long long)(want_gb * (double)(1ull << 30)) / chunk) * chunk;
+  if (want < chunk * 16) return false;
+  if (cudaHostAlloc((void**)&p->h_spill, want, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) {
+    cudaGetLastError();   // no pinned memory to be had
+    p->h_spill = nullptr;
+    return false;
+  }
+  if (cudaHostGetDevicePointer((void**)&p->d_spill, p->h_spill, 0) != cudaSuccess) { cudaFreeHost(p->h_spill); p->h_spill = p->d_spill = nullptr; return false; }
+  p->spill_bytes = want;
+  return true;
+}
+
+// the automatic size limit of the host region: a quarter of the host's available memory, at most 64 GB
+static double host_spill_limit_gb(const psd_plan* p) {
+  if (p->opt.host_spill_gb >= 0) return p->opt.host_spill_gb;
+  double gb = 8;
+  if (FILE* mf = fopen("/proc/meminfo", "r")) {
+    char line[256];
+    while (fgets(line, sizeof line, mf)) { unsigned long long kb; if (sscanf(line, "MemAvailable: %llu kB", &kb) == 1) gb = (double)kb / (1024.0 * 1024.0) * 0.25; }
+    fclose(mf);
+  }
+  return gb > 64 ? 64 : gb;
+}
+
 // DP + backtrack for every uploaded problem.  Device-only: no host<->device row traffic.
 int psd_plan_solve_impl(psd_plan* p, void* stream_v) {
   cudaStream_t st = (cudaStream_t)stream_v;
@@ -817,6 +845,49 @@ int psd_plan_solve_impl(psd_plan* p, void* stream_v) {
   });
   std::vector<int> deferred;            // same tier, waiting for the store pool to be recycled
   std::vector<int> overflow_acc;        // need the next piece-list tier
+  // Store planning from a PREDICTION of the record bytes (16 B header + 8 B index + 40 B per piece pair
+  // per row; the mean piece count of the plan's previous solve when there was one, else 12), so that a
+  // batch larger than the store is not discovered by running out half way:
+  //   * problems are dealt into waves whose predicted records fit the store (each wave recycles it);
+  //   * a single problem larger than the HBM pool gets its pinned host region (spill) before it starts.
+  double est_row_bytes = p->last_mean_intervals > 0 ? 1.15 * (64.0 + 40.0 * p->last_mean_intervals) : 520.0;
+  auto plan_wave = [&](std::vector<int>& wave, std::vector<int>& later) {
+    const double cap_bytes = 0.92 * (double)(p->pool_bytes + p->spill_bytes);
+    double sum = 0;
+    size_t keep = 0;
+    for (; keep < wave.size(); keep++) {
+      const double b = est_row_bytes * (double)p->probs[p->gpu_ids[wave[keep]]].n_rows;
+      if (keep > 0 && sum + b > cap_bytes) break;
+      sum += b;
+    }
+    later.insert(later.end(), wave.begin() + keep, wave.end());
+    wave.resize(keep);
+  };
+  if (!todo.empty() && p->opt.host_spill_gb != 0 && !p->d_spill) {
+    const double first = est_row_bytes * (double)p->probs[p->gpu_ids[todo[0]]].n_rows;
+    if (first > 0.92 * (double)p->pool_bytes) {
+      const double gb = std::min(host_spill_limit_gb(p), 1.3 * (first - 0.8 * (double)p->pool_bytes) / (double)(1ull << 30) + 0.05);
+      alloc_host_spill(p, gb, chunk);
+      tr.mark("solve: pinned host region for the spill");
+    }
+  }
+  plan_wave(todo, deferred);
+  if (!deferred.empty() && p->opt.host_spill_gb != 0 && !p->d_spill) {
+    // A second wave costs at least the critical path of its longest problem (~15 us per row); pinned
+    // host memory for the same records costs ~0.33 s per GB.  Spill instead of waiting when that is cheaper.
+    double later_bytes = 0, later_longest = 0;
+    for (int g : deferred) {
+      const double r = (double)p->probs[p->gpu_ids[g]].n_rows;
+      later_bytes += est_row_bytes * r; later_longest = std::max(later_longest, r);
+    }
+    const double need_gb = 1.15 * later_bytes / (double)(1ull << 30) + 0.05;
+    if (need_gb <= host_spill_limit_gb(p) && 0.33 * need_gb < later_longest * 15e-6 && alloc_host_spill(p, need_gb, chunk)) {
+      todo.insert(todo.end(), deferred.begin(), deferred.end());
+      deferred.clear();
+      plan_wave(todo, deferred);
+      tr.mark("solve: pinned host region instead of a second wave");
+    }
+  }
   CK(cudaMemsetAsync(p->d_cursors, 0, sizeof(unsigned long long) * 8, st));
   bool global_tier = false;
   int gcap = p->opt.overflow_cap;
@@ -824,8 +895,14 @@ int psd_plan_solve_impl(psd_plan* p, void* stream_v) {
   for (int guard = 0;; guard++) {
     if (guard > 4096) { g_last_error = "solve did not converge"; return PSD_ERR_INTERNAL; }
     if (todo.empty()) {
-      if (!deferred.empty()) todo.swap(deferred);
-      else if (!overflow_acc.empty()) {
+      if (!deferred.empty()) {
+        todo.swap(deferred);
+        std::sort(todo.begin(), todo.end(), [&](int a, int b) {
+          const int64_t na = p->probs[p->gpu_ids[a]].n_rows, nb = p->probs[p->gpu_ids[b]].n_rows;
+          return na != nb ? na > nb : a < b;
+        });
+        plan_wave(todo, deferred);
+      } else if (!overflow_acc.empty()) {
         if (global_tier) {
           if (gcap >= 32768) {   // largest tier exhausted: report status 101 for these problems
             for (int g : overflow_acc) { p->results[g] = DpResult(); p->results[g].status = PSD_ST_PIECE_OVERFLOW; }
@@ -1021,30 +1098,21 @@ int psd_plan_solve_impl(psd_plan* p, void* stream_v) {
         CK(cudaMalloc(&p->d_pool, want));
         p->pool_bytes = want;
         retry_bigger = true;
-      } else if (!p->d_spill && p->opt.host_spill_gb != 0) {
-        double gb = p->opt.host_spill_gb;
-        if (gb < 0) {   // automatic: a quarter of the host's available memory, at most 64 GB
-          gb = 8;
-          if (FILE* mf = fopen("/proc/meminfo", "r")) {
-            char line[256];
-            while (fgets(line, sizeof line, mf)) { unsigned long long kb; if (sscanf(line, "MemAvailable: %llu kB", &kb) == 1) gb = (double)kb / (1024.0 * 1024.0) * 0.25; }
-            fclose(mf);
-          }
-          if (gb > 64) gb = 64;
-          // pinning is slow (~3 GB/s): do not pin more than the remaining problems can plausibly need
-          double need_rows = 0;
-          for (int g : exhausted) need_rows += (double)p->probs[p->gpu_ids[g]].n_rows;
-          const double est_gb = std::max(0.25, need_rows * 800.0 / (double)(1ull << 30));
-          if (gb > est_gb) gb = est_gb;
+      } else {
+        // The prediction was too low for these problems.  They are re-run in later waves (each
+        // recycles the store) unless the largest of them cannot fit the store at all: only then is
+        // pinned host memory added (pinning costs ~0.3 s per GB), sized for that problem.
+        est_row_bytes *= 1.3;
+        double largest = 0;
+        for (int g : exhausted) largest = std::max(largest, est_row_bytes * (double)p->probs[p->gpu_ids[g]].n_rows);
+        if (largest > 0.92 * (double)(p->pool_bytes + p->spill_bytes) && !p->d_spill && p->opt.host_spill_gb != 0) {
+          const double gb = std::min(host_spill_limit_gb(p), 1.3 * (largest - 0.8 * (double)p->pool_bytes) / (double)(1ull << 30) + 0.25);
+          retry_bigger = alloc_host_spill(p, gb, chunk);
         }
-        const unsigned long long want = ((unsigned long long)(gb * (double)(1ull << 30)) / chunk) * chunk;
-        if (want >= chunk * 16 && cudaHostAlloc((void**)&p->h_spill, want, cudaHostAllocMapped | cudaHostAllocPortable) == cudaSuccess) {
-          CK(cudaHostGetDevicePointer((void**)&p->d_spill, p->h_spill, 0));
-          p->spill_bytes = want;
-          retry_bigger = true;
-        } else {
-          cudaGetLastError();   // no pinned memory to be had: smaller waves
-          p->h_spill = nullptr;
+        if (!retry_bigger && (int)exhausted.size() < n) {   // part of the wave fitted: the rest goes into planned later waves
+          std::vector<int> later;
+          plan_wave(exhausted, later);
+          deferred.insert(deferred.end(), later.begin(), later.end());
         }
       }
       if (!retry_bigger && (int)exhausted.size() == n) {   // same store, and it held none of them

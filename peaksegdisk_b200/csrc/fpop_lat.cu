@@ -6,8 +6,11 @@
 // the GPU has room for (a sequential search on one long chromosome, config 3; the worst-case
 // sequences, config 5; single calls of PeakSegFPOP_disk, config 1), where the one-warp-per-problem
 // kernel leaves most of the chip idle and a row is one long chain of dependent fp64 instructions.
-// 64 threads per block leave every thread up to 255 registers: no spills; the piece lists get the
-// block's whole shared memory (640 pieces per function with one block per SM).
+// Warps 2 and 3 of the block are HELPERS: when an overlap interval's difference function has two roots,
+// the chain's main warp solves get_smaller_root while its helper solves get_larger_root (named barriers,
+// a mailbox in shared memory), so the two Newton loops run side by side instead of back to back.
+// 128 threads per block leave every thread up to 255 registers: no spills; the piece lists get the
+// block's whole shared memory (~630 pieces per function with one block per SM).
 // Same arithmetic, same store records, same backtrack kernel as the throughput path.
 #include <cuda_runtime.h>
 #include "dp_params.h"
@@ -19,7 +22,9 @@
 static __device__ const uint64_t d_lat_exp_tab[256] = PSD_EXP_TAB_INIT;
 static __device__ const uint64_t d_lat_log_tab[256] = PSD_LOG_TAB_INIT;
 
-__global__ void __launch_bounds__(PSD_LAT_WARPS * 32)
+static_assert(sizeof(LatShared) <= PSD_LAT_SHARED_BYTES, "PSD_LAT_SHARED_BYTES too small");
+
+__global__ void __launch_bounds__(PSD_LAT_THREADS)
 fpop_dp_lat_kernel(const DpKernelParams P) {
   uint64_t* etab = (uint64_t*)psd_smem;
   uint64_t* ltab = etab + 256;
@@ -31,11 +36,13 @@ fpop_dp_lat_kernel(const DpKernelParams P) {
   const int id = P.order[b];
   WarpWs ws_s, ws_g;
   ws_s.base = psd_smem + PSD_TAB_BYTES + PSD_LAT_SHARED_BYTES;
-  ws_s.scratch = nullptr; ws_s.flags = (int*)ws_s.base; ws_s.cap = P.cap_s; ws_s.ccap = P.ccap_s;
+  ws_s.scratch = nullptr; ws_s.flags = (int*)ws_s.base; ws_s.cap = P.cap_s; ws_s.ccap = P.ccap_s; ws_s.help = nullptr;
   ws_g.base = P.gws ? P.gws + (unsigned long long)b * P.ws_g_bytes : nullptr;
-  ws_g.scratch = nullptr; ws_g.flags = ws_s.flags; ws_g.cap = P.gws ? P.cap_g : 0; ws_g.ccap = P.ccap_g;
+  ws_g.scratch = nullptr; ws_g.flags = ws_s.flags; ws_g.cap = P.gws ? P.cap_g : 0; ws_g.ccap = P.ccap_g; ws_g.help = nullptr;
+  const int warp = (int)(threadIdx.x >> 5);
+  if (warp >= PSD_LAT_WARPS) { lat_helper_loop(&sh->help[warp - PSD_LAT_WARPS], warp - PSD_LAT_WARPS); return; }
   const DpProblem pb = P.problems[id];
-  dp_run_latency(ws_s, ws_g, pb, &P.results[id], P.pool, sh);
+  dp_run_latency(ws_s, ws_g, pb, &P.results[id], P.pool, sh, true);
 }
 
 int psd_lat_set_smem(size_t smem_bytes) {
@@ -44,12 +51,12 @@ int psd_lat_set_smem(size_t smem_bytes) {
 
 int psd_lat_max_blocks_per_sm(size_t smem_bytes) {
   int nb = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fpop_dp_lat_kernel, PSD_LAT_WARPS * 32, smem_bytes) != cudaSuccess) return 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fpop_dp_lat_kernel, PSD_LAT_THREADS, smem_bytes) != cudaSuccess) return 0;
   return nb;
 }
 
 int psd_lat_launch(const DpKernelParams& P, int grid, size_t smem_bytes, void* stream) {
-  fpop_dp_lat_kernel<<<grid, PSD_LAT_WARPS * 32, smem_bytes, (cudaStream_t)stream>>>(P);
+  fpop_dp_lat_kernel<<<grid, PSD_LAT_THREADS, smem_bytes, (cudaStream_t)stream>>>(P);
   return (int)cudaGetLastError();
 }
 

@@ -61,6 +61,9 @@ PSD_DEV unsigned psd_g_ballot(int p) { return __ballot_sync(0xffffffffu, p); }
 PSD_DEV void psd_g_sync() { __syncwarp(); }
 PSD_DEV void psd_cta_sync() { __syncthreads(); }
 PSD_DEV int psd_warp_in_block() { return (int)(threadIdx.x >> 5); }
+// named barriers: sync = arrive and wait, arrive = arrive and go on (n = threads of all participating warps)
+PSD_DEV void psd_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(n) : "memory"); }
+PSD_DEV void psd_bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" :: "r"(id), "r"(n) : "memory"); }
 #else
 // 16-lane groups: the two half-warps of a problem's warp run the up- and the down-recursion
 PSD_DEV int psd_glane() { return (int)(threadIdx.x & 15u); }
@@ -188,7 +191,7 @@ struct PList { double* base; int n; };
 //   2 x scratch (one per half-warp group): candidate right ends (ccap doubles), interval codes
 //   (2*cap ints: i_f | i_g << 16), candidate sources (ccap ints: bit 30 = from g | piece index).
 // The handle is passed BY VALUE (`scratch` already points at the calling group's scratch).
-struct WarpWs { unsigned char* base; unsigned char* scratch; int* flags; int cap; int ccap; };
+struct WarpWs { unsigned char* base; unsigned char* scratch; int* flags; int cap; int ccap; void* help; };   // help: the chain's LatHelp (latency kernel with helper warps) or null
 #define PSD_WS_HDR 16
 #define PSD_WS_LISTS 6
 #define PSD_FLAG_OVERFLOW 1
@@ -629,6 +632,154 @@ PSD_DEV PairOut pair_rule(const int cap, const PList f, const PList g, int i, in
   return o;
 }
 
+#if defined(PSD_G32)
+// ---- pair_rule split at the has_two_roots decision (latency kernel) ---------------------------------
+// pair_pre() finishes every interval that does not need the two Newton solves and otherwise returns
+// the state the solves and the rule's tail need; pair_post() is the tail given both roots.  In
+// between, the chain's main warp solves the smaller roots while its HELPER warp solves the larger
+// ones (LatHelp): the two Newton loops of an interval run on two warps instead of back to back.
+struct PairJob { double da, db, dc, lo, hi, xo, m, c1, c2, dl, dr, elo, dmid; int flags; };   // flags: eq_left | eq_right << 1 | by_mid << 2
+
+PSD_DEV bool pair_pre(const int cap, const PList f, const PList g, int i, int j, double dmin, double* hi_out, PairOut* op, PairJob* job) {
+  PairOut o; o.nc = 1; o.s0 = 0; o.x1 = 0; o.x2 = 0;
+#if defined(PSD_TIMING) || defined(PSD_EMU_STATS)
+  o.two = 0; o.heavy = 0;
+#endif
+  const double pa = PL_A(f, i), pb = PL_B(f, i), pcst = PL_C(f, i);
+  const double qa = PL_A(g, j), qb = PL_B(g, j), qcst = PL_C(g, j);
+  const double plo = (i == 0) ? dmin : PL_X(f, i - 1), phi = PL_X(f, i);
+  const double qlo = (j == 0) ? dmin : PL_X(g, j - 1), qhi = PL_X(g, j);
+  bool eq_left, eq_right;
+  double lo, hi;
+  if (plo < qlo) { eq_left = same_coefs(PL_A(g, j - 1), PL_B(g, j - 1), PL_C(g, j - 1), pa, pb, pcst); lo = qlo; }
+  else {
+    lo = plo;
+    if (qlo < plo) eq_left = same_coefs(PL_A(f, i - 1), PL_B(f, i - 1), PL_C(f, i - 1), qa, qb, qcst);
+    else eq_left = (i == 0 || j == 0) ? false
+                   : same_coefs(PL_A(f, i - 1), PL_B(f, i - 1), PL_C(f, i - 1), PL_A(g, j - 1), PL_B(g, j - 1), PL_C(g, j - 1));
+  }
+  if (phi < qhi) { eq_right = same_coefs(PL_A(f, i + 1), PL_B(f, i + 1), PL_C(f, i + 1), qa, qb, qcst); hi = phi; }
+  else {
+    hi = qhi;
+    if (qhi < phi) eq_right = same_coefs(pa, pb, pcst, PL_A(g, j + 1), PL_B(g, j + 1), PL_C(g, j + 1));
+    else eq_right = (i + 1 == f.n || j + 1 == g.n) ? false
+                    : same_coefs(PL_A(f, i + 1), PL_B(f, i + 1), PL_C(f, i + 1), PL_A(g, j + 1), PL_B(g, j + 1), PL_C(g, j + 1));
+  }
+  *hi_out = hi;
+  if (lo == hi) { o.nc = 0; *op = o; return false; }
+  if (same_coefs(pa, pb, pcst, qa, qb, qcst)) { o.s0 = 0; *op = o; return false; }
+  const double da = pa - qa, db = pb - qb, dc = pcst - qcst;
+  const double ehi = w_exp(hi), elo = w_exp(lo);
+  const double mid_m = (ehi + elo) / 2;
+  const double dmid = pc_cost(da, db, dc, w_log(mid_m));
+  const int by_mid = (dmid < 0) ? 0 : 1;
+  if (eq_left && eq_right) { o.s0 = by_mid; *op = o; return false; }
+  if (db == 0) {
+    if (da == 0) { o.s0 = (dc < 0) ? 0 : 1; *op = o; return false; }
+    if (dc == 0) { o.s0 = (da < 0) ? 0 : 1; *op = o; return false; }
+    const double x = w_log(-dc / da);
+    if (lo < x && x < hi) { o.nc = 2; o.x1 = x; o.s0 = (0 < da) ? 0 : 1; *op = o; return false; }
+    o.s0 = by_mid; *op = o; return false;
+  }
+  const double dl = pc_cost_e(da, db, dc, lo, elo), dr = pc_cost_e(da, db, dc, hi, ehi);
+  const double m = -db / da;
+  const double xo = w_log(m);
+  const double c1 = pc_cost(da, db, dc, xo);
+  const double c2 = pc_cost_m(da, db, dc, m, xo);
+  const bool two = two_roots(da, c1, c2, 0.0);
+  if (!two) {   // the rule's tail without roots (:536-582 of pair_rule with two == false)
+    if (eq_right || eq_left) o.s0 = by_mid;
+    else { const double v = (pc_abs(dmid) < PSD_EPS) ? dr : dmid; o.s0 = (v < 0) ? 0 : 1; }
+    *op = o; return false;
+  }
+  job->da = da; job->db = db; job->dc = dc; job->lo = lo; job->hi = hi; job->xo = xo; job->m = m; job->c1 = c1; job->c2 = c2;
+  job->dl = dl; job->dr = dr; job->elo = elo; job->dmid = dmid;
+  job->flags = (eq_left ? 1 : 0) | (eq_right ? 2 : 0) | (by_mid ? 4 : 0);
+  *op = o;
+  return true;
+}
+
+// the two Newton solves and the rule's tail for an interval whose difference has two roots
+PSD_DEV PairOut pair_post(const PairJob jb, const double rs, const double rl) {
+  PairOut o; o.nc = 1; o.s0 = 0; o.x1 = 0; o.x2 = 0;
+#if defined(PSD_TIMING) || defined(PSD_EMU_STATS)
+  o.two = 1; o.heavy = 1;
+#endif
+  const double da = jb.da, db = jb.db, dc = jb.dc, lo = jb.lo, hi = jb.hi, xo = jb.xo, dl = jb.dl, dr = jb.dr, elo = jb.elo;
+  const bool eq_left = (jb.flags & 1) != 0, eq_right = (jb.flags & 2) != 0;
+  if (eq_right) {
+    if (lo < rs && rs < xo && xo < hi) { o.nc = 2; o.x1 = rs; o.s0 = (dl < 0) ? 0 : 1; return o; }
+    const bool f_low_at_zero = 0 < db;
+    if (rs < lo) o.s0 = f_low_at_zero ? 1 : 0;
+    else o.s0 = f_low_at_zero ? 0 : 1;
+    return o;
+  }
+  if (eq_left) {
+    if (lo < xo && xo < rl && rl < hi) { o.nc = 2; o.x1 = rl; o.s0 = (dr < 0) ? 1 : 0; return o; }
+    o.s0 = (jb.flags & 4) ? 1 : 0; return o;
+  }
+  double x1 = PSD_INF, x2 = PSD_INF;
+  {
+    const bool l_in = lo < rl && rl < hi;
+    const bool s_in = lo < rs && 0 < w_exp(rs) && rs < hi;
+    if (l_in) { if (s_in && rs < rl) { x1 = rs; x2 = rl; } else x1 = rl; }
+    else if (s_in) x1 = rs;
+  }
+  if (x2 != PSD_INF) {
+    bool f_first;
+    if (x2 - x1 < x1 - lo) {
+      const double bm = (elo + w_exp(x1)) / 2;
+      f_first = pc_cost(da, db, dc, w_log(bm)) < 0;
+    } else {
+      f_first = !(pc_cost(da, db, dc, (x1 + x2) / 2) < 0);
+    }
+    o.nc = 3; o.x1 = x1; o.x2 = x2; o.s0 = f_first ? 0 : 1;
+  } else if (x1 != PSD_INF) {
+    const double bm = (elo + w_exp(x1)) / 2;
+    const double before = pc_cost(da, db, dc, w_log(bm));
+    const double after = pc_cost(da, db, dc, (hi + x1) / 2);
+    if (before < 0) {
+      if (after < 0) o.s0 = 0;
+      else { o.nc = 2; o.x1 = x1; o.s0 = 0; }
+    } else {
+      if (after < 0) { o.nc = 2; o.x1 = x1; o.s0 = 1; }
+      else o.s0 = 1;
+    }
+  } else {
+    const double v = (pc_abs(jb.dmid) < PSD_EPS) ? dr : jb.dmid;
+    o.s0 = (v < 0) ? 0 : 1;
+  }
+  return o;
+}
+
+
+// mailbox between a chain's main warp and its helper warp (shared memory)
+struct LatHelp {
+  int cmd;                 // 1: solve the posted jobs, 2: exit
+  unsigned mask;           // lanes that posted a job
+  double job[32][8];       // da, db, dc, hi, m, c2, dr of the interval's difference function
+  double rl[32];           // the helper's answer: get_larger_root
+};
+#define PSD_BAR_PAIR 1          /* named barriers of a latency block: the two main warps of the problem */
+#define psd_pair_sync() psd_bar_sync(PSD_BAR_PAIR, 64)
+#define PSD_BAR_JOBS(g) (2 + (g))   /* chain g: jobs posted (main arrives, helper waits) */
+#define PSD_BAR_DONE(g) (4 + (g))   /* chain g: larger roots ready (helper arrives, main waits) */
+
+PSD_DEV void lat_helper_loop(LatHelp* H, int g) {
+  const int lane = psd_lane();
+  for (;;) {
+    psd_bar_sync(PSD_BAR_JOBS(g), 64);
+    if (*(volatile int*)&H->cmd == 2) break;
+    const unsigned m = *(volatile unsigned*)&H->mask;
+    if ((m >> lane) & 1u) {
+      const double* J = H->job[lane];
+      H->rl[lane] = root_right(J[0], J[1], J[2], J[3], 0.0, J[4], J[5], J[6]);
+    }
+    psd_bar_arrive(PSD_BAR_DONE(g), 64);
+  }
+}
+#endif
+
 #define PSD_SRC_G 0x40000000
 
 
@@ -691,18 +842,44 @@ PSD_OP int min_env_op(const WarpWs ws, const PList f, const PList g, const PList
   PSD_T0(t2);
 #if defined(PSD_G32)
   // 2. crossing rule per interval -> candidate pieces: one lane per interval of THIS chain (the
-  // chain has the whole warp to itself in the latency kernel; of / og are unused)
+  // chain has the whole warp to itself in the latency kernel; of / og are unused).  Intervals whose
+  // difference function has two roots post their get_larger_root to the chain's helper warp and
+  // solve get_smaller_root themselves meanwhile.
   int T = 0;
+  LatHelp* const H = (LatHelp*)ws.help;
+  const int chain = psd_warp_in_block() & 1;
   for (int base = 0; base < K; base += 32) {
     const int q = base + lane;
     const bool valid = q < K;
     PairOut o; o.nc = 0; o.s0 = 0; o.x1 = 0; o.x2 = 0;
-    double lo = 0, hi = 0;
+#if defined(PSD_TIMING) || defined(PSD_EMU_STATS)
+    o.two = 0; o.heavy = 0;
+#endif
+    PairJob jb; jb.da = jb.db = jb.dc = jb.lo = jb.hi = jb.xo = jb.m = jb.c1 = jb.c2 = jb.dl = jb.dr = jb.elo = jb.dmid = 0; jb.flags = 0;
+    double hi = 0;
     int i = 0, j = 0;
+    bool need = false;
     if (valid) {
       const int code = ivl[q];
       i = code & 0xffff; j = code >> 16;
-      o = pair_rule(cap, f, g, i, j, dmin, &lo, &hi);
+      need = pair_pre(cap, f, g, i, j, dmin, &hi, &o, &jb);
+    }
+    if (H) {
+      const unsigned nm = psd_g_ballot(need);
+      if (nm) {
+        if (need) { double* J = H->job[lane]; J[0] = jb.da; J[1] = jb.db; J[2] = jb.dc; J[3] = jb.hi; J[4] = jb.m; J[5] = jb.c2; J[6] = jb.dr; }
+        psd_syncwarp();
+        if (lane == 0) { H->mask = nm; H->cmd = 1; }
+        psd_bar_arrive(PSD_BAR_JOBS(chain), 64);
+        double rs = 0;
+        if (need) rs = root_left(jb.da, jb.db, jb.dc, jb.lo, 0.0, jb.xo, jb.c1, jb.dl);
+        psd_bar_sync(PSD_BAR_DONE(chain), 64);
+        if (need) o = pair_post(jb, rs, H->rl[lane]);
+      }
+    } else if (need) {
+      const double rs = root_left(jb.da, jb.db, jb.dc, jb.lo, 0.0, jb.xo, jb.c1, jb.dl);
+      const double rl = root_right(jb.da, jb.db, jb.dc, jb.hi, 0.0, jb.m, jb.c2, jb.dr);
+      o = pair_post(jb, rs, rl);
     }
     const int mine_nc = valid ? o.nc : 0;
     int incl = mine_nc;
@@ -1386,6 +1563,7 @@ struct LatShared {
   int n_out[2][2];                  // [row parity][chain]: pieces of the new function
   unsigned long long chunk_first;   // store chunk handed out by warp 0 to both warps
   long long chunk_slot;             // its ring slot (-1: none)
+  LatHelp help[2];                  // mailboxes of the two helper warps (warps 2 and 3 of the block)
 };
 
 // store chunk allocation for the block: both warps keep identical StoreWriter state; the chunk is
@@ -1394,14 +1572,14 @@ struct LatShared {
 PSD_DEV unsigned long long store_alloc_cta(const StorePool& sp, StoreWriter& w, unsigned long long bytes, LatShared* sh, int grp) {
   if (w.cur + bytes > w.end) {
     const unsigned long long need = (bytes + sp.chunk_bytes - 1) / sp.chunk_bytes;
-    if (w.slot >= 0) { if (psd_lane() == 0) psd_bulk_wait_all(); psd_fence_system(); psd_cta_sync(); }
+    if (w.slot >= 0) { if (psd_lane() == 0) psd_bulk_wait_all(); psd_fence_system(); psd_pair_sync(); }
     if (grp == 0 && psd_lane() == 0) {
       if (w.slot >= 0) store_ring_publish(sp, w.end / sp.chunk_bytes - 1ull - sp.n_chunks, w.slot);
       long long slot = -1;
       sh->chunk_first = store_take(sp, need, &slot);
       sh->chunk_slot = slot;
     }
-    psd_cta_sync();
+    psd_pair_sync();
     const unsigned long long first = *(volatile unsigned long long*)&sh->chunk_first;
     w.slot = *(volatile long long*)&sh->chunk_slot;
     if (first == ~0ull) { w.slot = -1; return ~0ull; }
@@ -1431,7 +1609,8 @@ PSD_DEV void store_write_fn(const WarpWs ws, unsigned char* rec, int row, const 
   store_fn_lanes<SH>(ws, rec, R, L, which, lane, 32);
 }
 
-PSD_DEV void dp_run_latency(const WarpWs& ws_s, const WarpWs& ws_g, const DpProblem& pb, DpResult* res, const StorePool& sp, LatShared* sh
+// use_help: warps 2 and 3 of the block run lat_helper_loop() for chains 0 and 1
+PSD_DEV void dp_run_latency(const WarpWs& ws_s, const WarpWs& ws_g, const DpProblem& pb, DpResult* res, const StorePool& sp, LatShared* sh, const bool use_help
 #if defined(PSD_EMU)
                             , psd_trace_fn trace, void* trace_user
 #endif
@@ -1458,6 +1637,7 @@ PSD_DEV void dp_run_latency(const WarpWs& ws_s, const WarpWs& ws_g, const DpProb
     wg = ws;                                                                                         \
     wg.scratch = ws_scratch0(ws) + (unsigned long long)grp * PSD_WS_SCRATCH_BYTES(ws.cap, ws.ccap);  \
     wg.flags = flag_words + 2 * (t & 1) + grp;                                                       \
+    wg.help = use_help ? (void*)&sh->help[grp] : nullptr;                                            \
     upP.base = ws_list(ws, 0); downP.base = ws_list(ws, 1); upN.base = ws_list(ws, 2);               \
     downN.base = ws_list(ws, 3); tmp.base = ws_list(ws, 4 + grp);                                    \
   } while (0)
@@ -1498,7 +1678,7 @@ PSD_DEV void dp_run_latency(const WarpWs& ws_s, const WarpWs& ws_g, const DpProb
       if (lane == 0) sh->n_out[t & 1][grp] = n_out;
     }
     PSD_T0(tw);
-    psd_cta_sync();   // the row's one barrier: both new functions are complete and visible
+    psd_pair_sync();   // the row's one barrier: both new functions are complete and visible
     PSD_T1(tw, 5);
     PSD_T0(tc);
     const int flags = ((volatile int*)flag_words)[2 * (t & 1)] | ((volatile int*)flag_words)[2 * (t & 1) + 1];
@@ -1511,7 +1691,7 @@ PSD_DEV void dp_run_latency(const WarpWs& ws_s, const WarpWs& ws_g, const DpProb
         else pl_move(downP.base, ws_s.cap, ws_list(ws_g, 1), ws_g.cap, downP.n);
         in_g = true; n_spill++;
         PSD_BIND_TIER();
-        psd_cta_sync();   // both warps have read the flag words and moved their function
+        psd_pair_sync();   // both warps have read the flag words and moved their function
         redo = true;
       } else {
         status = (flags & PSD_FLAG_INTERNAL) ? PSD_ST_INTERNAL : PSD_ST_PIECE_OVERFLOW;
@@ -1567,14 +1747,19 @@ PSD_DEV void dp_run_latency(const WarpWs& ws_s, const WarpWs& ws_g, const DpProb
       else pl_move(downP.base, ws_g.cap, ws_list(ws_s, 1), ws_s.cap, downP.n);
       in_g = false;
       PSD_BIND_TIER();
-      psd_cta_sync();
+      psd_pair_sync();
     }
   }
   if (lane == 0) psd_bulk_wait_all();   // no bulk copy may outlive the block's shared memory
   if (sw.slot >= 0) {   // the ring chunk still open at the end goes to the host like the others
     psd_fence_system();
-    psd_cta_sync();
+    psd_pair_sync();
     if (grp == 0 && lane == 0) store_ring_publish(sp, sw.end / sp.chunk_bytes - 1ull - sp.n_chunks, sw.slot);
+  }
+  if (use_help) {       // release this chain's helper warp
+    if (lane == 0) sh->help[grp].cmd = 2;
+    psd_syncwarp();
+    psd_bar_arrive(PSD_BAR_JOBS(grp), 64);
   }
 #undef PSD_BIND_TIER
 }

@@ -15,6 +15,7 @@ struct Job {
   int order0 = 0; int cursor = 1;
 #if defined(PSD_G32)
   LatShared lat;
+  bool helpers = true;     // PSD_EMU_NO_HELPERS=1: two warps only, each chain solves both Newton roots itself
 #endif
 };
 // The host side of the store's DMA drain (fpop_gpu.cu: RingDrain), done synchronously: copy every
@@ -36,13 +37,14 @@ void emu_ring_drain(const StorePool* sp) {
 // latency kernel: a block of two warps owns the problem (one chain per warp); the backtrack is one warp
 void lane_main(void* arg) {
   Job* J = (Job*)arg;
-  dp_run_latency(J->ws, J->ws_g, J->pb, J->res, J->sp, &J->lat, J->trace, J->trace_user);
+  if (psd_warp_in_block() >= 2) lat_helper_loop(&J->lat.help[psd_warp_in_block() - 2], psd_warp_in_block() - 2);   // helper warps
+  else dp_run_latency(J->ws, J->ws_g, J->pb, J->res, J->sp, &J->lat, J->helpers, J->trace, J->trace_user);
   psd_cta_sync();
   if (J->sp.ring.n_slots && psd_warp_in_block() == 0 && psd_lane() == 0) emu_ring_drain(&J->sp);
   psd_cta_sync();
   if (psd_warp_in_block() == 0) backtrack_problem(J->sp, J->pb.index, J->pb.n_rows, J->res, J->seg_row, J->seg_x);
 }
-#define PSD_EMU_WARPS 2
+#define PSD_EMU_WARPS (J.helpers ? 4 : 2)
 #else
 void lane_main(void* arg) {
   Job* J = (Job*)arg;
@@ -91,10 +93,13 @@ int emu_fpop_rows(int n_rows, const int* chrom_start, const int* chrom_end, cons
   // shared-memory-tier stand-in (capacity cap) and the global workspace the warp can move to
   const int ccap = 3 * cap;
   std::vector<double> wsmem(PSD_WS_BYTES(cap, ccap) / 8 + 16);
-  J.ws.base = (unsigned char*)wsmem.data(); J.ws.scratch = nullptr; J.ws.flags = (int*)J.ws.base; J.ws.cap = cap; J.ws.ccap = ccap;
+  J.ws.base = (unsigned char*)wsmem.data(); J.ws.scratch = nullptr; J.ws.flags = (int*)J.ws.base; J.ws.cap = cap; J.ws.ccap = ccap; J.ws.help = nullptr;
+#if defined(PSD_G32)
+  J.helpers = getenv("PSD_EMU_NO_HELPERS") == nullptr;
+#endif
   std::vector<double> wsmem_g(spill_cap > 0 ? PSD_WS_BYTES(spill_cap, 3 * spill_cap) / 8 + 16 : 1);
   J.ws_g.base = spill_cap > 0 ? (unsigned char*)wsmem_g.data() : nullptr; J.ws_g.scratch = nullptr; J.ws_g.flags = J.ws.flags;
-  J.ws_g.cap = spill_cap; J.ws_g.ccap = 3 * spill_cap;
+  J.ws_g.cap = spill_cap; J.ws_g.ccap = 3 * spill_cap; J.ws_g.help = nullptr;
   const unsigned long long chunk = 1 << 16;
   std::vector<unsigned char> pool;
   unsigned long long cursor = 0;

@@ -30,6 +30,28 @@ psd_emu_switch:
 .size psd_emu_switch,.-psd_emu_switch
 )");
 
+// named barriers of the block being run: arrival count and generation per id
+static int g_named_count[16], g_named_need[16];
+static unsigned g_named_gen[16];
+static Fiber* g_named_waiters[16][1024];
+static int g_named_nwait[16];
+
+void named_arrive(int id, int n_threads, bool wait, int site) {
+  Warp* w = g_warp;
+  g_named_need[id] = n_threads;
+  g_named_count[id]++;
+  if (g_named_count[id] == n_threads) {          // the barrier completes: release the waiters, start a new generation
+    for (int k = 0; k < g_named_nwait[id]; k++) g_named_waiters[id][k]->state = RUNNABLE;
+    g_named_nwait[id] = 0; g_named_count[id] = 0; g_named_gen[id]++;
+    return;
+  }
+  if (!wait) return;
+  Fiber& me = w->f[w->cur];
+  g_named_waiters[id][g_named_nwait[id]++] = &me;
+  me.state = WAIT_NAMED; me.site = site;
+  psd_emu_switch(&me.sp, w->sched_sp);
+}
+
 static void trampoline() {
   Warp* w = g_warp;
   w->entry(w->arg);
@@ -105,6 +127,7 @@ static bool step_warp(Warp& w) {
 }
 
 void run_block(void (*entry)(void*), void* arg, int n_warps, int descending) {
+  memset(g_named_count, 0, sizeof g_named_count); memset(g_named_nwait, 0, sizeof g_named_nwait);
   Warp* ws = new Warp[n_warps];
   for (int k = 0; k < n_warps; k++) init_warp(ws[k], entry, arg, descending, k, n_warps);
   Warp* outer = g_warp;

@@ -18,7 +18,7 @@
 
 namespace psd_emu {
 
-enum { RUNNABLE = 0, WAIT_GROUP = 1, WAIT_FULL = 2, DONE = 3, WAIT_BLOCK = 4 };
+enum { RUNNABLE = 0, WAIT_GROUP = 1, WAIT_FULL = 2, DONE = 3, WAIT_BLOCK = 4, WAIT_NAMED = 5 };
 struct Fiber { void* sp; char* stack; int state; int site; };
 struct Warp {
   Fiber f[32];
@@ -85,6 +85,9 @@ inline uint32_t g_ballot(int pred, int site) {
   return m;
 }
 
+// Named barriers (PTX bar.sync / bar.arrive with an id and a thread count): arrivals are counted per
+// id; a fiber that syncs blocks until the count reaches n_threads, a fiber that only arrives goes on.
+void named_arrive(int id, int n_threads, bool wait, int site);
 void run_warp(void (*entry)(void*), void* arg, int descending);
 // A thread block of n_warps warps (the latency kernel: the warps of one problem).  Block barriers
 // (block(WAIT_BLOCK, site)) release when every lane of every warp waits at the same call site.
@@ -108,6 +111,8 @@ static inline double psd_dbl_(uint64_t u) { double v; memcpy(&v, &u, 8); return 
 
 // block barrier (multi-warp blocks only; with one warp it degenerates to a warp barrier)
 #define psd_cta_sync() psd_emu::block(psd_emu::WAIT_BLOCK, PSD_SITE)
+#define psd_bar_sync(id, n) psd_emu::named_arrive((id), (n), true, PSD_SITE)
+#define psd_bar_arrive(id, n) psd_emu::named_arrive((id), (n), false, PSD_SITE)
 static inline int psd_warp_in_block() { return psd_emu::warp_id(); }
 // whole-warp collectives
 #define psd_shfl_d(v, src) psd_dbl_(psd_emu::exchange(psd_bits_(v), (src), PSD_SITE))
