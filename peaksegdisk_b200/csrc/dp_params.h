@@ -23,9 +23,10 @@ struct DpKernelParams {
   unsigned char* gws;         // per-warp (per-block) global-memory workspaces (null: none)
   int cap_g, ccap_g;
   unsigned long long ws_g_bytes;
+  int lat_help;               // latency kernel: the block has two helper warps (128 threads) that solve the larger Newton roots
 };
 
 // fpop_lat.cu: the latency kernel.  Block b solves problem order[b] (no queue).
 int psd_lat_set_smem(size_t smem_bytes);                                   // cudaFuncSetAttribute; returns a cudaError_t
-int psd_lat_max_blocks_per_sm(size_t smem_bytes);                          // occupancy query
+int psd_lat_max_blocks_per_sm(size_t smem_bytes, int helpers);             // occupancy query
 int psd_lat_launch(const DpKernelParams& P, int grid, size_t smem_bytes, void* stream);   // returns a cudaError_t

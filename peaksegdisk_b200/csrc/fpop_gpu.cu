@@ -363,6 +363,13 @@ void psd_plan_invalidate(psd_plan* p) { p->uploaded = false; p->solved = false; 
 void psd_plan_mark_penalty_changed(psd_plan* p) { p->solved = false; }
 const psd_stats& psd_plan_stats_ref(const psd_plan* p) { return p->stats; }
 
+// Predicted store bytes per row (record + index): 16 B header + 8 B index + 40 B per piece pair; 520 B
+// (12 pieces per function) until a solve of this plan has measured the mean piece count.  The pool is
+// sized with it and the wave planner uses the same number, so a batch is split only when HBM is short.
+static double psd_est_row_bytes(const psd_plan* p) {
+  return p->last_mean_intervals > 0 ? std::max(520.0, 1.15 * (64.0 + 40.0 * p->last_mean_intervals)) : 520.0;
+}
+
 // H2D: pack the rows of the non-trivial problems, allocate index / result / segment buffers.
 int psd_plan_upload_impl(psd_plan* p, void* stream_v) {
   cudaStream_t st = (cudaStream_t)stream_v;
@@ -517,7 +524,7 @@ int psd_plan_upload_impl(psd_plan* p, void* stream_v) {
   else {
     // estimate: 16 B header + 8 B index + 20 B x 2 functions x ~11 pieces per row (config 2 writes 380 B
     // per row, Mono27ac 300-560); a wave that still runs out grows the pool x4 and repeats; clamp to 80% of free memory
-    want = (unsigned long long)total_index * 520ull + (64ull << 20);
+    want = (unsigned long long)((double)total_index * psd_est_row_bytes(p)) + (64ull << 20);
     const unsigned long long lim = (unsigned long long)((double)free_b * 0.80);
     if (want > lim) want = lim;
   }
@@ -754,7 +761,7 @@ static int ring_prepare(psd_plan* p, unsigned long long chunk, unsigned long lon
 // Which kernel for a wave?  Makespan model from measurements on B200 (profiles/README.md, round 2):
 //   throughput kernel (one problem per warp, 14 per SM): 53 M rows/s when all 2,072 slots are busy, but a
 //   row of ONE problem takes 17.6 us with <= 148 problems in flight and 38 us at full load;
-//   latency kernel (one problem per block): 13.7 / 15.2 / 19 / 24 us per row with 1 / 2 / 3 / 4 blocks per
+//   latency kernel (one problem per block): 12.3 / 15.2 / 19 / 24 us per row with 1 / 2 / 3 / 4 blocks per
 //   SM, no gain beyond 4 resident blocks (instruction cache), further blocks queue behind them.
 // Both makespans = max(work bound, critical path of the longest problem); todo is sorted longest first.
 static bool choose_latency_kernel(const psd_plan* p, const std::vector<int>& todo) {
@@ -850,9 +857,10 @@ int psd_plan_solve_impl(psd_plan* p, void* stream_v) {
   // batch larger than the store is not discovered by running out half way:
   //   * problems are dealt into waves whose predicted records fit the store (each wave recycles it);
   //   * a single problem larger than the HBM pool gets its pinned host region (spill) before it starts.
-  double est_row_bytes = p->last_mean_intervals > 0 ? 1.15 * (64.0 + 40.0 * p->last_mean_intervals) : 520.0;
+  double est_row_bytes = psd_est_row_bytes(p);
   auto plan_wave = [&](std::vector<int>& wave, std::vector<int>& later) {
-    const double cap_bytes = 0.92 * (double)(p->pool_bytes + p->spill_bytes);
+    // (the automatic pool is sized with the same 520 B per row: a batch is only split when HBM could not hold the prediction)
+    const double cap_bytes = (double)(p->pool_bytes + p->spill_bytes);
     double sum = 0;
     size_t keep = 0;
     for (; keep < wave.size(); keep++) {
@@ -865,7 +873,7 @@ int psd_plan_solve_impl(psd_plan* p, void* stream_v) {
   };
   if (!todo.empty() && p->opt.host_spill_gb != 0 && !p->d_spill) {
     const double first = est_row_bytes * (double)p->probs[p->gpu_ids[todo[0]]].n_rows;
-    if (first > 0.92 * (double)p->pool_bytes) {
+    if (first > (double)p->pool_bytes) {
       const double gb = std::min(host_spill_limit_gb(p), 1.3 * (first - 0.8 * (double)p->pool_bytes) / (double)(1ull << 30) + 0.05);
       alloc_host_spill(p, gb, chunk);
       tr.mark("solve: pinned host region for the spill");
@@ -921,6 +929,7 @@ int psd_plan_solve_impl(psd_plan* p, void* stream_v) {
     K.pool.base = p->d_pool; K.pool.cursor = p->d_cursors; K.pool.n_chunks = p->pool_bytes / chunk; K.pool.chunk_bytes = chunk;
     K.pool.host_base = p->d_spill; K.pool.host_cursor = p->d_cursors + 2; K.pool.host_chunks = p->spill_bytes / chunk;
     memset(&K.pool.ring, 0, sizeof K.pool.ring);
+    K.lat_help = 0;
     int grid; size_t smem; int wpb; int which = 0; int blocks = 1;
     // Few problems (a sequential search on one chromosome, the worst-case sequences, single calls):
     // the latency kernel, one problem per block and one chain per warp (fpop_lat.cu)
@@ -947,7 +956,9 @@ int psd_plan_solve_impl(psd_plan* p, void* stream_v) {
       }
       smem = PSD_TAB_BYTES + PSD_LAT_SHARED_BYTES + (size_t)K.ws_s_bytes;
       grid = n;
-      S.piece_cap = K.cap_s; S.warps_per_sm = PSD_LAT_WARPS * std::min(per_sm, std::max(1, psd_lat_max_blocks_per_sm(smem)));
+      // helper warps pay with one block per SM (-9 % per row); with more resident blocks they cost more than they give (measured)
+      K.lat_help = per_sm <= 1 ? 1 : 0;
+      S.piece_cap = K.cap_s; S.warps_per_sm = (K.lat_help ? 4 : PSD_LAT_WARPS) * std::min(per_sm, std::max(1, psd_lat_max_blocks_per_sm(smem, K.lat_help)));
     } else if (!global_tier) {
       // shared-memory tier, with a per-warp global workspace the kernel moves to (and back from)
       // when a row's functions outgrow shared memory
@@ -1105,7 +1116,7 @@ int psd_plan_solve_impl(psd_plan* p, void* stream_v) {
         est_row_bytes *= 1.3;
         double largest = 0;
         for (int g : exhausted) largest = std::max(largest, est_row_bytes * (double)p->probs[p->gpu_ids[g]].n_rows);
-        if (largest > 0.92 * (double)(p->pool_bytes + p->spill_bytes) && !p->d_spill && p->opt.host_spill_gb != 0) {
+        if (largest > (double)(p->pool_bytes + p->spill_bytes) && !p->d_spill && p->opt.host_spill_gb != 0) {
           const double gb = std::min(host_spill_limit_gb(p), 1.3 * (largest - 0.8 * (double)p->pool_bytes) / (double)(1ull << 30) + 0.25);
           retry_bigger = alloc_host_spill(p, gb, chunk);
         }

@@ -40,23 +40,24 @@ fpop_dp_lat_kernel(const DpKernelParams P) {
   ws_g.base = P.gws ? P.gws + (unsigned long long)b * P.ws_g_bytes : nullptr;
   ws_g.scratch = nullptr; ws_g.flags = ws_s.flags; ws_g.cap = P.gws ? P.cap_g : 0; ws_g.ccap = P.ccap_g; ws_g.help = nullptr;
   const int warp = (int)(threadIdx.x >> 5);
-  if (warp >= PSD_LAT_WARPS) { lat_helper_loop(&sh->help[warp - PSD_LAT_WARPS], warp - PSD_LAT_WARPS); return; }
+  if (warp >= PSD_LAT_WARPS) { lat_helper_loop(&sh->help[warp - PSD_LAT_WARPS], warp - PSD_LAT_WARPS); return; }   // only launched when P.lat_help
   const DpProblem pb = P.problems[id];
-  dp_run_latency(ws_s, ws_g, pb, &P.results[id], P.pool, sh, true);
+  dp_run_latency(ws_s, ws_g, pb, &P.results[id], P.pool, sh, P.lat_help != 0);
 }
 
 int psd_lat_set_smem(size_t smem_bytes) {
   return (int)cudaFuncSetAttribute(fpop_dp_lat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
 }
 
-int psd_lat_max_blocks_per_sm(size_t smem_bytes) {
+int psd_lat_max_blocks_per_sm(size_t smem_bytes, int helpers) {
   int nb = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fpop_dp_lat_kernel, PSD_LAT_THREADS, smem_bytes) != cudaSuccess) return 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fpop_dp_lat_kernel, helpers ? PSD_LAT_THREADS : PSD_LAT_WARPS * 32, smem_bytes) != cudaSuccess) return 0;
   return nb;
 }
 
+// P.lat_help: 128 threads per block (two helper warps), else 64
 int psd_lat_launch(const DpKernelParams& P, int grid, size_t smem_bytes, void* stream) {
-  fpop_dp_lat_kernel<<<grid, PSD_LAT_THREADS, smem_bytes, (cudaStream_t)stream>>>(P);
+  fpop_dp_lat_kernel<<<grid, P.lat_help ? PSD_LAT_THREADS : PSD_LAT_WARPS * 32, smem_bytes, (cudaStream_t)stream>>>(P);
   return (int)cudaGetLastError();
 }
 

@@ -274,10 +274,12 @@ def test_store_waves_and_small_piece_tier_give_identical_results(psd):
     lib = psd._lib.lib
     try:
         lib.psd_set_option(b"store_gb", 0.004)     # ~4 MB: not enough for all six
+        lib.psd_set_option(b"host_spill_gb", 0.0)  # no pinned-host spill: the store must be recycled in waves
         lib.psd_set_option(b"piece_cap", 8.0)
         plan, ids2 = psd.solve_batch(probs)
     finally:
         lib.psd_set_option(b"store_gb", 0.0)
+        lib.psd_set_option(b"host_spill_gb", -1.0)
         lib.psd_set_option(b"piece_cap", 48.0)
     st = plan.stats()
     assert st["n_waves"] > 1 and st["n_overflow_tier"] > 0, st

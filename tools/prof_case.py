@@ -13,7 +13,7 @@ reps = int(sys.argv[3]) if len(sys.argv) > 3 else 1
 plan = psd.Plan(0)
 rows = 0
 for k in range(nv):
-    s, e, c = synth.poisson_problem(k, n)
+    s, e, c = synth.poisson_problem(k, n if n > 0 else None)     # 0: config 2's own vector lengths (1e4..1e5)
     for pen in ([float(os.environ['PSD_PEN'])] * 5 if os.environ.get('PSD_PEN') else synth.C2_PENALTIES):
         plan.add(s, e, c, pen); rows += len(c)
 plan.upload()
