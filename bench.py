@@ -208,7 +208,7 @@ def main():
     ap.add_argument("--vectors", type=int, default=1024, help="count vectors per GPU (config 2: 1024)")
     ap.add_argument("--quick", action="store_true", help="small problems (development only; not a bench value)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--ref-seconds", type=float, default=15.0, help="reference arm: CPU work per step, seconds per core")
+    ap.add_argument("--ref-seconds", type=float, default=30.0, help="reference arm: CPU work per step, seconds per core")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

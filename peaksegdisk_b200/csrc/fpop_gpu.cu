@@ -50,8 +50,13 @@ static inline unsigned long long psd_ws_bytes(int cap, int ccap) { return cap > 
 // Two builds of the same kernel: <16,1> one phase-locked block per SM at 128 registers (the default:
 // lowest per-row latency), <14,2> two blocks per SM at 72 registers (28 warps/SM: +18 % on batches of
 // many short problems, -25 % when a long problem sets the critical path; see choose_config()).
+#if defined(PSD_MAXNREG)   // experiment: 14 warps x 32 x 144 registers fill the register file of an SM exactly
+#define PSD_DP_KERNEL_ATTR __maxnreg__(MINB == 1 ? PSD_MAXNREG : 72)
+#else
+#define PSD_DP_KERNEL_ATTR __launch_bounds__(MAXW * 32, MINB)
+#endif
 template <int MAXW, int MINB>
-__global__ void __launch_bounds__(MAXW * 32, MINB)
+__global__ void PSD_DP_KERNEL_ATTR
 fpop_dp_kernel(const DpKernelParams P) {
   uint64_t* etab = (uint64_t*)psd_smem;     // psd_smem: the block's dynamic shared memory (fpop_warp.cuh)
   uint64_t* ltab = etab + 256;

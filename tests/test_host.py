@@ -230,3 +230,30 @@ def test_reference_interface_cpp_linked_against_the_library(tmp_path):
         assert outputs(path, case["penalty"]) == (case["segments"], case["loss"]), case["name"]
         n += 1
     assert n >= 15
+
+
+def test_write_bedgraph_and_in_memory_validation(tmp_path):
+    """Host-only entry points: psd_write_bedgraph writes the text R/writeBedGraph.R:35-37 produces;
+    psd_plan_add enforces the file path's contract on in-memory rows (contiguous: status 6; positive
+    widths and non-negative coverage: PSD_ERR_ARG) -- no GPU is touched."""
+    import numpy as np
+    from peaksegdisk_b200 import _lib, synth, Plan
+    i32p = C.POINTER(C.c_int32)
+    s, e, c = synth.poisson_problem(3, 5000)
+    c = c.copy(); c[7] = -12                      # the writer prints what it is given, sign included
+    a, b = str(tmp_path / "a.bedGraph"), str(tmp_path / "b.bedGraph")
+    synth.write_bedgraph(a, s, e, c, chrom="chr7_x")
+    assert _lib.lib.psd_write_bedgraph(b.encode(), b"chr7_x", len(c), s.ctypes.data_as(i32p), e.ctypes.data_as(i32p), c.ctypes.data_as(i32p)) == 0
+    assert open(a, "rb").read() == open(b, "rb").read()
+    assert _lib.lib.psd_write_bedgraph(str(tmp_path / "no" / "dir.bedGraph").encode(), b"c", 1, s.ctypes.data_as(i32p), e.ctypes.data_as(i32p), c.ctypes.data_as(i32p)) == 111
+    plan = Plan(0)
+    ok = np.array([0, 5, 9], np.int32), np.array([5, 9, 20], np.int32), np.array([1, 7, 0], np.int32)
+    assert plan.add(*ok, 1.0) == 0
+    for rows in [(np.array([0, 6, 9], np.int32), ok[1], ok[2]),            # gap
+                 (np.array([0, 5, 5], np.int32), np.array([5, 5, 20], np.int32), ok[2]),   # zero width
+                 (ok[0], ok[1], np.array([1, -7, 0], np.int32))]:          # negative coverage
+        with pytest.raises(ValueError):
+            plan.add(*rows, 1.0)
+    assert len(plan) == 1
+    st = _lib.last_batch_stats()
+    assert set(st) >= {"parse_ms", "run_ms", "dp_ms", "n_problems"}
