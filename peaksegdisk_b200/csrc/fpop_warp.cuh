@@ -1449,7 +1449,10 @@ PSD_DEV void dp_run_queue(const WarpWs& ws_s, const WarpWs& ws_g, const DpQueue&
     }
     // block barrier 1 of 2; it doubles as the block's termination vote (a warp that just saw an empty
     // queue has have == 0; the block leaves when every warp has)
-    if (!psd_block_or(have)) break;
+    PSD_T0(tw1);
+    const int any_have = psd_block_or(have);
+    PSD_T1(tw1, 5);     // wait at barrier 1 (after min_less / min_more)
+    if (!any_have) break;
     // ---- phase B: both min_env's as one converged call --------------------------------------------------
     int n_out = 0;
     if (have && t >= 1) {
@@ -1466,7 +1469,9 @@ PSD_DEV void dp_run_queue(const WarpWs& ws_s, const WarpWs& ws_g, const DpQueue&
       }
       psd_syncwarp();   // both chains done; their lists are visible to the whole warp
     }
+    PSD_T0(tw2);
     psd_block_sync();   // block barrier 2 of 2
+    PSD_T1(tw2, 6);     // wait at barrier 2 (after min_env)
     // ---- phase C: tier switch or: counters, store record, end of problem --------------------------------
     PSD_T0(tc);
     if (have) {

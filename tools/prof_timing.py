@@ -4,6 +4,7 @@ import ctypes as C, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 os.environ["PSD_LIB"] = os.path.join(ROOT, "peaksegdisk_b200", "libpsd_timing.so")
+os.environ["PSD_LATENCY_MODE"] = "2"      # this tool reads the throughput kernel's counters
 import peaksegdisk_b200 as psd
 from peaksegdisk_b200 import synth, _lib
 npb = int(sys.argv[1]); rows = int(sys.argv[2]); pen = float(sys.argv[3]) if len(sys.argv) > 3 else 1000.0
@@ -18,8 +19,8 @@ buf = (C.c_ulonglong * 32)()
 _lib.lib.psd_debug_read(buf, 32, 1)
 plan.solve(); st = plan.stats()
 _lib.lib.psd_debug_read(buf, 32, 0)
-names = {0: "min_less (g0)", 1: "min_more (g1)", 2: "min_env up (g0)", 3: "min_env down (g1)", 4: "epilogue (both lanes counted)",
+names = {0: "min_less (g0)", 1: "min_more (g1)", 2: "min_env up (g0)", 3: "min_env down (g1)", 4: "epilogue (both lanes counted)", 5: "wait at barrier 1, after min_less/min_more (both lanes counted)", 6: "wait at barrier 2, after min_env (both lanes counted)",
          8: "  env: enumerate", 9: "  env: pair rule loop", 10: "  env: merge/emit", 16: "    pair: loads + eq flags", 17: "    pair: exp,exp,log,exp (dmid)", 18: "    pair: dl,dr,log,exp (two_roots)", 19: "    pair: post-Newton", 20: "    pair-loop chunks (count/row)", 21: "    intervals (count/row)", 12: "    pair: root_left", 13: "    pair: root_right"}
 print("problems=%d rows=%d dp_ms=%.2f -> %.0f cycles/row wall (1965 MHz)" % (npb, tot, st["dp_ms"], st["dp_ms"] * 1e-3 * 1.965e9 / rows / max(1, (npb + 147) // 148 / 14 if npb > 148 else 1)))
 for i in sorted(names):
-    print("%-34s %8.0f cycles/row" % (names[i], buf[i] / tot))
+    print("%-66s %8.0f cycles/row" % (names[i], buf[i] / tot))
