@@ -97,6 +97,7 @@ PSD_DEV void psd_st_cs_i(int* p, int v) { __stcs(p, v); }
 PSD_DEV void psd_st_cs_u64(unsigned long long* p, unsigned long long v) { __stcs(p, v); }
 PSD_DEV void psd_st_cs_u4(unsigned* p, unsigned a, unsigned b, unsigned c, unsigned d) { __stcs((uint4*)p, make_uint4(a, b, c, d)); }
 PSD_DEV void psd_fence_system() { __threadfence_system(); }
+PSD_DEV void psd_fence_device() { __threadfence(); }
 // Bulk asynchronous copies shared -> global (the copy engine of the SM moves the bytes; the issuing
 // lane goes on).  Sizes are multiples of 16 bytes, both addresses 16-byte aligned.  One lane issues
 // the copies of a record as one bulk group and later waits until the engine has READ the sources.
@@ -1194,7 +1195,10 @@ PSD_DEV unsigned long long store_take(const StorePool& sp, unsigned long long ne
   if (sp.host_chunks == 0) return ~0ull;
   if (sp.ring.n_slots != 0 && need == 1) {
     const unsigned long long pos = psd_atomic_add_ull(sp.ring.head, 1ull);
-    // host chunks: ring positions from the bottom, zero-copy allocations from the top
+    // host chunks: ring positions from the bottom, zero-copy allocations from the top.  Each side bumps
+    // its own counter, fences, then reads the other's: of two allocations racing for the last chunks at
+    // least one sees the other and gives up, so they can never be handed the same chunk.
+    psd_fence_device();
     if (pos + 1ull + *(volatile unsigned long long*)sp.host_cursor > sp.host_chunks) return ~0ull;
     PSD_RING_WAIT(sp, pos);
     if (*sp.ring.free_tail <= pos) return ~0ull;
@@ -1204,6 +1208,7 @@ PSD_DEV unsigned long long store_take(const StorePool& sp, unsigned long long ne
   }
   const unsigned long long h = psd_atomic_add_ull(sp.host_cursor, need);
   if (sp.ring.n_slots == 0) return (h + need > sp.host_chunks) ? ~0ull : sp.n_chunks + h;
+  psd_fence_device();
   if (h + need + *(volatile unsigned long long*)sp.ring.head > sp.host_chunks) return ~0ull;
   return sp.n_chunks + sp.host_chunks - h - need;
 }

@@ -152,6 +152,7 @@ static inline unsigned long long psd_atomic_add_ull(unsigned long long* p, unsig
 }
 static inline int psd_atomic_add_int(int* p, int v) { int old = *p; *p = old + v; return old; }
 static inline void psd_fence_system() {}
+static inline void psd_fence_device() {}
 // bulk shared -> global copies of the record store: immediate copies here
 static inline void psd_bulk_s2g(void* dst, const void* src, unsigned bytes) { memcpy(dst, src, bytes); }
 static inline void psd_bulk_fence() {}
