@@ -1252,6 +1252,11 @@ int psd_device_count_impl() {
 extern "C" int psd_debug_block_ends(unsigned long long* out) {
   return cudaMemcpyFromSymbol(out, psd_blk_end, sizeof(unsigned long long) * 160) == cudaSuccess ? 0 : -1;
 }
+extern "C" int psd_debug_hist(unsigned long long* out256, int reset) {
+  if (cudaMemcpyFromSymbol(out256, psd_hist, sizeof(unsigned long long) * 256) != cudaSuccess) return -1;
+  if (reset) { unsigned long long z[256]; memset(z, 0, sizeof z); cudaMemcpyToSymbol(psd_hist, z, sizeof z); }
+  return 0;
+}
 extern "C" int psd_debug_read(unsigned long long* out, int n, int reset) {
   unsigned long long tmp[32];
   if (cudaMemcpyFromSymbol(tmp, psd_dbg, sizeof tmp) != cudaSuccess) return -1;

@@ -118,6 +118,8 @@ PSD_DEV void psd_bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::
 // PSD_TIMING (experiment builds only): per-section cycle counters, accumulated by lane 0 / lane 16
 #if defined(PSD_TIMING) && !defined(PSD_EMU)
 __device__ unsigned long long psd_dbg[32];
+__device__ unsigned long long psd_hist[4][64];   // phase durations per warp and row, 2,048-cycle buckets: [0] min_less/min_more, [1] min_env (<= 32 intervals), [2] min_env (> 32), [3] barrier-to-barrier row time
+#define PSD_HIST(slot, cyc) do { if ((threadIdx.x & 31u) == 0) { long long b_ = (long long)(cyc) >> 11; atomicAdd(&psd_hist[slot][b_ < 0 ? 0 : (b_ > 63 ? 63 : b_)], 1ull); } } while (0)
 #define PSD_T0(v) const long long v = clock64()
 #if defined(PSD_G32)
 #define PSD_T1(v, slot) do { if ((threadIdx.x & 31u) == 0) atomicAdd(&psd_dbg[slot], (unsigned long long)(clock64() - v)); } while (0)
@@ -127,6 +129,7 @@ __device__ unsigned long long psd_dbg[32];
 #else
 #define PSD_T0(v) do {} while (0)
 #define PSD_T1(v, slot) do {} while (0)
+#define PSD_HIST(slot, cyc) do {} while (0)
 #endif
 // PSD_EMU_STATS (emulator only, tools/emu_stats.py): histograms of the sizes that decide how many
 // 16- or 32-lane passes an operator takes -- the source of the waiting at the phase barriers
@@ -1450,6 +1453,9 @@ PSD_DEV void dp_run_queue(const WarpWs& ws_s, const WarpWs& ws_g, const DpQueue&
         tmp.n = in_g ? min_mono_op<false>(wg, grp ? upP : downP, tmp, dmin, t - 1, penalty / cw_done, grp)
                      : min_mono_op<true>(wg, grp ? upP : downP, tmp, dmin, t - 1, penalty / cw_done, grp);
         PSD_T1(ta, grp);
+#if defined(PSD_TIMING) && !defined(PSD_EMU)
+        PSD_HIST(0, clock64() - ta);
+#endif
       }
     }
     // block barrier 1 of 2; it doubles as the block's termination vote (a warp that just saw an empty
@@ -1471,6 +1477,9 @@ PSD_DEV void dp_run_queue(const WarpWs& ws_s, const WarpWs& ws_g, const DpQueue&
         n_out = in_g ? min_env_op<false>(wg, tmp, prev, otmp, oprev, dst, dmin, rs)
                      : min_env_op<true>(wg, tmp, prev, otmp, oprev, dst, dmin, rs);
         PSD_T1(tb, 2 + grp);
+#if defined(PSD_TIMING) && !defined(PSD_EMU)
+        PSD_HIST((tmp.n + prev.n + otmp.n + oprev.n > 36) ? 2 : 1, clock64() - tb);   // (pieces of the four lists: a proxy for > 32 overlap intervals)
+#endif
       }
       psd_syncwarp();   // both chains done; their lists are visible to the whole warp
     }
