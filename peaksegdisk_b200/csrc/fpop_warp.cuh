@@ -636,6 +636,8 @@ PSD_DEV PairOut pair_rule(const int cap, const PList f, const PList g, int i, in
   return o;
 }
 
+#define PSD_SRC_G 0x40000000   /* candidate source code: bit 30 = the piece comes from g, low bits = piece index */
+
 #if defined(PSD_G32)
 // ---- pair_rule split at the has_two_roots decision (latency kernel) ---------------------------------
 // pair_pre() finishes every interval that does not need the two Newton solves and otherwise returns
@@ -759,21 +761,65 @@ PSD_DEV PairOut pair_post(const PairJob jb, const double rs, const double rl) {
 
 // mailbox between a chain's main warp and its helper warp (shared memory)
 struct LatHelp {
-  int cmd;                 // 1: solve the posted jobs, 2: exit
+  int cmd;                 // 1: solve the posted jobs, 2: exit, 3: a wide pass (below)
   unsigned mask;           // lanes that posted a job
   double job[32][8];       // da, db, dc, hi, m, c2, dr of the interval's difference function
   double rl[32];           // the helper's answer: get_larger_root
+  // wide pass: a call with more than 32 overlap intervals left hands the second 32 to the helper,
+  // which applies the whole crossing rule to them while the main warp does the first 32
+  double* f_base; double* g_base; int nf, ng;     // the two functions of the call
+  int* ivl; double* cand_x; int* cand_s; int* flags;
+  int cap, ccap, K, base, T_in;                   // helper's intervals: [base + 32, base + 64) ∩ [0, K); candidates written so far
+  int tot_main, tot_help;                         // candidates of the main warp's / of the helper's 32 intervals
+  double dmin;
 };
 #define PSD_BAR_PAIR 1          /* named barriers of a latency block: the two main warps of the problem */
 #define psd_pair_sync() psd_bar_sync(PSD_BAR_PAIR, 64)
 #define PSD_BAR_JOBS(g) (2 + (g))   /* chain g: jobs posted (main arrives, helper waits) */
-#define PSD_BAR_DONE(g) (4 + (g))   /* chain g: larger roots ready (helper arrives, main waits) */
+#define PSD_BAR_DONE(g) (4 + (g))   /* chain g: helper's results ready (helper arrives, main waits) */
+#define PSD_BAR_MID(g) (6 + (g))    /* chain g, wide pass: the main warp's candidate count is known (main arrives, helper waits) */
 
 PSD_DEV void lat_helper_loop(LatHelp* H, int g) {
   const int lane = psd_lane();
   for (;;) {
     psd_bar_sync(PSD_BAR_JOBS(g), 64);
-    if (*(volatile int*)&H->cmd == 2) break;
+    const int cmd = *(volatile int*)&H->cmd;
+    if (cmd == 2) break;
+    if (cmd == 3) {
+      // the second 32 intervals of a wide pass: whole crossing rule, candidates appended after the main warp's
+      const int cap = H->cap, ccap = H->ccap;
+      PList F, G;
+      F.base = H->f_base; F.n = H->nf; G.base = H->g_base; G.n = H->ng;
+      const int q = H->base + 32 + lane;
+      const bool valid = q < H->K;
+      PairOut o; o.nc = 0; o.s0 = 0; o.x1 = 0; o.x2 = 0;
+      double lo = 0, hi = 0;
+      int i = 0, j = 0;
+      if (valid) {
+        const int code = H->ivl[q];
+        i = code & 0xffff; j = code >> 16;
+        o = pair_rule(cap, F, G, i, j, H->dmin, &lo, &hi);
+      }
+      const int nc = valid ? o.nc : 0;
+      int incl = nc;
+      for (int d = 1; d < 32; d <<= 1) { const int t = psd_g_shfl_up_i(incl, d); if (lane >= d) incl += t; }
+      const int tot = psd_g_shfl_i(incl, 31);
+      psd_bar_sync(PSD_BAR_MID(g), 64);       // the main warp's count is in the mailbox
+      const int off = H->T_in + *(volatile int*)&H->tot_main + incl - nc;
+      if (nc > 0) {
+        const int sf = i, sg = j | PSD_SRC_G;
+        const int c0 = o.s0 ? sg : sf, c1 = o.s0 ? sf : sg;
+        if (off + nc <= ccap) {
+          H->cand_s[off] = c0; H->cand_x[off] = (nc > 1) ? o.x1 : hi;
+          if (nc > 1) { H->cand_s[off + 1] = c1; H->cand_x[off + 1] = (nc > 2) ? o.x2 : hi; }
+          if (nc > 2) { H->cand_s[off + 2] = c0; H->cand_x[off + 2] = hi; }
+        } else *(volatile int*)H->flags = *(volatile int*)H->flags | PSD_FLAG_OVERFLOW;
+      }
+      if (lane == 0) H->tot_help = tot;
+      psd_syncwarp();
+      psd_bar_arrive(PSD_BAR_DONE(g), 64);
+      continue;
+    }
     const unsigned m = *(volatile unsigned*)&H->mask;
     if ((m >> lane) & 1u) {
       const double* J = H->job[lane];
@@ -784,7 +830,6 @@ PSD_DEV void lat_helper_loop(LatHelp* H, int g) {
 }
 #endif
 
-#define PSD_SRC_G 0x40000000
 
 
 // ---- set_to_min_env_of(f, g) followed by the row rescale -------------------------------------------
@@ -853,6 +898,41 @@ PSD_OP int min_env_op(const WarpWs ws, const PList f, const PList g, const PList
   LatHelp* const H = (LatHelp*)ws.help;
   const int chain = psd_warp_in_block() & 1;
   for (int base = 0; base < K; base += 32) {
+    if (H && K - base > 32) {
+      // WIDE pass: more than 32 intervals left (functions of more than ~16 pieces: high penalties,
+      // the worst-case sequences).  The helper warp takes intervals [base + 32, base + 64) with the whole
+      // crossing rule while this warp does [base, base + 32): 64 intervals per pass.
+      if (lane == 0) {
+        H->f_base = f.base; H->g_base = g.base; H->nf = nf; H->ng = ng; H->ivl = ivl; H->cand_x = cand_x; H->cand_s = cand_s;
+        H->flags = (int*)ws.flags; H->cap = cap; H->ccap = ccap; H->K = K; H->base = base; H->T_in = T; H->dmin = dmin; H->cmd = 3;
+      }
+      psd_syncwarp();
+      psd_bar_arrive(PSD_BAR_JOBS(chain), 64);
+      const int code = ivl[base + lane];
+      const int i = code & 0xffff, j = code >> 16;
+      double lo = 0, hi = 0;
+      const PairOut o = pair_rule(cap, f, g, i, j, dmin, &lo, &hi);
+      int incl = o.nc;
+      for (int d = 1; d < 32; d <<= 1) { const int t = psd_g_shfl_up_i(incl, d); if (lane >= d) incl += t; }
+      const int tot = psd_g_shfl_i(incl, 31);
+      if (lane == 0) H->tot_main = tot;
+      psd_syncwarp();
+      psd_bar_arrive(PSD_BAR_MID(chain), 64);
+      const int off = T + incl - o.nc;
+      if (o.nc > 0) {
+        const int sf = i, sg = j | PSD_SRC_G;
+        const int c0 = o.s0 ? sg : sf, c1 = o.s0 ? sf : sg;
+        if (off + o.nc <= ccap) {
+          cand_s[off] = c0; cand_x[off] = (o.nc > 1) ? o.x1 : hi;
+          if (o.nc > 1) { cand_s[off + 1] = c1; cand_x[off + 1] = (o.nc > 2) ? o.x2 : hi; }
+          if (o.nc > 2) { cand_s[off + 2] = c0; cand_x[off + 2] = hi; }
+        } else ws_raise(ws, PSD_FLAG_OVERFLOW);
+      }
+      psd_bar_sync(PSD_BAR_DONE(chain), 64);
+      T += tot + *(volatile int*)&H->tot_help;
+      base += 32;       // (the loop adds the other 32)
+      continue;
+    }
     const int q = base + lane;
     const bool valid = q < K;
     PairOut o; o.nc = 0; o.s0 = 0; o.x1 = 0; o.x2 = 0;
