@@ -5,7 +5,7 @@
 #include "fpop_warp.cuh"
 
 #define PSD_TAB_BYTES 4096          /* exp + log tables at the start of dynamic shared memory */
-#define PSD_LAT_SHARED_BYTES 4736   /* LatShared (incl. the helpers' mailboxes), between the tables and the workspace (latency kernel) */
+#define PSD_LAT_SHARED_BYTES 4992   /* LatShared (incl. the helpers' mailboxes), between the tables and the workspace (latency kernel) */
 #define PSD_LAT_WARPS 2             /* main warps of a latency block: the up chain and the down chain */
 #define PSD_LAT_THREADS 128         /* + two helper warps that solve the larger Newton roots */
 
