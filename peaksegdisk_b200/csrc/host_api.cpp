@@ -81,6 +81,14 @@ void parse_bedgraph(const char* path, Parsed& P) {
   if (!f) { P.status = PSD_ERR_UNABLE_TO_OPEN_BEDGRAPH; return; }
   std::vector<char> buf;
   {
+    // regular files: one read of the whole size; anything else (pipes, /proc): 64 KB at a time
+    long size = -1;
+    if (fseek(f, 0, SEEK_END) == 0) { size = ftell(f); if (fseek(f, 0, SEEK_SET) != 0) size = -1; }
+    if (size > 0) {
+      buf.resize((size_t)size);
+      const size_t got = fread(buf.data(), 1, (size_t)size, f);
+      buf.resize(got);
+    }
     char tmp[1 << 16];
     size_t n;
     while ((n = fread(tmp, 1, sizeof tmp, f)) > 0) buf.insert(buf.end(), tmp, tmp + n);
@@ -92,27 +100,29 @@ void parse_bedgraph(const char* path, Parsed& P) {
   const char* const fend = p + buf.size();
   int line_i = 0, prev_end = -1;
   const char* chrom_b = nullptr; const char* chrom_e = nullptr;
+  {   // typical rows are 20-30 bytes: one allocation instead of a dozen doublings
+    const size_t guess = buf.size() / 16 + 16;
+    P.rows->chrom_start.reserve(guess); P.rows->chrom_end.reserve(guess); P.rows->coverage.reserve(guess);
+  }
   while (p < fend) {
     const char* nl = (const char*)memchr(p, '\n', (size_t)(fend - p));
-    const char* lend = nl ? nl : fend;
-    const char* nul = (const char*)memchr(p, '\0', (size_t)(lend - p));
-    const char* e = nul ? nul : lend;
+    const char* const e = nl ? nl : fend;        // sscanf works on a C string: a NUL inside the line ends it (checked below)
     line_i++;
     const char* q = p;
     int items = 0;
     int cs = 0, ce = 0, cv = 0;
     while (q < e && is_ws((unsigned char)*q)) q++;
-    if (q >= e) items = -1;   // sscanf returns EOF on an empty line
+    if (q >= e || *q == '\0') items = -1;   // sscanf returns EOF on an empty line
     else {
       chrom_b = q;
-      while (q < e && !is_ws((unsigned char)*q)) q++;
+      while (q < e && *q != '\0' && !is_ws((unsigned char)*q)) q++;
       chrom_e = q;
       items = 1;
       if (scan_int(q, e, &cs)) { items = 2; if (scan_int(q, e, &ce)) { items = 3; if (scan_int(q, e, &cv)) items = 4; } }
     }
     if (items < 4) { P.status = PSD_ERR_NOT_ENOUGH_COLUMNS; P.bad_items = items; P.bad_line = line_i; return; }
     while (q < e && is_ws((unsigned char)*q)) q++;
-    if (q < e) { P.status = PSD_ERR_NON_INTEGER_DATA; return; }   // "%d%s": trailing text after the 4th column
+    if (q < e && *q != '\0') { P.status = PSD_ERR_NON_INTEGER_DATA; return; }   // "%d%s": trailing text after the 4th column
     if (line_i > 1 && cs != prev_end) { P.status = PSD_ERR_INCONSISTENT_CHROMSTART_CHROMEND; return; }
     prev_end = ce;
     P.rows->chrom_start.push_back(cs); P.rows->chrom_end.push_back(ce); P.rows->coverage.push_back(cv);
@@ -124,23 +134,37 @@ void parse_bedgraph(const char* path, Parsed& P) {
 }
 
 // Pass-1 totals of a row set: weights, sum of weights, sum of weight x coverage, log range.
+// The reference takes log(coverage) of every row and keeps the smallest and the largest
+// (src/PeakSegFPOPLog.cpp:190-197); log is monotone on the integers, so these are the logs of the
+// smallest and the largest coverage: two log calls instead of one per row.
 void finish_rows(RowData& r) {
   const int64_t n = (int64_t)r.coverage.size();
   r.weight.resize(n);
-  double W = 0, SWZ = 0, xmin = INFINITY, xmax = -INFINITY;
-  int32_t last_cov = 0; double last_log = 0; bool have = false;
+  double W = 0, SWZ = 0;
+  int32_t zmin = n ? r.coverage[0] : 0, zmax = zmin;
   for (int64_t t = 0; t < n; t++) {
     const int32_t wi = r.chrom_end[t] - r.chrom_start[t];
     r.weight[t] = wi;
     const double w = (double)wi;
-    W += w;
-    SWZ += w * r.coverage[t];
     const int32_t z = r.coverage[t];
-    if (!have || z != last_cov) { last_log = hlog((double)z); last_cov = z; have = true; }
-    if (last_log < xmin) xmin = last_log;
-    if (xmax < last_log) xmax = last_log;
+    W += w;
+    SWZ += w * z;
+    zmin = z < zmin ? z : zmin; zmax = z > zmax ? z : zmax;
   }
-  r.bases = W; r.sum_wz = SWZ; r.dmin = xmin; r.dmax = xmax;
+  r.bases = W; r.sum_wz = SWZ;
+  if (zmin < 0) {
+    // negative coverage (the reference accepts it): log gives NaN, and NaN never replaces the running
+    // min / max in the reference's comparisons -- keep its exact row-by-row semantics for this corner
+    double xmin = INFINITY, xmax = -INFINITY;
+    for (int64_t t = 0; t < n; t++) {
+      const double lx = hlog((double)r.coverage[t]);
+      if (lx < xmin) xmin = lx;
+      if (xmax < lx) xmax = lx;
+    }
+    r.dmin = xmin; r.dmax = xmax;
+  } else {
+    r.dmin = n ? hlog((double)zmin) : INFINITY; r.dmax = n ? hlog((double)zmax) : -INFINITY;
+  }
 }
 
 // Fills the derived fields of a problem from its (finished) rows.
