@@ -438,11 +438,15 @@ int psd_plan_upload_impl(psd_plan* p, void* stream_v) {
       const HostProblem& hp = p->probs[id];
       if (hp.from_counts) memcpy(p->p_raw + hp.raw_off, hp.counts.data(), sizeof(int32_t) * hp.n_pos);
     }
-    for (const auto& rs : p->row_sets) {
-      // row sets are laid out first and in order, so the device offset equals the staging offset
+    // row sets are laid out first and in order, so the device offset equals the staging offset; a big
+    // batch is packed on all host cores (240 MB for config 2)
+    auto pack_one = [&](int k) {
+      const auto& rs = p->row_sets[k];
       memcpy(p->p_weight + rs.second, rs.first->weight.data(), sizeof(int32_t) * rs.first->weight.size());
       memcpy(p->p_cov + rs.second, rs.first->coverage.data(), sizeof(int32_t) * rs.first->coverage.size());
-    }
+    };
+    if (p->rows_plain > (1 << 22)) parallel_for((int)p->row_sets.size(), pack_one);
+    else for (int k = 0; k < (int)p->row_sets.size(); k++) pack_one(k);
     p->packed = true;
   }
   tr.mark("upload: pack rows");

@@ -248,18 +248,6 @@ struct FileJob {
   int dev_slot = 0;          // which of the batch's plans (one per GPU in use) owns this problem
 };
 
-// Runs fn(i) for i in [0,n) on up to hardware_concurrency host threads.
-template <class F> void parallel_for(int n, F fn) {
-  int nt = (int)std::thread::hardware_concurrency();
-  if (nt < 1) nt = 1;
-  if (nt > n) nt = n;
-  if (nt <= 1) { for (int i = 0; i < n; i++) fn(i); return; }
-  std::atomic<int> next(0);
-  std::vector<std::thread> pool;
-  for (int t = 0; t < nt; t++) pool.emplace_back([&]() { for (;;) { const int i = next.fetch_add(1); if (i >= n) break; fn(i); } });
-  for (auto& th : pool) th.join();
-}
-
 // creates / truncates a file and closes it again (outputs exist, empty, before the solve)
 bool touch(const std::string& path) {
   FILE* f = fopen(path.c_str(), "wb");

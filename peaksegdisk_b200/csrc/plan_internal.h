@@ -5,7 +5,9 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <atomic>
 #include <memory>
+#include <thread>
 #include <string>
 #include <vector>
 #include "../../include/peaksegdisk_b200.h"
@@ -60,6 +62,18 @@ struct Trace {
     t = n;
   }
 };
+
+// Runs fn(i) for i in [0,n) on up to hardware_concurrency host threads.
+template <class F> void parallel_for(int n, F fn) {
+  int nt = (int)std::thread::hardware_concurrency();
+  if (nt < 1) nt = 1;
+  if (nt > n) nt = n;
+  if (nt <= 1) { for (int i = 0; i < n; i++) fn(i); return; }
+  std::atomic<int> next(0);
+  std::vector<std::thread> pool;
+  for (int t = 0; t < nt; t++) pool.emplace_back([&]() { for (;;) { const int i = next.fetch_add(1); if (i >= n) break; fn(i); } });
+  for (auto& th : pool) th.join();
+}
 
 struct psd_plan;
 psd_plan* psd_plan_create_impl(int device);
