@@ -1,14 +1,19 @@
 // fpop_warp.cuh -- the PeakSegFPOP dynamic program as warp-cooperative device code (sm_100a).
 //
-// One warp owns one problem (one bedGraph x one penalty).  The two cost functions of the
-// up-down-constrained optimal-partitioning DP are piecewise Poisson-loss functions of the
-// log-mean; each is a structure-of-arrays piece list in shared memory (the warp's global-memory
-// workspace when a function outgrows it), one lane per piece.  Per bedGraph row the warp runs
-//     up_t   = rescale( min_env( min_less(down_{t-1}) + penalty/W_{t-1}, up_{t-1} ) )    lanes  0-15
-//     down_t = rescale( min_env( min_more(up_{t-1}),                     down_{t-1} ) )  lanes 16-31
-// (the two recursions are independent given row t-1, so the two half-warps run them side by side
-// through the same code) and appends the breakpoints/back-pointers of both functions to the
-// cost-function store (HBM, overflowing into mapped pinned host memory).
+// The two cost functions of the up-down-constrained optimal-partitioning DP are piecewise
+// Poisson-loss functions of the log-mean; each is a structure-of-arrays piece list in shared memory
+// (a global-memory workspace when a function outgrows it), one lane per piece.  Per bedGraph row
+//     up_t   = rescale( min_env( min_less(down_{t-1}) + penalty/W_{t-1}, up_{t-1} ) )
+//     down_t = rescale( min_env( min_more(up_{t-1}),                     down_{t-1} ) )
+// and the breakpoints/back-pointers of both functions are appended to the cost-function store
+// (HBM; spilling through an HBM ring and cudaMemcpyAsync to pinned host memory).  The two
+// recursions are independent given row t-1.  This source is compiled TWICE:
+//   * fpop_gpu.cu (operator group = 16 lanes): the THROUGHPUT kernel.  One warp owns one problem, its two
+//     half-warps run the two recursions side by side through the same code; 14 warps per SM march in
+//     phase lock (dp_run_queue).
+//   * fpop_lat.cu (-DPSD_G32, operator group = 32 lanes): the LATENCY kernel.  One block owns one
+//     problem, one warp per recursion, two helper warps for the second Newton solve and for the
+//     second half of wide passes (dp_run_latency, lat_helper_loop).
 //
 // Reference behaviour being reproduced (file:line into tdhock/PeakSegDisk):
 //   piece algebra, Newton roots     src/funPieceListLog.cpp:29-234
@@ -18,8 +23,8 @@
 //                                   src/funPieceListLog.cpp:832-1285  -> min_env_op (+ pair_rule)
 //   add / multiply / set_prev_seg_end  :618-641  -> fused into the operators' output writes
 //   Minimize / findMean             :689-712 / :643-653  -> best_piece / backtrack_problem
-//   DP loop, decode                 src/PeakSegFPOPLog.cpp:258-442  -> dp_run_queue / backtrack_problem
-//   per-row store                   src/PeakSegFPOPLog.cpp:12-141   -> StoreWriter (HBM chunk arena)
+//   DP loop, decode                 src/PeakSegFPOPLog.cpp:258-442  -> dp_run_queue, dp_run_latency / backtrack_problem
+//   per-row store                   src/PeakSegFPOPLog.cpp:12-141   -> StorePool, StoreRing, store_write (HBM chunk arena)
 // Every floating-point expression keeps the reference's operand order and rounding (build with
 // -fmad=false); exp/log are psd_math.h, bit-identical to the libm the reference links.
 //
@@ -34,7 +39,8 @@
 //     a scan and adjacent equal pieces are merged by a run-head pass that reproduces push_piece.
 //
 // This header is compiled by nvcc for the product and, unmodified, by g++ against
-// tests/emu/warp_emu.h (PSD_EMU) where 32 fibers stand in for the lanes -- a test tool only.
+// tests/emu/warp_emu.h (PSD_EMU) where fibers stand in for the lanes of one or several warps -- a test
+// tool only.
 // Experiment switches (never set in the product build): PSD_TIMING (cycle counters), PSD_SPEC,
 // PSD_RETURN_NUM/DEN, PSD_INLINE_MATH / PSD_INLINE_EXP / PSD_INLINE_LOG, PSD_NOINLINE_ROOTS,
 // PSD_NOINLINE_OPS, PSD_NO_SHARED_HINT, PSD_NO_BULK_STORE;
@@ -92,7 +98,6 @@ PSD_DEV int psd_popc(unsigned m) { return __popc(m); }
 PSD_DEV unsigned long long psd_atomic_add_ull(unsigned long long* p, unsigned long long v) { return atomicAdd(p, v); }
 PSD_DEV int psd_atomic_add_int(int* p, int v) { return atomicAdd(p, v); }
 // the cost-function store is written once and read (sparsely) once: evict-first streaming stores
-PSD_DEV void psd_st_cs_d2(double* p, double x, double y) { __stcs((double2*)p, make_double2(x, y)); }
 PSD_DEV void psd_st_cs_i(int* p, int v) { __stcs(p, v); }
 PSD_DEV void psd_st_cs_u64(unsigned long long* p, unsigned long long v) { __stcs(p, v); }
 PSD_DEV void psd_st_cs_u4(unsigned* p, unsigned a, unsigned b, unsigned c, unsigned d) { __stcs((uint4*)p, make_uint4(a, b, c, d)); }
@@ -1223,7 +1228,7 @@ PSD_DEVNI void best_piece(const WarpWs ws, const PList f, double dmin, double* b
 //     the chunk it publishes (host chunk, slot) in a pinned done-queue, a host thread copies the slot
 //     to its place in the host region with cudaMemcpyAsync on a side stream and hands the slot back
 //     through a pinned free-queue.  The DP's stores stay HBM stores; PCIe sees 64 KB DMA transfers.
-//   * zero-copy (ring off, or records larger than a chunk): the 128-bit stores go through the mapping.
+//   * zero-copy (ring off, or records larger than a chunk): the lanes' stores go through the mapping.
 struct StoreRing {
   unsigned char* base;                      // HBM ring: n_slots slots of chunk_bytes (n_slots = 0: ring off)
   unsigned long long n_slots;

@@ -166,7 +166,6 @@ struct StorePool;
 extern void (*psd_emu_ring_drain)(const StorePool* sp);
 #define PSD_RING_WAIT(sp, pos) do { if (*(sp).ring.free_tail <= (pos)) psd_emu_ring_drain(&(sp)); if (*(sp).ring.free_tail <= (pos)) { fprintf(stderr, "warp_emu: ring drain freed nothing\n"); abort(); } } while (0)
 // streaming (evict-first) stores of the cost-function store: plain stores here
-static inline void psd_st_cs_d2(double* p, double x, double y) { p[0] = x; p[1] = y; }
 static inline void psd_st_cs_i(int* p, int v) { *p = v; }
 static inline void psd_st_cs_u64(unsigned long long* p, unsigned long long v) { *p = v; }
 static inline void psd_st_cs_u4(unsigned* p, unsigned a, unsigned b, unsigned c, unsigned d) { p[0] = a; p[1] = b; p[2] = c; p[3] = d; }
